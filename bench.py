@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- task placements/sec on BASELINE.json's headline configuration.
+
+Workload (config.workload): cfg3-oneoff = 1M pending one-off tasks x 100k nodes,
+8 constraint expressions (node.labels / role / platform) per task, PlatformFilter
+on half the services, spread ranking -- the reference's own
+BenchmarkScheduler100kNodes1MTasks shape (scheduler_test.go:3358,3378-3468).
+
+A "step" is one pass of the hot path (one Scheduler.tick group loop) over that
+batch of synthetic pending tasks:
+  value : placements/s with the node mirror and the tick descriptors already in
+          HBM (pe_tick_run), device time from CUDA events on the engine stream
+  e2e   : the same through pe_schedule with HOST buffers (pinned), H2D of the
+          descriptors and D2H of the placements inside the timed region
+  roofline : the scan kernel's algorithmic bytes / its CUDA-event time vs the
+          measured HBM peak
+  cpu_baseline : the CPU oracle (oracle/flat_oracle.cpp, 1 thread like the
+          reference's single goroutine) on a bounded sample of the same workload
+`--impl reference` times that CPU restatement alone (the reference is Go and no
+Go toolchain exists on the box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "task placements/sec at 1M tasks x 100k nodes"
+UNIT = "placements/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_copy(a: np.ndarray) -> np.ndarray:
+    """Copy into page-locked host memory (torch is only the allocator here)."""
+    import torch
+    t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+    v = t.numpy().view(a.dtype).reshape(a.shape)
+    v[...] = a
+    _KEEP.append(t)
+    return v
+
+
+_KEEP = []
+
+
+def make_workload(name: str, n_tasks: int, n_nodes: int):
+    from swarmkit_b200 import workloads as W
+    base, _, mode = name.partition("-")
+    kw = {}
+    if base != "cfg1":
+        kw = {"n_nodes": n_nodes, "n_tasks": n_tasks}
+    return W.by_name(name, **kw)
+
+
+def cpu_sample(w, sample_tasks: int):
+    """Time the CPU oracle on the first `sample_tasks` groups of the workload (full node table)."""
+    from tests.oracle_lib import OracleEngine
+    o = OracleEngine(node_capacity=w.n_nodes)
+    o.node_upsert(w.nodes)
+    o.set_node_count(w.n_nodes)
+    sub = w.tick.slice_groups(0, min(sample_tasks, w.tick.n_groups))
+    t0 = time.perf_counter()
+    out, _ = o.schedule(sub)
+    dt = time.perf_counter() - t0
+    placed = int((out != 0xFFFFFFFF).sum())
+    return placed, sub.n_tasks, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    w = make_workload(args.workload, args.tasks, args.nodes)
+    sample = args.cpu_sample
+    vals = []
+    for i in range(args.warmup + args.steps):
+        placed, n, dt = cpu_sample(w, sample)
+        if i >= args.warmup:
+            vals.append((placed, dt))
+    placed = sum(p for p, _ in vals)
+    tt = sum(d for _, d in vals)
+    v = placed / tt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tt / max(len(vals), 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64/u32", "data": "synthetic",
+        "config": {"workload": args.workload, "tasks": w.tick.n_tasks, "nodes": w.n_nodes},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"first {min(sample, w.tick.n_groups)} tasks of the workload against all {w.n_nodes} nodes, "
+                                   "oracle/flat_oracle.cpp single thread (the reference scheduler is one goroutine); "
+                                   "Go reference not runnable: no go toolchain"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3-oneoff")
+    ap.add_argument("--tasks", type=int, default=1_000_000)
+    ap.add_argument("--nodes", type=int, default=100_000)
+    ap.add_argument("--cpu-sample", type=int, default=2000, help="tasks in the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--max-batch", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from swarmkit_b200 import PlacementEngine
+
+    w = make_workload(args.workload, args.tasks, args.nodes)
+    n_tasks = w.tick.n_tasks
+    eng = PlacementEngine(node_capacity=w.n_nodes, device=local_rank, max_batch=args.max_batch)
+    # pinned host copies of what crosses PCIe each step
+    w.tick.groups = pinned_copy(w.tick.groups)
+    w.tick.task_flags = pinned_copy(w.tick.task_flags)
+
+    def reset_state():
+        eng.node_upsert(w.nodes)   # rewrites every row and zeroes every per-service counter column
+        eng.set_node_count(w.n_nodes)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: W warm-up + K timed steps
+    for _ in range(args.warmup):
+        reset_state()
+        eng.tick_upload(w.tick)
+        eng.tick_run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.stats_reset()
+    dev_ms, wall_ms, placed_total = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        reset_state()
+        eng.tick_upload(w.tick)
+        s0 = eng.stats()
+        barrier()
+        t0 = time.perf_counter()
+        eng.tick_run()
+        barrier()
+        wall_ms += 1e3 * (time.perf_counter() - t0)
+        s1 = eng.stats()
+        dev_ms += s1["run_ms"] - s0["run_ms"]
+        placed_total += s1["placements"] - s0["placements"]
+    st = eng.stats()
+    out_node, _ = eng.tick_download()
+    clocks = sampler.stop()
+
+    # ---- end-to-end arm: host buffers in, host buffers out
+    e2e_ms, e2e_placed = 0.0, 0
+    s_before = eng.stats()
+    for i in range(1 + args.steps):
+        reset_state()
+        barrier()
+        t0 = time.perf_counter()
+        on, _ = eng.schedule(w.tick)
+        barrier()
+        if i > 0:
+            e2e_ms += 1e3 * (time.perf_counter() - t0)
+            e2e_placed += int((on != 0xFFFFFFFF).sum())
+    s_after = eng.stats()
+    h2d = (s_after["h2d_bytes"] - s_before["h2d_bytes"]) // (1 + args.steps)
+    d2h = (s_after["d2h_bytes"] - s_before["d2h_bytes"]) // (1 + args.steps)
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([placed_total, e2e_placed], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms, e2e_ms = t.tolist()
+    placed_all, e2e_all = cnt.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        scan_s = st["scan_ms"] / 1e3
+        achieved = st["scan_bytes"] / scan_s / 1e9 if scan_s > 0 else 0.0
+        value = placed_all / (dev_ms / 1e3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64/u32", "data": "synthetic",
+            "config": {"workload": args.workload, "tasks": n_tasks, "nodes": w.n_nodes, "mode": "one-off (k=1 groups)",
+                       "parallelism": "replicas" if world > 1 else "1 gpu",
+                       "l2": "state reset between steps rewrites every node column and 400 MB of service counters (> L2); "
+                             "inside a step the 4.4 MB node table is deliberately L2-resident"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "placed_per_step": placed_all / args.steps / world,
+            "evals_per_s_per_gpu": st["evals"] / scan_s if scan_s > 0 else None,
+            "split_ms_per_step": {"scan": st["scan_ms"] / args.steps, "sequencer": st["sequencer_ms"] / args.steps},
+            "paths": {"fast": st["fast_path"], "slow": st["slow_path"]},
+            "e2e": {"value": e2e_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(st["kernel_launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "kernel k_scan; algorithmic bytes = sum over (task,node) evals of the columns that eval reads "
+                                 "(meta 4 + total 4 + service count 4 + 4 per distinct constraint column [+16 cpu/mem, ...]); "
+                                 "streaming-equivalent: node tiles are re-used by 16 tasks per CTA from shared memory and are "
+                                 "L2-resident, so DRAM traffic is far below this figure (SURVEY 8d caveat)",
+                         "bytes_per_launch": st["scan_bytes"] / max(st["scan_launches"], 1),
+                         "ms_per_launch": st["scan_ms"] / max(st["scan_launches"], 1)},
+        }
+        if not args.no_cpu:
+            placed, n, dt = cpu_sample(w, args.cpu_sample)
+            line["cpu_baseline"] = {"value": placed / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"first {n} tasks of the same workload against all {w.n_nodes} nodes "
+                                              f"({n * w.n_nodes:.3g} (task,node) visits, {dt:.1f} s), oracle/flat_oracle.cpp, 1 thread"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

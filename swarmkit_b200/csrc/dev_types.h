@@ -1,0 +1,59 @@
+// dev_types.h -- device-side layout of the node mirror and of one tick.
+//
+// HBM layout (DESIGN.md "Data layout"): the node mirror is struct-of-arrays,
+// one contiguous column per field, every column padded to a multiple of
+// PE_ROW_PAD rows so that any node tile is a 16-byte aligned contiguous slice
+// of each column (what cp.async.bulk needs).  Columns trace to NodeInfo fields
+// (manager/scheduler/nodeinfo.go:28-44) exactly as SURVEY.md Appendix B lists.
+#pragma once
+#include <stdint.h>
+#include "../../include/placement_engine.h"
+
+#define PE_ROW_PAD 2048u          // row padding = largest scan tile
+#define PE_META_FLAGS_MASK 0xFFu  // meta = flags | os_id << 8 | arch_id << 16
+#define PE_PREF_NONE 0xFFFFFFFFFFFFFFFFull
+
+// Status bits the kernels raise in DevStatus::error.
+#define PE_DEV_ERR_SVC_OVERFLOW 0x1u  // a per-service count reached 2^24
+
+struct DevTable {
+    uint32_t n_nodes;   // rows covered by scans (N)
+    uint32_t n_attr, n_gen, n_svc, n_portw, n_plugw;
+    uint32_t *meta;     // flags | os << 8 | arch << 16
+    int64_t *cpu;       // AvailableResources.NanoCPUs
+    int64_t *mem;       // AvailableResources.MemoryBytes
+    uint32_t *total;    // ActiveTasksCount
+    uint4 *ip;          // 16-byte address
+    uint32_t **attr;    // [n_attr]  folded value ids per attribute column
+    int64_t **gen;      // [n_gen]   PE_GEN_ENCODE cells
+    uint32_t **svc;     // [n_svc]   ActiveTasksCountByService, dense per service
+    uint32_t **ports;   // [n_portw] usedHostPorts bit words
+    uint32_t **plug;    // [n_plugw] plugin-present bit words
+};
+
+struct TickDev {
+    const pe_group *groups;
+    const uint8_t *task_flags;
+    const pe_generic_want *gens;
+    const pe_constraint *cons;
+    const pe_ip_constraint *ips;
+    const pe_platform *plats;
+    const uint32_t *ports;
+    const uint32_t *plugs;
+    const pe_node_fail *fails;
+    uint32_t *out_node;  // [n_tasks]
+    uint32_t *out_fail;  // [n_groups * 8]
+};
+
+// Per-task result of the batched k=1 scan.
+struct ScanResult {
+    unsigned long long c0;  // smallest (f5, svc, total) prefix among feasible nodes; PE_PREF_NONE if none
+    uint32_t w0;            // first valid word of the class bitmap (earlier words are stale)
+    uint32_t n_class;       // nodes in the class
+};
+
+struct DevCounters {
+    unsigned long long fast_path, slow_path, placements, evals_generic;
+    uint32_t error;
+    uint32_t pad;
+};

@@ -1,0 +1,808 @@
+// engine.cu -- host side of the B200 placement engine and its C ABI
+// (include/placement_engine.h).  Owns the device mirror of the scheduler's
+// nodeSet (manager/scheduler/nodeset.go:13-48, nodeinfo.go:28-44) and drives
+// the kernels that replace the body of Scheduler.tick's group loop
+// (manager/scheduler/scheduler.go:464-469) and taskFitNode (:646-690).
+//
+// There is no CPU fallback: without a CUDA device pe_create fails with
+// PE_ERR_NO_DEVICE and nothing else can be called.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernel_misc.cuh"
+#include "kernel_scan.cuh"
+#include "kernel_sequencer.cuh"
+
+using namespace pe;
+
+namespace {
+
+std::string g_create_err;
+
+#define CU(expr)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            char b_[512];                                                                      \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            this->err = b_;                                                                    \
+            return PE_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+struct EvPair { cudaEvent_t a, b; int kind; };
+
+}  // namespace
+
+struct pe_engine {
+    std::string err;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    uint32_t cfg_flags = 0, max_batch = 0;
+
+    // ---- node mirror
+    uint32_t cap = 0, n_nodes = 0;
+    uint32_t *meta = nullptr;
+    int64_t *cpu = nullptr, *mem = nullptr;
+    uint32_t *total = nullptr;
+    uint4 *ip = nullptr;
+    std::vector<uint32_t *> attr, svc, ports, plug;
+    std::vector<int64_t *> gen;
+    void **d_tab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // attr, gen, svc, ports, plug
+    size_t tab_cap[5] = {0, 0, 0, 0, 0};
+    bool tabs_dirty = true;
+
+    // ---- staged tick
+    void *tick_buf = nullptr; size_t tick_cap = 0;
+    TickDev K{};
+    std::vector<pe_group> groups;
+    std::vector<pe_constraint> h_cons;
+    std::vector<pe_generic_want> h_gens;
+    std::vector<uint32_t> h_ports, h_plugs;
+    uint32_t n_groups = 0, n_tasks = 0;
+    uint32_t *d_out_node = nullptr, *d_out_fail = nullptr; size_t out_node_cap = 0, out_fail_cap = 0;
+
+    // ---- scratch
+    uint32_t scratch_cap = 0, st_cap = 0;
+    uint8_t *ff8 = nullptr; unsigned long long *pref64 = nullptr;
+    CandKey *cand_g = nullptr;
+    int64_t *st_cpu_g = nullptr, *st_mem_g = nullptr, *st_gen_g = nullptr;
+    uint32_t *st_svc_g = nullptr, *st_tot_g = nullptr, *st_placed_g = nullptr;
+    uint8_t *st_flags_g = nullptr;
+    uint32_t *touched_g = nullptr;
+    uint32_t *E = nullptr; size_t E_words = 0;
+    ScanResult *scan_out = nullptr; uint32_t scan_out_cap = 0;
+    DevCounters *d_ctr = nullptr;
+    void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
+
+    pe_stats stats{};
+    std::vector<EvPair> ev_pool; size_t ev_used = 0;
+    bool timing = true;
+
+    // =====================================================================
+    int32_t init(const pe_config *cfg) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count == 0") +
+                  "); the placement engine has no CPU fallback";
+            return PE_ERR_NO_DEVICE;
+        }
+        if (cfg->device >= 0) { device = cfg->device; CU(cudaSetDevice(device)); }
+        else CU(cudaGetDevice(&device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        num_sms = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        cfg_flags = cfg->flags;
+        max_batch = cfg->max_batch;
+        CU(cudaMalloc(&d_ctr, sizeof(DevCounters)));
+        CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
+        CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(16384)));
+        CU(cudaFuncSetAttribute(k_scan<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        int32_t rc = ensure_cap(cfg->node_capacity ? cfg->node_capacity : 1);
+        if (rc) return rc;
+        // the five fixed attribute columns always exist
+        for (uint32_t c = 0; c < PE_ATTR_FIRST_LABEL; c++) { rc = ensure_col(attr, c, 4); if (rc) return rc; }
+        return PE_OK;
+    }
+
+    void destroy() {
+        if (stream) cudaStreamSynchronize(stream);
+        auto fr = [](void *p) { if (p) cudaFree(p); };
+        fr(meta); fr(cpu); fr(mem); fr(total); fr(ip);
+        for (auto p : attr) fr(p);
+        for (auto p : svc) fr(p);
+        for (auto p : ports) fr(p);
+        for (auto p : plug) fr(p);
+        for (auto p : gen) fr(p);
+        for (auto p : d_tab) fr(p);
+        fr(tick_buf); fr(d_out_node); fr(d_out_fail); fr(ff8); fr(pref64); fr(cand_g); fr(st_cpu_g); fr(st_mem_g); fr(st_gen_g);
+        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(scan_out); fr(d_ctr); fr(up_buf);
+        for (auto &p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    // ---- columns ---------------------------------------------------------
+    template <class T> int32_t regrow(T *&p, size_t elem, uint32_t old_cap, uint32_t new_cap) {
+        void *q = nullptr;
+        CU(cudaMalloc(&q, (size_t)new_cap * elem));
+        CU(cudaMemsetAsync(q, 0, (size_t)new_cap * elem, stream));
+        if (p && old_cap) CU(cudaMemcpyAsync(q, p, (size_t)old_cap * elem, cudaMemcpyDeviceToDevice, stream));
+        if (p) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(p)); }
+        p = reinterpret_cast<T *>(q);
+        return PE_OK;
+    }
+
+    int32_t ensure_cap(uint32_t rows) {
+        if (rows <= cap) return PE_OK;
+        uint32_t nc = round_up(std::max(rows, cap + cap / 2), PE_ROW_PAD);
+        int32_t rc;
+        if ((rc = regrow(meta, 4, cap, nc))) return rc;
+        if ((rc = regrow(cpu, 8, cap, nc))) return rc;
+        if ((rc = regrow(mem, 8, cap, nc))) return rc;
+        if ((rc = regrow(total, 4, cap, nc))) return rc;
+        if ((rc = regrow(ip, 16, cap, nc))) return rc;
+        for (auto &p : attr) if (p && (rc = regrow(p, 4, cap, nc))) return rc;
+        for (auto &p : svc) if (p && (rc = regrow(p, 4, cap, nc))) return rc;
+        for (auto &p : ports) if (p && (rc = regrow(p, 4, cap, nc))) return rc;
+        for (auto &p : plug) if (p && (rc = regrow(p, 4, cap, nc))) return rc;
+        for (auto &p : gen) if (p && (rc = regrow(p, 8, cap, nc))) return rc;
+        cap = nc;
+        tabs_dirty = true;
+        return PE_OK;
+    }
+
+    template <class T> int32_t ensure_col(std::vector<T *> &tab, uint32_t idx, size_t elem) {
+        if (idx >= (1u << 20)) { err = "column index too large"; return PE_ERR_INVALID; }
+        if (idx >= tab.size()) { tab.resize(idx + 1, nullptr); tabs_dirty = true; }
+        if (!tab[idx]) {
+            void *q = nullptr;
+            CU(cudaMalloc(&q, (size_t)cap * elem));
+            CU(cudaMemsetAsync(q, 0, (size_t)cap * elem, stream));
+            tab[idx] = reinterpret_cast<T *>(q);
+            tabs_dirty = true;
+        }
+        return PE_OK;
+    }
+
+    template <class T> int32_t sync_tab(int which, std::vector<T *> &tab) {
+        size_t n = std::max<size_t>(tab.size(), 1);
+        if (n > tab_cap[which]) {
+            if (d_tab[which]) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(d_tab[which])); }
+            size_t nc = std::max<size_t>(64, n * 2);
+            CU(cudaMalloc(&d_tab[which], nc * sizeof(void *)));
+            tab_cap[which] = nc;
+        }
+        if (!tab.empty()) CU(cudaMemcpyAsync(d_tab[which], tab.data(), tab.size() * sizeof(void *), cudaMemcpyHostToDevice, stream));
+        return PE_OK;
+    }
+
+    int32_t sync_tabs() {
+        if (!tabs_dirty) return PE_OK;
+        int32_t rc;
+        // pageable host vectors: the copies are staged before the call returns
+        if ((rc = sync_tab(0, attr))) return rc;
+        if ((rc = sync_tab(1, gen))) return rc;
+        if ((rc = sync_tab(2, svc))) return rc;
+        if ((rc = sync_tab(3, ports))) return rc;
+        if ((rc = sync_tab(4, plug))) return rc;
+        CU(cudaStreamSynchronize(stream));
+        tabs_dirty = false;
+        return PE_OK;
+    }
+
+    DevTable table() const {
+        DevTable T;
+        T.n_nodes = n_nodes;
+        T.n_attr = (uint32_t)attr.size(); T.n_gen = (uint32_t)gen.size(); T.n_svc = (uint32_t)svc.size();
+        T.n_portw = (uint32_t)ports.size(); T.n_plugw = (uint32_t)plug.size();
+        T.meta = meta; T.cpu = cpu; T.mem = mem; T.total = total; T.ip = ip;
+        T.attr = reinterpret_cast<uint32_t **>(d_tab[0]);
+        T.gen = reinterpret_cast<int64_t **>(d_tab[1]);
+        T.svc = reinterpret_cast<uint32_t **>(d_tab[2]);
+        T.ports = reinterpret_cast<uint32_t **>(d_tab[3]);
+        T.plug = reinterpret_cast<uint32_t **>(d_tab[4]);
+        return T;
+    }
+
+    int32_t ensure_buf(void *&p, size_t &capb, size_t need) {
+        if (need <= capb) return PE_OK;
+        if (p) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(p)); p = nullptr; }
+        size_t nc = std::max(need, capb + capb / 2);
+        CU(cudaMalloc(&p, nc));
+        capb = nc;
+        return PE_OK;
+    }
+
+    // ---- timing ------------------------------------------------------------
+    EvPair *ev_begin(int kind) {
+        if (!timing) return nullptr;
+        if (ev_used == ev_pool.size()) {
+            EvPair p; p.kind = kind;
+            if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return nullptr;
+            ev_pool.push_back(p);
+        }
+        EvPair *p = &ev_pool[ev_used++];
+        p->kind = kind;
+        cudaEventRecord(p->a, stream);
+        return p;
+    }
+    void ev_end(EvPair *p) { if (p) cudaEventRecord(p->b, stream); }
+    void ev_collect() {
+        for (size_t i = 0; i < ev_used; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b) == cudaSuccess) {
+                if (ev_pool[i].kind == 0) stats.scan_ms += ms;
+                else if (ev_pool[i].kind == 1) stats.sequencer_ms += ms;
+                else if (ev_pool[i].kind == 2) stats.h2d_ms += ms;
+                else if (ev_pool[i].kind == 3) stats.d2h_ms += ms;
+                else stats.run_ms += ms;
+            }
+        }
+        ev_used = 0;
+    }
+
+    // ---- node mirror ---------------------------------------------------------
+    int32_t upsert(const pe_node_row *rows, uint32_t n_rows, const pe_kv32 *attrs, const pe_kv64 *gens, const pe_kv32 *svcs,
+                   const uint32_t *prt, const uint32_t *plg) {
+        if (!n_rows) return PE_OK;
+        uint32_t maxrow = 0;
+        size_t na = 0, ng = 0, ns = 0, np = 0, nq = 0;
+        int32_t rc;
+        for (uint32_t r = 0; r < n_rows; r++) {
+            const pe_node_row &row = rows[r];
+            if (row.os_id > 255 || row.arch_id > 255) { err = "os_id / arch_id must be <= 255"; return PE_ERR_INVALID; }
+            maxrow = std::max(maxrow, row.node_idx);
+            na = std::max<size_t>(na, (size_t)row.attr_off + row.attr_cnt);
+            ng = std::max<size_t>(ng, (size_t)row.gen_off + row.gen_cnt);
+            ns = std::max<size_t>(ns, (size_t)row.svc_off + row.svc_cnt);
+            np = std::max<size_t>(np, (size_t)row.port_off + row.port_cnt);
+            nq = std::max<size_t>(nq, (size_t)row.plug_off + row.plug_cnt);
+        }
+        if ((rc = ensure_cap(maxrow + 1))) return rc;
+        for (uint32_t r = 0; r < n_rows; r++) {
+            const pe_node_row &row = rows[r];
+            for (uint32_t i = 0; i < row.attr_cnt; i++) if ((rc = ensure_col(attr, attrs[row.attr_off + i].key, 4))) return rc;
+            for (uint32_t i = 0; i < row.gen_cnt; i++) if ((rc = ensure_col(gen, gens[row.gen_off + i].key, 8))) return rc;
+            for (uint32_t i = 0; i < row.svc_cnt; i++) if ((rc = ensure_col(svc, svcs[row.svc_off + i].key, 4))) return rc;
+            for (uint32_t i = 0; i < row.port_cnt; i++) if ((rc = ensure_col(ports, prt[row.port_off + i] >> 5, 4))) return rc;
+            for (uint32_t i = 0; i < row.plug_cnt; i++) if ((rc = ensure_col(plug, plg[row.plug_off + i] >> 5, 4))) return rc;
+        }
+        if ((rc = sync_tabs())) return rc;
+        // one arena: rows | attrs | gens | svcs | ports | plugs
+        size_t o_rows = 0, o_a = o_rows + round_up((uint32_t)(n_rows * sizeof(pe_node_row)), 16), o_g = o_a + round_up((uint32_t)(na * 8), 16);
+        size_t o_s = o_g + ng * 16, o_p = o_s + round_up((uint32_t)(ns * 8), 16), o_q = o_p + round_up((uint32_t)(np * 4), 16);
+        size_t tot = o_q + round_up((uint32_t)(nq * 4), 16) + 16;
+        if ((rc = ensure_buf(up_buf, up_cap, tot))) return rc;
+        char *b = reinterpret_cast<char *>(up_buf);
+        CU(cudaMemcpyAsync(b + o_rows, rows, n_rows * sizeof(pe_node_row), cudaMemcpyHostToDevice, stream));
+        if (na) CU(cudaMemcpyAsync(b + o_a, attrs, na * 8, cudaMemcpyHostToDevice, stream));
+        if (ng) CU(cudaMemcpyAsync(b + o_g, gens, ng * 16, cudaMemcpyHostToDevice, stream));
+        if (ns) CU(cudaMemcpyAsync(b + o_s, svcs, ns * 8, cudaMemcpyHostToDevice, stream));
+        if (np) CU(cudaMemcpyAsync(b + o_p, prt, np * 4, cudaMemcpyHostToDevice, stream));
+        if (nq) CU(cudaMemcpyAsync(b + o_q, plg, nq * 4, cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += n_rows * sizeof(pe_node_row) + na * 8 + ng * 16 + ns * 8 + np * 4 + nq * 4;
+        UpsertParams P;
+        P.T = table();
+        P.rows = reinterpret_cast<pe_node_row *>(b + o_rows); P.n_rows = n_rows;
+        P.attrs = reinterpret_cast<pe_kv32 *>(b + o_a); P.gens = reinterpret_cast<pe_kv64 *>(b + o_g);
+        P.svcs = reinterpret_cast<pe_kv32 *>(b + o_s); P.ports = reinterpret_cast<uint32_t *>(b + o_p);
+        P.plugs = reinterpret_cast<uint32_t *>(b + o_q);
+        // services: a row upsert replaces the node's whole counter set
+        if (!svc.empty()) {
+            // zero every service counter of the upserted rows first (k_upsert then sets the listed ones)
+            k_zero_svc_rows<<<(n_rows + 127) / 128, 128, 0, stream>>>(P.T, P.rows, n_rows);
+            stats.kernel_launches++;
+        }
+        k_upsert<<<(n_rows + 127) / 128, 128, 0, stream>>>(P);
+        stats.kernel_launches++;
+        CU(cudaGetLastError());
+        if (maxrow + 1 > n_nodes) n_nodes = maxrow + 1;
+        CU(cudaStreamSynchronize(stream));  // caller buffers may be reused after return
+        return PE_OK;
+    }
+
+    int32_t remove(const uint32_t *idx, uint32_t n) {
+        if (!n) return PE_OK;
+        for (uint32_t i = 0; i < n; i++) if (idx[i] >= cap) { err = "node index out of range"; return PE_ERR_INVALID; }
+        int32_t rc;
+        if ((rc = ensure_buf(up_buf, up_cap, (size_t)n * 4))) return rc;
+        CU(cudaMemcpyAsync(up_buf, idx, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+        if ((rc = sync_tabs())) return rc;
+        k_remove<<<(n + 127) / 128, 128, 0, stream>>>(table(), reinterpret_cast<uint32_t *>(up_buf), n);
+        stats.kernel_launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(stream));
+        return PE_OK;
+    }
+
+    int32_t delta(const pe_task_delta *d, uint32_t n, const pe_kv64 *gens, const uint32_t *prt) {
+        if (!n) return PE_OK;
+        size_t ng = 0, np = 0;
+        int32_t rc;
+        for (uint32_t i = 0; i < n; i++) {
+            if (d[i].node_idx >= cap) { err = "node index out of range"; return PE_ERR_INVALID; }
+            ng = std::max<size_t>(ng, (size_t)d[i].gen_off + d[i].gen_cnt);
+            np = std::max<size_t>(np, (size_t)d[i].port_off + d[i].port_cnt);
+            if (d[i].counts && (rc = ensure_col(svc, d[i].svc_id, 4))) return rc;
+            for (uint32_t j = 0; j < d[i].gen_cnt; j++) if ((rc = ensure_col(gen, gens[d[i].gen_off + j].key, 8))) return rc;
+            for (uint32_t j = 0; j < d[i].port_cnt; j++) if ((rc = ensure_col(ports, prt[d[i].port_off + j] >> 5, 4))) return rc;
+        }
+        if ((rc = sync_tabs())) return rc;
+        size_t o_g = round_up((uint32_t)(n * sizeof(pe_task_delta)), 16), o_p = o_g + ng * 16;
+        if ((rc = ensure_buf(up_buf, up_cap, o_p + np * 4 + 16))) return rc;
+        char *b = reinterpret_cast<char *>(up_buf);
+        CU(cudaMemcpyAsync(b, d, n * sizeof(pe_task_delta), cudaMemcpyHostToDevice, stream));
+        if (ng) CU(cudaMemcpyAsync(b + o_g, gens, ng * 16, cudaMemcpyHostToDevice, stream));
+        if (np) CU(cudaMemcpyAsync(b + o_p, prt, np * 4, cudaMemcpyHostToDevice, stream));
+        k_delta_add<<<(n + 127) / 128, 128, 0, stream>>>(table(), reinterpret_cast<pe_task_delta *>(b), n);
+        stats.kernel_launches++;
+        if (ng || np) {
+            k_delta_seq<<<1, 32, 0, stream>>>(table(), reinterpret_cast<pe_task_delta *>(b), n, reinterpret_cast<pe_kv64 *>(b + o_g),
+                                             reinterpret_cast<uint32_t *>(b + o_p));
+            stats.kernel_launches++;
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(stream));
+        return PE_OK;
+    }
+
+    // ---- tick ------------------------------------------------------------------
+    int32_t validate_and_prepare(const pe_tick *tk) {
+        if (!tk) { err = "null tick"; return PE_ERR_INVALID; }
+        int32_t rc;
+        for (uint32_t i = 0; i < tk->n_groups; i++) {
+            const pe_group &g = tk->groups[i];
+            if ((uint64_t)g.task_off + g.n_tasks > tk->n_tasks) { err = "group task range out of bounds"; return PE_ERR_INVALID; }
+            if ((uint64_t)g.gen_off + g.gen_cnt > tk->n_gens || (uint64_t)g.con_off + g.con_cnt > tk->n_cons ||
+                (uint64_t)g.ip_off + g.ip_cnt > tk->n_ips || (uint64_t)g.plat_off + g.plat_cnt > tk->n_plats ||
+                (uint64_t)g.port_off + g.port_cnt > tk->n_ports || (uint64_t)g.plug_off + g.plug_cnt > tk->n_plugs ||
+                (uint64_t)g.fail_off + g.fail_cnt > tk->n_fails) { err = "group side-array range out of bounds"; return PE_ERR_INVALID; }
+            if (n_nodes && g.tie_start >= n_nodes) { err = "tie_start >= node count"; return PE_ERR_INVALID; }
+            if (g.gen_cnt > PE_MAX_GEN_WANTS) { err = "more than 8 generic reservations in one task"; return PE_ERR_UNSUPPORTED; }
+            if ((rc = ensure_col(svc, g.svc_id, 4))) return rc;
+            if ((g.flags & PE_G_LOG_DRIVER) && (rc = ensure_col(plug, g.log_plugin >> 5, 4))) return rc;
+        }
+        for (uint32_t i = 0; i < tk->n_cons; i++) if ((rc = ensure_col(attr, tk->cons[i].col, 4))) return rc;
+        for (uint32_t i = 0; i < tk->n_gens; i++) if ((rc = ensure_col(gen, tk->gens[i].kind, 8))) return rc;
+        for (uint32_t i = 0; i < tk->n_ports; i++) if ((rc = ensure_col(ports, tk->ports[i] >> 5, 4))) return rc;
+        for (uint32_t i = 0; i < tk->n_plugs; i++) if ((rc = ensure_col(plug, tk->plugs[i] >> 5, 4))) return rc;
+        for (uint32_t i = 0; i < tk->n_fails; i++) {
+            if (tk->fails[i].count > 255) { err = "more than 255 recent failures on one node"; return PE_ERR_OVERFLOW; }
+        }
+        return sync_tabs();
+    }
+
+    int32_t tick_upload(const pe_tick *tk) {
+        int32_t rc = validate_and_prepare(tk);
+        if (rc) return rc;
+        n_groups = tk->n_groups; n_tasks = tk->n_tasks;
+        groups.assign(tk->groups, tk->groups + tk->n_groups);
+        h_cons.assign(tk->cons, tk->cons + tk->n_cons);
+        h_gens.assign(tk->gens, tk->gens + tk->n_gens);
+        h_ports.assign(tk->ports, tk->ports + tk->n_ports);
+        h_plugs.assign(tk->plugs, tk->plugs + tk->n_plugs);
+        size_t off[10]; size_t o = 0;
+        auto place = [&](int i, size_t bytes) { off[i] = o; o += (bytes + 15) / 16 * 16; };
+        place(0, (size_t)tk->n_groups * sizeof(pe_group));
+        place(1, (size_t)tk->n_tasks);
+        place(2, (size_t)tk->n_gens * sizeof(pe_generic_want));
+        place(3, (size_t)tk->n_cons * sizeof(pe_constraint));
+        place(4, (size_t)tk->n_ips * sizeof(pe_ip_constraint));
+        place(5, (size_t)tk->n_plats * sizeof(pe_platform));
+        place(6, (size_t)tk->n_ports * 4);
+        place(7, (size_t)tk->n_plugs * 4);
+        place(8, (size_t)tk->n_fails * sizeof(pe_node_fail));
+        if ((rc = ensure_buf(tick_buf, tick_cap, o + 16))) return rc;
+        char *b = reinterpret_cast<char *>(tick_buf);
+        EvPair *ev = ev_begin(2);
+        auto up = [&](int i, const void *src, size_t bytes) -> cudaError_t {
+            stats.h2d_bytes += bytes;
+            return bytes ? cudaMemcpyAsync(b + off[i], src, bytes, cudaMemcpyHostToDevice, stream) : cudaSuccess;
+        };
+        CU(up(0, tk->groups, (size_t)tk->n_groups * sizeof(pe_group)));
+        CU(up(1, tk->task_flags, (size_t)tk->n_tasks));
+        CU(up(2, tk->gens, (size_t)tk->n_gens * sizeof(pe_generic_want)));
+        CU(up(3, tk->cons, (size_t)tk->n_cons * sizeof(pe_constraint)));
+        CU(up(4, tk->ips, (size_t)tk->n_ips * sizeof(pe_ip_constraint)));
+        CU(up(5, tk->plats, (size_t)tk->n_plats * sizeof(pe_platform)));
+        CU(up(6, tk->ports, (size_t)tk->n_ports * 4));
+        CU(up(7, tk->plugs, (size_t)tk->n_plugs * 4));
+        CU(up(8, tk->fails, (size_t)tk->n_fails * sizeof(pe_node_fail)));
+        ev_end(ev);
+        K.groups = reinterpret_cast<pe_group *>(b + off[0]);
+        K.task_flags = reinterpret_cast<uint8_t *>(b + off[1]);
+        K.gens = reinterpret_cast<pe_generic_want *>(b + off[2]);
+        K.cons = reinterpret_cast<pe_constraint *>(b + off[3]);
+        K.ips = reinterpret_cast<pe_ip_constraint *>(b + off[4]);
+        K.plats = reinterpret_cast<pe_platform *>(b + off[5]);
+        K.ports = reinterpret_cast<uint32_t *>(b + off[6]);
+        K.plugs = reinterpret_cast<uint32_t *>(b + off[7]);
+        K.fails = reinterpret_cast<pe_node_fail *>(b + off[8]);
+        void *p = d_out_node; size_t c = out_node_cap;
+        if ((rc = ensure_buf(p, c, (size_t)std::max(n_tasks, 1u) * 4))) return rc;
+        d_out_node = reinterpret_cast<uint32_t *>(p); out_node_cap = c;
+        p = d_out_fail; c = out_fail_cap;
+        if ((rc = ensure_buf(p, c, (size_t)std::max(n_groups, 1u) * PE_NUM_FILTERS * 4))) return rc;
+        d_out_fail = reinterpret_cast<uint32_t *>(p); out_fail_cap = c;
+        K.out_node = d_out_node; K.out_fail = d_out_fail;
+        CU(cudaStreamSynchronize(stream));  // caller buffers may be reused after return
+        return PE_OK;
+    }
+
+    int32_t ensure_scratch() {
+        if (scratch_cap >= cap && ff8) return PE_OK;
+        CU(cudaStreamSynchronize(stream));
+        auto re = [&](auto *&p, size_t bytes) -> cudaError_t {
+            if (p) cudaFree(p);
+            p = nullptr;
+            return cudaMalloc(reinterpret_cast<void **>(&p), bytes);
+        };
+        uint32_t sc = 1;
+        while (sc < cap) sc <<= 1;
+        CU(re(ff8, cap));
+        CU(re(pref64, (size_t)cap * 8));
+        CU(re(cand_g, (size_t)sc * sizeof(CandKey)));
+        CU(re(st_cpu_g, (size_t)sc * 8));
+        CU(re(st_mem_g, (size_t)sc * 8));
+        CU(re(st_gen_g, (size_t)sc * 8 * PE_MAX_GEN_WANTS));
+        CU(re(st_svc_g, (size_t)sc * 4));
+        CU(re(st_tot_g, (size_t)sc * 4));
+        CU(re(st_placed_g, (size_t)sc * 4));
+        CU(re(st_flags_g, (size_t)sc));
+        CU(re(touched_g, (size_t)cap / 8 + 256));
+        scratch_cap = cap;
+        st_cap = sc;
+        return PE_OK;
+    }
+
+    uint32_t e_stride() const { return round_up(cap / 32, 32); }
+
+    int32_t launch_sequencer(uint32_t g0, uint32_t g1, bool with_scan) {
+        SeqParams P;
+        P.T = table(); P.K = K;
+        P.g_begin = g0; P.g_end = g1;
+        P.scan = with_scan ? scan_out : nullptr;
+        P.E = E; P.e_stride = e_stride();
+        P.ff8 = ff8; P.pref64 = pref64; P.cand_g = cand_g;
+        P.st_cpu_g = st_cpu_g; P.st_mem_g = st_mem_g; P.st_svc_g = st_svc_g; P.st_tot_g = st_tot_g;
+        P.st_placed_g = st_placed_g; P.st_flags_g = st_flags_g; P.st_gen_g = st_gen_g; P.st_cap = st_cap;
+        P.touched_g = touched_g;
+        P.touched_words = with_scan ? (n_nodes + 31) / 32 : 0;
+        P.touched_in_smem = P.touched_words <= 16384 ? 1 : 0;
+        P.ctr = d_ctr;
+        size_t dyn = seq_dyn_smem_bytes(P.touched_in_smem ? P.touched_words : 0);
+        EvPair *ev = ev_begin(1);
+        k_sequencer<<<1, PE_SEQ_THREADS, dyn, stream>>>(P);
+        ev_end(ev);
+        stats.kernel_launches++;
+        CU(cudaGetLastError());
+        return PE_OK;
+    }
+
+    // Plan one scan batch over groups [g0, g0+B): which columns ride in the
+    // tile, the tile size, the kernel variant.  Returns false if the batch
+    // needs something the scan path does not stage (sequencer handles it).
+    bool plan_scan(uint32_t g0, uint32_t B, ScanParams &P, bool &has_res, bool &has_extra, uint64_t &alg_bytes) {
+        std::vector<uint8_t> use_attr(attr.size(), 0), use_gen(gen.size(), 0), use_pw(ports.size(), 0), use_qw(plug.size(), 0);
+        has_res = false; has_extra = false;
+        bool use_ip = false;
+        alg_bytes = 0;
+        uint32_t seen_cols[PE_SCAN_MAXCON];
+        for (uint32_t i = 0; i < B; i++) {
+            const pe_group &g = groups[g0 + i];
+            if (g.con_cnt > PE_SCAN_MAXCON) return false;
+            uint64_t per_eval = 12;  // meta + total + per-service count
+            uint32_t nseen = 0;
+            for (uint32_t e = 0; e < g.con_cnt; e++) {
+                uint32_t c = h_cons[g.con_off + e].col;
+                if (c >= PE_SCAN_MAXATTR) return false;
+                use_attr[c] = 1;
+                bool dup = false;
+                for (uint32_t s = 0; s < nseen; s++) dup |= seen_cols[s] == c;
+                if (!dup) { seen_cols[nseen++] = c; per_eval += 4; }
+            }
+            if ((g.filter_mask >> PE_F_RESOURCE) & 1u) {
+                has_res = true;
+                per_eval += 16;
+                for (uint32_t e = 0; e < g.gen_cnt; e++) {
+                    uint32_t kd = h_gens[g.gen_off + e].kind;
+                    if (kd >= PE_SCAN_MAXGENK) return false;
+                    use_gen[kd] = 1;
+                    per_eval += 8;
+                }
+            }
+            if ((g.filter_mask >> PE_F_PLUGIN) & 1u) {
+                has_extra = true;
+                for (uint32_t e = 0; e < g.plug_cnt; e++) {
+                    uint32_t w = h_plugs[g.plug_off + e] >> 5;
+                    if (w >= PE_SCAN_MAXW) return false;
+                    use_qw[w] = 1;
+                }
+                if (g.flags & PE_G_LOG_DRIVER) {
+                    uint32_t w = g.log_plugin >> 5;
+                    if (w >= PE_SCAN_MAXW) return false;
+                    use_qw[w] = 1;
+                }
+                per_eval += 4;
+            }
+            if ((g.filter_mask >> PE_F_HOSTPORT) & 1u) {
+                has_extra = true;
+                for (uint32_t e = 0; e < g.port_cnt; e++) {
+                    uint32_t w = h_ports[g.port_off + e] >> 5;
+                    if (w >= PE_SCAN_MAXW) return false;
+                    use_pw[w] = 1;
+                }
+                per_eval += 4;
+            }
+            if (g.ip_cnt) { has_extra = true; use_ip = true; per_eval += 16; }
+            if ((g.filter_mask >> PE_F_MAXREPLICAS) & 1u) has_extra = true;
+            if (g.fail_cnt) has_extra = true;
+            alg_bytes += per_eval * n_nodes;
+        }
+        // column list
+        P.n_cols = 0;
+        uint32_t bpn = 0;
+        struct Tmp { const void *base; uint32_t elem; uint32_t *off32; uint16_t *off16; };
+        std::vector<Tmp> cols;
+        cols.push_back({meta, 4, &P.off_meta, nullptr});
+        cols.push_back({total, 4, &P.off_total, nullptr});
+        P.off_cpu = P.off_mem = P.off_ip = 0;
+        if (has_res) { cols.push_back({cpu, 8, &P.off_cpu, nullptr}); cols.push_back({mem, 8, &P.off_mem, nullptr}); }
+        if (use_ip) cols.push_back({ip, 16, &P.off_ip, nullptr});
+        memset(P.off_attr, 0xFF, sizeof P.off_attr); memset(P.off_gen, 0xFF, sizeof P.off_gen);
+        memset(P.off_portw, 0xFF, sizeof P.off_portw); memset(P.off_plugw, 0xFF, sizeof P.off_plugw);
+        for (uint32_t c = 0; c < use_attr.size() && c < PE_SCAN_MAXATTR; c++) if (use_attr[c]) cols.push_back({attr[c], 4, nullptr, &P.off_attr[c]});
+        for (uint32_t c = 0; c < use_gen.size() && c < PE_SCAN_MAXGENK; c++) if (use_gen[c]) cols.push_back({gen[c], 8, nullptr, &P.off_gen[c]});
+        for (uint32_t c = 0; c < use_pw.size() && c < PE_SCAN_MAXW; c++) if (use_pw[c]) cols.push_back({ports[c], 4, nullptr, &P.off_portw[c]});
+        for (uint32_t c = 0; c < use_qw.size() && c < PE_SCAN_MAXW; c++) if (use_qw[c]) cols.push_back({plug[c], 4, nullptr, &P.off_plugw[c]});
+        if (cols.size() > PE_SCAN_MAXCOLS) return false;
+        for (auto &c : cols) bpn += c.elem;
+        // largest tile whose two stages fit the per-CTA budget (2 CTAs / SM)
+        const uint32_t budget = 100 * 1024;
+        uint32_t TN = 2048;
+        while (TN > 256 && 2u * TN * bpn > budget) TN >>= 1;
+        if (2u * TN * bpn > budget) return false;
+        uint32_t o = 0;
+        // 8- and 16-byte columns first so every column start stays aligned to its element size
+        std::stable_sort(cols.begin(), cols.end(), [](const Tmp &a, const Tmp &b) { return a.elem > b.elem; });
+        for (auto &c : cols) {
+            ScanCol &sc = P.cols[P.n_cols++];
+            sc.base = c.base; sc.elem = c.elem; sc.smem_off = o;
+            if (c.off32) *c.off32 = o;
+            if (c.off16) *c.off16 = (uint16_t)(o / 16);
+            o += TN * c.elem;
+        }
+        P.stage_bytes = o;
+        P.tile_nodes = TN;
+        P.n_tiles = (n_nodes + TN - 1) / TN;
+        P.K = K;
+        P.n_nodes = n_nodes;
+        P.g_begin = g0; P.n_tasks = B;
+        P.svc = reinterpret_cast<uint32_t *const *>(d_tab[2]);
+        P.out = scan_out; P.E = E; P.e_stride = e_stride();
+        return true;
+    }
+
+    int32_t tick_run() {
+        int32_t rc;
+        if ((rc = sync_tabs())) return rc;
+        if ((rc = ensure_scratch())) return rc;
+        const uint32_t wave = (uint32_t)num_sms * 2u * PE_SCAN_WARPS;
+        const uint32_t Bmax = max_batch ? max_batch : wave;
+        const bool spec = !(cfg_flags & PE_CFG_NO_SPECULATION) && n_nodes > 0;
+        if (spec) {
+            size_t need = (size_t)Bmax * e_stride();
+            if (need > E_words) {
+                void *p = E; size_t c = E_words * 4;
+                if ((rc = ensure_buf(p, c, need * 4))) return rc;
+                E = reinterpret_cast<uint32_t *>(p); E_words = c / 4;
+            }
+            if (Bmax > scan_out_cap) {
+                void *p = scan_out; size_t c = (size_t)scan_out_cap * sizeof(ScanResult);
+                if ((rc = ensure_buf(p, c, (size_t)Bmax * sizeof(ScanResult)))) return rc;
+                scan_out = reinterpret_cast<ScanResult *>(p); scan_out_cap = Bmax;
+            }
+        }
+        EvPair *ev_run = ev_begin(4);
+        uint32_t g = 0;
+        while (g < n_groups) {
+            // maximal run of k == 1 groups -> batched scan path; anything else -> sequencer alone
+            uint32_t e = g;
+            const bool one = groups[g].n_tasks == 1;
+            while (e < n_groups && (groups[e].n_tasks == 1) == one) e++;
+            if (one && spec && e - g >= 4) {
+                for (uint32_t b0 = g; b0 < e; b0 += Bmax) {
+                    const uint32_t B = std::min(Bmax, e - b0);
+                    ScanParams SP;
+                    bool has_res, has_extra;
+                    uint64_t alg = 0;
+                    if (plan_scan(b0, B, SP, has_res, has_extra, alg)) {
+                        const uint32_t grid = (B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS;
+                        const size_t dyn = 2 * (size_t)SP.stage_bytes;
+                        EvPair *ev = ev_begin(0);
+                        if (has_res && has_extra) k_scan<true, true><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+                        else if (has_res) k_scan<true, false><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+                        else if (has_extra) k_scan<false, true><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+                        else k_scan<false, false><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+                        ev_end(ev);
+                        CU(cudaGetLastError());
+                        stats.kernel_launches++; stats.scan_launches++;
+                        stats.evals += (uint64_t)B * n_nodes;
+                        stats.scan_bytes += alg;
+                        if ((rc = launch_sequencer(b0, b0 + B, true))) return rc;
+                    } else {
+                        if ((rc = launch_sequencer(b0, b0 + B, false))) return rc;
+                    }
+                }
+            } else {
+                if ((rc = launch_sequencer(g, e, false))) return rc;
+            }
+            g = e;
+        }
+        ev_end(ev_run);
+        CU(cudaStreamSynchronize(stream));
+        return collect_counters();
+    }
+
+    int32_t collect_counters() {
+        DevCounters c;
+        CU(cudaMemcpy(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost));
+        CU(cudaMemset(d_ctr, 0, sizeof c));
+        stats.fast_path += c.fast_path; stats.slow_path += c.slow_path;
+        stats.placements += c.placements; stats.evals_generic += c.evals_generic;
+        ev_collect();
+        if (c.error & PE_DEV_ERR_SVC_OVERFLOW) { err = "a per-service task count reached 2^24 - 1 on one node"; return PE_ERR_OVERFLOW; }
+        return PE_OK;
+    }
+
+    int32_t tick_download(uint32_t *out_node, uint32_t *out_fail) {
+        EvPair *ev = ev_begin(3);
+        if (out_node && n_tasks) { CU(cudaMemcpyAsync(out_node, d_out_node, (size_t)n_tasks * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (size_t)n_tasks * 4; }
+        if (out_fail && n_groups) { CU(cudaMemcpyAsync(out_fail, d_out_fail, (size_t)n_groups * PE_NUM_FILTERS * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (size_t)n_groups * PE_NUM_FILTERS * 4; }
+        ev_end(ev);
+        CU(cudaStreamSynchronize(stream));
+        ev_collect();
+        return PE_OK;
+    }
+
+    int32_t fit(const pe_tick *tk, const uint32_t *node_idx, uint8_t *out_ok, uint32_t *out_fail) {
+        int32_t rc = tick_upload(tk);
+        if (rc) return rc;
+        if (!n_groups) return PE_OK;
+        if ((rc = ensure_buf(up_buf, up_cap, (size_t)n_groups * 5 + 64))) return rc;
+        uint32_t *d_idx = reinterpret_cast<uint32_t *>(up_buf);
+        uint8_t *d_ok = reinterpret_cast<uint8_t *>(d_idx + n_groups);
+        CU(cudaMemcpyAsync(d_idx, node_idx, (size_t)n_groups * 4, cudaMemcpyHostToDevice, stream));
+        k_fit<<<1, 32, 0, stream>>>(table(), K, n_groups, d_idx, d_ok, d_ctr);
+        stats.kernel_launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out_ok, d_ok, n_groups, cudaMemcpyDeviceToHost, stream));
+        if (out_fail) CU(cudaMemcpyAsync(out_fail, d_out_fail, (size_t)n_groups * PE_NUM_FILTERS * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return collect_counters();
+    }
+
+    template <class T> int32_t snap_col(const T *col, uint32_t first, uint32_t n, T *out) {
+        if ((uint64_t)first + n > cap) { err = "snapshot range out of bounds"; return PE_ERR_INVALID; }
+        if (!col) { std::memset(out, 0, (size_t)n * sizeof(T)); return PE_OK; }
+        CU(cudaMemcpyAsync(out, col + first, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return PE_OK;
+    }
+};
+
+// ============================ C ABI ==========================================
+extern "C" {
+
+uint32_t pe_abi_version(void) { return PE_ABI_VERSION; }
+
+int32_t pe_create(const pe_config *cfg, pe_engine **out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return PE_ERR_INVALID; }
+    if (cfg->abi_version != PE_ABI_VERSION) { g_create_err = "ABI version mismatch"; return PE_ERR_INVALID; }
+    if (cfg->world_size > 1) { g_create_err = "world_size > 1: build with node sharding (see DESIGN.md)"; return PE_ERR_UNSUPPORTED; }
+    pe_engine *h = new pe_engine();
+    int32_t rc = h->init(cfg);
+    if (rc) { g_create_err = h->err; h->destroy(); delete h; return rc; }
+    *out = h;
+    return PE_OK;
+}
+
+void pe_destroy(pe_engine *h) {
+    if (!h) return;
+    h->destroy();
+    delete h;
+}
+
+const char *pe_last_error(const pe_engine *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int32_t pe_node_upsert(pe_engine *h, const pe_node_row *rows, uint32_t n_rows, const pe_kv32 *attrs, const pe_kv64 *gens,
+                       const pe_kv32 *svcs, const uint32_t *ports, const uint32_t *plugs) {
+    return h->upsert(rows, n_rows, attrs, gens, svcs, ports, plugs);
+}
+int32_t pe_node_remove(pe_engine *h, const uint32_t *idx, uint32_t n) { return h->remove(idx, n); }
+int32_t pe_set_node_count(pe_engine *h, uint32_t n) {
+    int32_t rc = h->ensure_cap(n);
+    if (rc) return rc;
+    h->n_nodes = n;
+    return PE_OK;
+}
+int32_t pe_node_task_delta(pe_engine *h, const pe_task_delta *d, uint32_t n, const pe_kv64 *gens, const uint32_t *ports) {
+    return h->delta(d, n, gens, ports);
+}
+
+int32_t pe_tick_upload(pe_engine *h, const pe_tick *tick) { return h->tick_upload(tick); }
+int32_t pe_tick_run(pe_engine *h) { return h->tick_run(); }
+int32_t pe_tick_download(pe_engine *h, uint32_t *out_node, uint32_t *out_fail) { return h->tick_download(out_node, out_fail); }
+
+int32_t pe_schedule(pe_engine *h, const pe_tick *tick, uint32_t *out_node, uint32_t *out_fail) {
+    int32_t rc = h->tick_upload(tick);
+    if (rc) return rc;
+    if ((rc = h->tick_run())) return rc;
+    return h->tick_download(out_node, out_fail);
+}
+
+int32_t pe_fit(pe_engine *h, const pe_tick *tick, const uint32_t *node_idx, uint8_t *out_ok, uint32_t *out_fail) {
+    return h->fit(tick, node_idx, out_ok, out_fail);
+}
+
+int32_t pe_snapshot(pe_engine *h, uint32_t first, uint32_t n, pe_node_state *out) {
+    if ((uint64_t)first + n > h->cap) { h->err = "snapshot range out of bounds"; return PE_ERR_INVALID; }
+    std::vector<uint32_t> m(n), t(n);
+    std::vector<int64_t> c(n), mm(n);
+    int32_t rc;
+    if ((rc = h->snap_col(h->meta, first, n, m.data()))) return rc;
+    if ((rc = h->snap_col(h->total, first, n, t.data()))) return rc;
+    if ((rc = h->snap_col(h->cpu, first, n, c.data()))) return rc;
+    if ((rc = h->snap_col(h->mem, first, n, mm.data()))) return rc;
+    for (uint32_t i = 0; i < n; i++) { out[i].flags = m[i] & PE_META_FLAGS_MASK; out[i].total_tasks = t[i]; out[i].cpu_avail = c[i]; out[i].mem_avail = mm[i]; }
+    return PE_OK;
+}
+int32_t pe_snapshot_service(pe_engine *h, uint32_t s, uint32_t first, uint32_t n, uint32_t *out) {
+    return h->snap_col(s < h->svc.size() ? h->svc[s] : (uint32_t *)nullptr, first, n, out);
+}
+int32_t pe_snapshot_generic(pe_engine *h, uint32_t kd, uint32_t first, uint32_t n, int64_t *out) {
+    return h->snap_col(kd < h->gen.size() ? h->gen[kd] : (int64_t *)nullptr, first, n, out);
+}
+int32_t pe_snapshot_ports(pe_engine *h, uint32_t slot, uint32_t first, uint32_t n, uint8_t *out) {
+    std::vector<uint32_t> w(n);
+    int32_t rc = h->snap_col((slot >> 5) < h->ports.size() ? h->ports[slot >> 5] : (uint32_t *)nullptr, first, n, w.data());
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++) out[i] = (w[i] >> (slot & 31)) & 1;
+    return PE_OK;
+}
+
+int32_t pe_get_stats(pe_engine *h, pe_stats *out) { *out = h->stats; return PE_OK; }
+int32_t pe_stats_reset(pe_engine *h) { h->stats = pe_stats{}; return PE_OK; }
+
+int32_t pe_fold_value(const char *in, uint32_t len, char *out, uint32_t cap) {
+    uint32_t w = 0;
+    uint32_t i = 0;
+    while (i < len) {
+        const unsigned char c = (unsigned char)in[i];
+        char r;
+        uint32_t adv = 1;
+        if (c >= 'A' && c <= 'Z') r = (char)(c | 0x20);
+        else if (c == 0xE2 && i + 2 < len && (unsigned char)in[i + 1] == 0x84 && (unsigned char)in[i + 2] == 0xAA) { r = 'k'; adv = 3; }  // KELVIN SIGN
+        else if (c == 0xC5 && i + 1 < len && (unsigned char)in[i + 1] == 0xBF) { r = 's'; adv = 2; }                                      // LATIN SMALL LETTER LONG S
+        else r = (char)c;
+        if (w >= cap) return -1;
+        out[w++] = r;
+        i += adv;
+    }
+    return (int32_t)w;
+}
+
+}  // extern "C"

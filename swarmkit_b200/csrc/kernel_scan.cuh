@@ -1,0 +1,304 @@
+// kernel_scan.cuh -- the batched (task, node) filter + rank scan: THE hot kernel.
+//
+// One warp owns one pending k=1 task group ("one-off", scheduler.go:456-459,
+// 467-469 -- the shape BenchmarkScheduler100kNodes1MTasks exercises,
+// scheduler_test.go:3358,3378-3468).  The CTA's warps share node tiles: each
+// tile is a slice of every SoA column the batch needs, brought from HBM/L2 into
+// shared memory with cp.async.bulk (TMA bulk copy, mbarrier completion),
+// double-buffered.  Lane l of a warp evaluates node (tile*TN + step*32 + l):
+//
+//   Pipeline.Process   pipeline.go:56-68   (AND of the enabled filters)
+//   ReadyFilter        filter.go:40-43     meta bit
+//   ResourceFilter     filter.go:76-93     signed 64-bit compares + generic cells
+//   PluginFilter       filter.go:141-183   plugin bit words
+//   ConstraintFilter   filter.go:241-243   (col == value) ^ neq per expression
+//   PlatformFilter     filter.go:272-312   os/arch bytes of meta
+//   HostPortFilter     filter.go:342-353   port bit words
+//   MaxReplicasFilter  filter.go:379-381   svc < max
+//   nodeLess           scheduler.go:708-735 rank prefix (f5, svc, total)
+//
+// Output per task: the smallest rank prefix among feasible nodes and the bitmap
+// of the feasible nodes that have it (the "class").  The sequencer turns that
+// into the sequentially exact placement (kernel_sequencer.cuh).  No tensor
+// cores: this is integer/predicate work.
+#pragma once
+#include "kernels_common.cuh"
+
+namespace pe {
+
+#define PE_SCAN_WARPS 16
+#define PE_SCAN_THREADS (PE_SCAN_WARPS * 32)
+#define PE_SCAN_MAXCOLS 40
+#define PE_SCAN_MAXCON 16      // constraint expressions per task on the scan path
+#define PE_SCAN_MAXATTR 96
+#define PE_SCAN_MAXGENK 16
+#define PE_SCAN_MAXW 8         // port / plugin bit words
+
+struct ScanCol {
+    const void *base;
+    uint32_t elem;       // bytes per node
+    uint32_t smem_off;   // offset inside a stage
+};
+
+struct ScanParams {
+    TickDev K;
+    uint32_t n_nodes;
+    uint32_t g_begin, n_tasks;
+    uint32_t tile_nodes, n_tiles, stage_bytes, n_cols;
+    ScanCol cols[PE_SCAN_MAXCOLS];
+    uint32_t off_meta, off_total, off_cpu, off_mem, off_ip;   // stage offsets of the fixed columns
+    uint16_t off_attr[PE_SCAN_MAXATTR];   // stage offset / 16 of attribute column c (0xFFFF = not staged)
+    uint16_t off_gen[PE_SCAN_MAXGENK];
+    uint16_t off_portw[PE_SCAN_MAXW];
+    uint16_t off_plugw[PE_SCAN_MAXW];
+    uint32_t *const *svc;                 // per-service counter columns (read straight from L2)
+    ScanResult *out;
+    uint32_t *E;
+    uint32_t e_stride;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct WarpTask {          // per-warp descriptor staged in shared memory
+    pe_group G;
+    uint32_t con_off[PE_SCAN_MAXCON];   // stage byte offset of the expression's column
+    uint32_t con_val[PE_SCAN_MAXCON];
+    uint32_t con_neq[PE_SCAN_MAXCON];
+};
+
+template <bool HAS_RES, bool HAS_EXTRA>
+__global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_constant__ ScanParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ WarpTask wt_all[PE_SCAN_WARPS];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t TN = P.tile_nodes, N = P.n_nodes;
+    unsigned char *stage0 = smem, *stage1 = smem + P.stage_bytes;
+
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // ---- per-warp task descriptor
+    const uint32_t task = blockIdx.x * PE_SCAN_WARPS + warp;
+    const bool active = task < P.n_tasks;
+    WarpTask &W = wt_all[warp];
+    if (active) {
+        const pe_group *gsrc = P.K.groups + P.g_begin + task;
+        for (uint32_t i = lane; i < sizeof(pe_group) / 4; i += 32) reinterpret_cast<uint32_t *>(&W.G)[i] = reinterpret_cast<const uint32_t *>(gsrc)[i];
+        __syncwarp();
+        for (uint32_t i = lane; i < W.G.con_cnt && i < PE_SCAN_MAXCON; i += 32) {
+            const pe_constraint c = P.K.cons[W.G.con_off + i];
+            W.con_off[i] = (uint32_t)P.off_attr[c.col] * 16u;
+            W.con_val[i] = c.value;
+            W.con_neq[i] = c.neq;
+        }
+    }
+    __syncthreads();
+
+    auto issue_tile = [&](uint32_t tile, unsigned char *stage, uint64_t *bar) {
+        mbar_expect_tx(bar, P.stage_bytes);
+        for (uint32_t c = 0; c < P.n_cols; c++) {
+            const ScanCol col = P.cols[c];
+            const uint32_t bytes = TN * col.elem;
+            tma_bulk_g2s(stage + col.smem_off, (const unsigned char *)col.base + (size_t)tile * bytes, bytes, bar);
+        }
+    };
+    if (tid == 0) issue_tile(0, stage0, &full_bar[0]);
+
+    // ---- warp-uniform task state
+    const pe_group &G = W.G;
+    const uint32_t fm = active ? G.filter_mask : 0u;
+    const uint32_t con_cnt = active ? G.con_cnt : 0u;
+    const bool f_plat = ((fm >> PE_F_PLATFORM) & 1u) && G.plat_cnt > 0;
+    const bool f_con = (fm >> PE_F_CONSTRAINT) & 1u;
+    const bool f_never = f_con && (G.flags & PE_G_CONSTRAINT_NEVER);
+    const uint32_t *svccol = active ? P.svc[G.svc_id] : nullptr;
+    // up to 4 platforms kept in registers (os | arch << 8)
+    uint32_t plat[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (active && f_plat)
+        for (uint32_t i = 0; i < 4 && i < G.plat_cnt; i++) {
+            const pe_platform p = P.K.plats[G.plat_off + i];
+            plat[i] = p.os_id | (p.arch_id << 8);
+        }
+    // first 8 constraint expressions in registers
+    uint32_t c_off[8], c_val[8], c_neq[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const bool on = (uint32_t)e < con_cnt;
+        c_off[e] = on ? W.con_off[e] : 0u;
+        c_val[e] = on ? W.con_val[e] : 0u;
+        c_neq[e] = on ? W.con_neq[e] : 0u;
+    }
+
+    unsigned long long best = PE_PREF_NONE;
+    uint32_t w0 = 0, n_class = 0, myword = 0;
+    uint32_t *Erow = P.E + (size_t)task * P.e_stride;
+    const uint32_t steps = TN >> 5;
+
+    for (uint32_t tile = 0; tile < P.n_tiles; tile++) {
+        const uint32_t cur = tile & 1u;
+        unsigned char *stage = cur ? stage1 : stage0;
+        if (tid == 0 && tile + 1 < P.n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_tile(tile + 1, cur ? stage0 : stage1, &full_bar[cur ^ 1u]);
+        }
+        mbar_wait(&full_bar[cur], (tile >> 1) & 1u);
+
+        if (active) {
+            const uint32_t *s_meta = reinterpret_cast<const uint32_t *>(stage + P.off_meta);
+            const uint32_t *s_total = reinterpret_cast<const uint32_t *>(stage + P.off_total);
+            const uint32_t tile_base = tile * TN;
+            for (uint32_t sb = 0; sb < steps; sb += 8) {
+                // per-service counts come straight from L2 (one column per service):
+                // issue 8 independent loads, then consume
+                uint32_t svcv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t n = tile_base + (sb + u) * 32u + lane;
+                    svcv[u] = n < N ? svccol[n] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t s = sb + u;
+                    const uint32_t idx = s * 32u + lane;
+                    const uint32_t n = tile_base + idx;
+                    const uint32_t meta = s_meta[idx];
+                    const uint32_t svc_n = svcv[u];
+                    // ReadyFilter (always enabled, filter.go:35-43); rows past N / removed nodes are not in the set
+                    bool ok = (meta & (PE_NODE_VALID | PE_NODE_READY)) == (PE_NODE_VALID | PE_NODE_READY) && n < N;
+                    if (HAS_RES && ((fm >> PE_F_RESOURCE) & 1u)) {
+                        const long long cpu = reinterpret_cast<const long long *>(stage + P.off_cpu)[idx];
+                        const long long mem = reinterpret_cast<const long long *>(stage + P.off_mem)[idx];
+                        ok = ok && !(G.cpu_res > cpu) && !(G.mem_res > mem);
+                        for (uint32_t i = 0; i < G.gen_cnt; i++) {
+                            const pe_generic_want w = P.K.gens[G.gen_off + i];
+                            const long long cell = reinterpret_cast<const long long *>(stage + (uint32_t)P.off_gen[w.kind] * 16u)[idx];
+                            ok = ok && gen_enough(cell, w.value);
+                        }
+                    }
+                    if (f_con) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            if ((uint32_t)e < con_cnt) {
+                                const uint32_t v = *reinterpret_cast<const uint32_t *>(stage + c_off[e] + idx * 4u);
+                                ok = ok && ((v == c_val[e]) != (c_neq[e] != 0u));
+                            }
+                        }
+                        for (uint32_t e = 8; e < con_cnt; e++) {
+                            const uint32_t v = *reinterpret_cast<const uint32_t *>(stage + W.con_off[e] + idx * 4u);
+                            ok = ok && ((v == W.con_val[e]) != (W.con_neq[e] != 0u));
+                        }
+                        ok = ok && !f_never;
+                    }
+                    if (f_plat) {
+                        const uint32_t os = (meta >> 8) & 0xFFu, arch = (meta >> 16) & 0xFFu;
+                        bool pm = false;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint32_t po = plat[i] & 0xFFu, pa = (plat[i] >> 8) & 0xFFu;
+                            pm = pm || (plat[i] != 0xFFFFFFFFu && (pa == 0u || pa == arch) && (po == 0u || po == os));
+                        }
+                        for (uint32_t i = 4; i < G.plat_cnt; i++) {
+                            const pe_platform p = P.K.plats[G.plat_off + i];
+                            pm = pm || ((p.arch_id == 0u || p.arch_id == arch) && (p.os_id == 0u || p.os_id == os));
+                        }
+                        ok = ok && pm && (meta & PE_NODE_HAS_PLATFORM);
+                    }
+                    uint32_t fails = 0;
+                    if (HAS_EXTRA) {
+                        if (((fm >> PE_F_PLUGIN) & 1u) && (meta & PE_NODE_HAS_ENGINE)) {
+                            for (uint32_t i = 0; i < G.plug_cnt; i++) {
+                                const uint32_t sl = P.K.plugs[G.plug_off + i];
+                                const uint32_t wv = reinterpret_cast<const uint32_t *>(stage + (uint32_t)P.off_plugw[sl >> 5] * 16u)[idx];
+                                ok = ok && ((wv >> (sl & 31u)) & 1u);
+                            }
+                            if (G.flags & PE_G_LOG_DRIVER) {
+                                const uint32_t sl = G.log_plugin;
+                                const uint32_t wv = reinterpret_cast<const uint32_t *>(stage + (uint32_t)P.off_plugw[sl >> 5] * 16u)[idx];
+                                ok = ok && (((wv >> (sl & 31u)) & 1u) || !(meta & PE_NODE_HAS_LOGPLUGIN));
+                            }
+                        }
+                        if (f_con) {
+                            for (uint32_t i = 0; i < G.ip_cnt; i++) {
+                                const pe_ip_constraint c = P.K.ips[G.ip_off + i];
+                                bool hit = (meta & PE_NODE_IP_VALID) != 0;
+                                if (hit && c.is_cidr) hit = ((meta & PE_NODE_IP_V4) != 0) == (c.is_v4 != 0);
+                                if (hit) {
+                                    const uint4 a = reinterpret_cast<const uint4 *>(stage + P.off_ip)[idx];
+                                    hit = (a.x & c.mask[0]) == c.net[0] && (a.y & c.mask[1]) == c.net[1] &&
+                                          (a.z & c.mask[2]) == c.net[2] && (a.w & c.mask[3]) == c.net[3];
+                                }
+                                ok = ok && (hit != (c.neq != 0));
+                            }
+                        }
+                        if ((fm >> PE_F_HOSTPORT) & 1u) {
+                            for (uint32_t i = 0; i < G.port_cnt; i++) {
+                                const uint32_t sl = P.K.ports[G.port_off + i];
+                                const uint32_t wv = reinterpret_cast<const uint32_t *>(stage + (uint32_t)P.off_portw[sl >> 5] * 16u)[idx];
+                                ok = ok && !((wv >> (sl & 31u)) & 1u);
+                            }
+                        }
+                        if ((fm >> PE_F_MAXREPLICAS) & 1u) ok = ok && ((unsigned long long)svc_n < G.max_replicas);
+                        if (G.fail_cnt && n < N) fails = fail_count(P.K, G, n);
+                    }
+                    // rank prefix of nodeLess (scheduler.go:708-735)
+                    const unsigned long long pref = ok ? make_pref(fails, svc_n, s_total[idx]) : PE_PREF_NONE;
+                    if (__any_sync(0xFFFFFFFFu, pref < best)) {
+                        // a strictly better class starts here: everything emitted so far is stale
+                        const uint32_t hi = (uint32_t)(pref >> 32), lo = (uint32_t)pref;
+                        const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+                        const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
+                        best = ((unsigned long long)mh << 32) | ml;
+                        w0 = tile * steps + s;
+                        n_class = 0;
+                    }
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, ok && pref == best);
+                    n_class += __popc(word);
+                    if (lane == (s & 31u)) myword = word;
+                    if ((s & 31u) == 31u) Erow[tile * steps + (s & ~31u) + lane] = myword;
+                }
+            }
+            if (steps < 32u) {  // tiles shorter than 32 steps: flush what we have
+                if (lane < steps) Erow[tile * steps + lane] = myword;
+            }
+        }
+        __syncthreads();   // everyone is done with this stage before it is refilled
+    }
+    if (active && lane == 0) {
+        ScanResult r;
+        r.c0 = best;
+        r.w0 = w0;
+        r.n_class = n_class;
+        P.out[task] = r;
+    }
+}
+
+}  // namespace pe

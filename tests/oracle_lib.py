@@ -1,0 +1,33 @@
+"""Test-side access to the CPU oracle (oracle/).  Nothing in swarmkit_b200/ imports this."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+from swarmkit_b200.abi import FlatABI
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(ROOT, "oracle")
+
+
+def _make(target: str) -> str:
+    out = os.path.join(ORACLE, "_build", target)
+    res = subprocess.run(["make", "-C", ORACLE, os.path.join("_build", target)], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return out
+
+
+def build_flat() -> str:
+    return _make("liboracle_flat.so")
+
+
+def build_sched() -> str:
+    return _make("liboracle_sched.so")
+
+
+class OracleEngine(FlatABI):
+    """The flat CPU oracle behind the same ABI as the CUDA engine (prefix ope_)."""
+
+    def __init__(self, node_capacity: int = 0):
+        super().__init__(build_flat(), "ope_", node_capacity=node_capacity)
