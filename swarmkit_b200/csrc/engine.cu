@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -84,7 +85,7 @@ struct pe_engine {
     void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
 
     pe_stats stats{};
-    std::vector<EvPair> ev_pool; size_t ev_used = 0;
+    std::deque<EvPair> ev_pool; size_t ev_used = 0;  // deque: ev_begin hands out stable pointers
     bool timing = true;
 
     // =====================================================================
@@ -107,15 +108,28 @@ struct pe_engine {
         CU(cudaMalloc(&d_ctr, sizeof(DevCounters)));
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
         CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(16384)));
-        CU(cudaFuncSetAttribute(k_scan<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CU(cudaFuncSetAttribute(k_scan<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CU(cudaFuncSetAttribute(k_scan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CU(cudaFuncSetAttribute(k_scan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        for (auto fn : scan_variants()) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         int32_t rc = ensure_cap(cfg->node_capacity ? cfg->node_capacity : 1);
         if (rc) return rc;
         // the five fixed attribute columns always exist
         for (uint32_t c = 0; c < PE_ATTR_FIRST_LABEL; c++) { rc = ensure_col(attr, c, 4); if (rc) return rc; }
         return PE_OK;
+    }
+
+    typedef void (*ScanFn)(const ScanParams);
+    // [NE index 0/4/8/16][has_res][has_extra]
+    static ScanFn scan_fn(int ne_idx, bool res, bool extra) {
+        static ScanFn tab[4][2][2] = {
+            {{k_scan<0, false, false>, k_scan<0, false, true>}, {k_scan<0, true, false>, k_scan<0, true, true>}},
+            {{k_scan<4, false, false>, k_scan<4, false, true>}, {k_scan<4, true, false>, k_scan<4, true, true>}},
+            {{k_scan<8, false, false>, k_scan<8, false, true>}, {k_scan<8, true, false>, k_scan<8, true, true>}},
+            {{k_scan<16, false, false>, k_scan<16, false, true>}, {k_scan<16, true, false>, k_scan<16, true, true>}}};
+        return tab[ne_idx][res ? 1 : 0][extra ? 1 : 0];
+    }
+    static std::vector<ScanFn> scan_variants() {
+        std::vector<ScanFn> v;
+        for (int a = 0; a < 4; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 2; c++) v.push_back(scan_fn(a, b, c));
+        return v;
     }
 
     void destroy() {
@@ -495,15 +509,17 @@ struct pe_engine {
     // Plan one scan batch over groups [g0, g0+B): which columns ride in the
     // tile, the tile size, the kernel variant.  Returns false if the batch
     // needs something the scan path does not stage (sequencer handles it).
-    bool plan_scan(uint32_t g0, uint32_t B, ScanParams &P, bool &has_res, bool &has_extra, uint64_t &alg_bytes) {
+    bool plan_scan(uint32_t g0, uint32_t B, ScanParams &P, bool &has_res, bool &has_extra, uint64_t &alg_bytes, uint32_t &max_con) {
         std::vector<uint8_t> use_attr(attr.size(), 0), use_gen(gen.size(), 0), use_pw(ports.size(), 0), use_qw(plug.size(), 0);
         has_res = false; has_extra = false;
         bool use_ip = false;
         alg_bytes = 0;
+        max_con = 0;
         uint32_t seen_cols[PE_SCAN_MAXCON];
         for (uint32_t i = 0; i < B; i++) {
             const pe_group &g = groups[g0 + i];
             if (g.con_cnt > PE_SCAN_MAXCON) return false;
+            if ((g.filter_mask >> PE_F_CONSTRAINT) & 1u) max_con = std::max(max_con, g.con_cnt);
             uint64_t per_eval = 12;  // meta + total + per-service count
             uint32_t nseen = 0;
             for (uint32_t e = 0; e < g.con_cnt; e++) {
@@ -629,14 +645,13 @@ struct pe_engine {
                     ScanParams SP;
                     bool has_res, has_extra;
                     uint64_t alg = 0;
-                    if (plan_scan(b0, B, SP, has_res, has_extra, alg)) {
+                    uint32_t max_con = 0;
+                    if (plan_scan(b0, B, SP, has_res, has_extra, alg, max_con)) {
                         const uint32_t grid = (B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS;
                         const size_t dyn = 2 * (size_t)SP.stage_bytes;
                         EvPair *ev = ev_begin(0);
-                        if (has_res && has_extra) k_scan<true, true><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
-                        else if (has_res) k_scan<true, false><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
-                        else if (has_extra) k_scan<false, true><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
-                        else k_scan<false, false><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+                        const int ne_idx = max_con == 0 ? 0 : max_con <= 4 ? 1 : max_con <= 8 ? 2 : 3;
+                        scan_fn(ne_idx, has_res, has_extra)<<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
                         ev_end(ev);
                         CU(cudaGetLastError());
                         stats.kernel_launches++; stats.scan_launches++;

@@ -90,7 +90,10 @@ struct WarpTask {          // per-warp descriptor staged in shared memory
     uint32_t con_neq[PE_SCAN_MAXCON];
 };
 
-template <bool HAS_RES, bool HAS_EXTRA>
+// NE = constraint expressions kept in registers (0/4/8/16; the batch maximum
+// rounded up).  Unused slots compare the meta column against 0 with `!=`, which
+// every valid row passes, so the loop has no per-expression branch.
+template <int NE, bool HAS_RES, bool HAS_EXTRA>
 __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_constant__ ScanParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
             const pe_constraint c = P.K.cons[W.G.con_off + i];
             W.con_off[i] = (uint32_t)P.off_attr[c.col] * 16u;
             W.con_val[i] = c.value;
-            W.con_neq[i] = c.neq;
+            W.con_neq[i] = c.neq ? 1u : 0u;
         }
     }
     __syncthreads();
@@ -140,26 +143,32 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
     const bool f_plat = ((fm >> PE_F_PLATFORM) & 1u) && G.plat_cnt > 0;
     const bool f_con = (fm >> PE_F_CONSTRAINT) & 1u;
     const bool f_never = f_con && (G.flags & PE_G_CONSTRAINT_NEVER);
-    const uint32_t *svccol = active ? P.svc[G.svc_id] : nullptr;
-    // up to 4 platforms kept in registers (os | arch << 8)
-    uint32_t plat[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    if (active && f_plat)
-        for (uint32_t i = 0; i < 4 && i < G.plat_cnt; i++) {
-            const pe_platform p = P.K.plats[G.plat_off + i];
-            plat[i] = p.os_id | (p.arch_id << 8);
-        }
-    // first 8 constraint expressions in registers
-    uint32_t c_off[8], c_val[8], c_neq[8];
+    const uint32_t *svccol = active ? P.svc[G.svc_id] : P.svc[0];
+    // PlatformFilter patterns on the meta word: has_platform (bit 2), os (8..15), arch (16..23).
+    // pattern i matches iff ((meta ^ pv[i]) & pm[i]) == 0; an unused slot tests the VALID bit against 0.
+    uint32_t pm[4], pv[4];
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const bool on = (uint32_t)e < con_cnt;
-        c_off[e] = on ? W.con_off[e] : 0u;
-        c_val[e] = on ? W.con_val[e] : 0u;
-        c_neq[e] = on ? W.con_neq[e] : 0u;
+    for (int i = 0; i < 4; i++) {
+        pm[i] = PE_NODE_VALID; pv[i] = 0;
+        if (active && f_plat && (uint32_t)i < G.plat_cnt) {
+            const pe_platform p = P.K.plats[G.plat_off + i];
+            pm[i] = PE_NODE_HAS_PLATFORM | (p.os_id ? 0xFF00u : 0u) | (p.arch_id ? 0xFF0000u : 0u);
+            pv[i] = PE_NODE_HAS_PLATFORM | (p.os_id << 8) | (p.arch_id << 16);
+        }
     }
+    // constraint expressions in registers: stage offset (+ lane), value, neq
+    uint32_t c_off[NE > 0 ? NE : 1], c_val[NE > 0 ? NE : 1], c_neq[NE > 0 ? NE : 1];
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+        const bool on = f_con && (uint32_t)e < con_cnt;
+        c_off[e] = (on ? W.con_off[e] : P.off_meta) + lane * 4u;
+        c_val[e] = on ? W.con_val[e] : 0u;
+        c_neq[e] = on ? W.con_neq[e] : 1u;
+    }
+    const uint32_t o_meta = P.off_meta + lane * 4u, o_total = P.off_total + lane * 4u;
 
-    unsigned long long best = PE_PREF_NONE;
-    uint32_t w0 = 0, n_class = 0, myword = 0;
+    uint32_t best_hi = 0xFFFFFFFFu, best_lo = 0xFFFFFFFFu;
+    uint32_t w0 = 0, myword = 0;
     uint32_t *Erow = P.E + (size_t)task * P.e_stride;
     const uint32_t steps = TN >> 5;
 
@@ -173,81 +182,76 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
         mbar_wait(&full_bar[cur], (tile >> 1) & 1u);
 
         if (active) {
-            const uint32_t *s_meta = reinterpret_cast<const uint32_t *>(stage + P.off_meta);
-            const uint32_t *s_total = reinterpret_cast<const uint32_t *>(stage + P.off_total);
             const uint32_t tile_base = tile * TN;
+            const uint32_t rem = N - tile_base;          // rows of this tile that exist (>= TN except on the last tile)
+            const uint32_t *svcp = svccol + tile_base + lane;
             for (uint32_t sb = 0; sb < steps; sb += 8) {
-                // per-service counts come straight from L2 (one column per service):
-                // issue 8 independent loads, then consume
+                // per-service counts come straight from L2 (one column per service; the
+                // column is padded like every other, so no bounds check): 8 loads in flight
                 uint32_t svcv[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const uint32_t n = tile_base + (sb + u) * 32u + lane;
-                    svcv[u] = n < N ? svccol[n] : 0u;
-                }
+                for (int u = 0; u < 8; u++) svcv[u] = svcp[(sb + u) * 32u];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     const uint32_t s = sb + u;
-                    const uint32_t idx = s * 32u + lane;
-                    const uint32_t n = tile_base + idx;
-                    const uint32_t meta = s_meta[idx];
+                    const unsigned char *row = stage + s * 128u;
+                    const uint32_t meta = *reinterpret_cast<const uint32_t *>(row + o_meta);
                     const uint32_t svc_n = svcv[u];
-                    // ReadyFilter (always enabled, filter.go:35-43); rows past N / removed nodes are not in the set
-                    bool ok = (meta & (PE_NODE_VALID | PE_NODE_READY)) == (PE_NODE_VALID | PE_NODE_READY) && n < N;
-                    if (HAS_RES && ((fm >> PE_F_RESOURCE) & 1u)) {
-                        const long long cpu = reinterpret_cast<const long long *>(stage + P.off_cpu)[idx];
-                        const long long mem = reinterpret_cast<const long long *>(stage + P.off_mem)[idx];
-                        ok = ok && !(G.cpu_res > cpu) && !(G.mem_res > mem);
-                        for (uint32_t i = 0; i < G.gen_cnt; i++) {
-                            const pe_generic_want w = P.K.gens[G.gen_off + i];
-                            const long long cell = reinterpret_cast<const long long *>(stage + (uint32_t)P.off_gen[w.kind] * 16u)[idx];
-                            ok = ok && gen_enough(cell, w.value);
-                        }
+                    // ReadyFilter (filter.go:40-43) + membership: VALID and READY both set, row < N
+                    uint32_t bad = (meta & (PE_NODE_VALID | PE_NODE_READY)) ^ (PE_NODE_VALID | PE_NODE_READY);
+                    bad |= (s * 32u + lane < rem) ? 0u : 1u;
+                    // ConstraintFilter (constraint.go:84-104): fail = (value differs) xor neq
+#pragma unroll
+                    for (int e = 0; e < NE; e++) {
+                        const uint32_t v = *reinterpret_cast<const uint32_t *>(row + c_off[e]);
+                        const uint32_t nz = min(v ^ c_val[e], 1u);
+                        bad |= nz ^ c_neq[e];
                     }
                     if (f_con) {
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            if ((uint32_t)e < con_cnt) {
-                                const uint32_t v = *reinterpret_cast<const uint32_t *>(stage + c_off[e] + idx * 4u);
-                                ok = ok && ((v == c_val[e]) != (c_neq[e] != 0u));
-                            }
+                        for (uint32_t e = NE; e < con_cnt; e++) {
+                            const uint32_t v = *reinterpret_cast<const uint32_t *>(row + W.con_off[e] + lane * 4u);
+                            bad |= min(v ^ W.con_val[e], 1u) ^ W.con_neq[e];
                         }
-                        for (uint32_t e = 8; e < con_cnt; e++) {
-                            const uint32_t v = *reinterpret_cast<const uint32_t *>(stage + W.con_off[e] + idx * 4u);
-                            ok = ok && ((v == W.con_val[e]) != (W.con_neq[e] != 0u));
-                        }
-                        ok = ok && !f_never;
+                        bad |= f_never ? 1u : 0u;
                     }
-                    if (f_plat) {
-                        const uint32_t os = (meta >> 8) & 0xFFu, arch = (meta >> 16) & 0xFFu;
-                        bool pm = false;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const uint32_t po = plat[i] & 0xFFu, pa = (plat[i] >> 8) & 0xFFu;
-                            pm = pm || (plat[i] != 0xFFFFFFFFu && (pa == 0u || pa == arch) && (po == 0u || po == os));
-                        }
+                    if (f_plat) {   // PlatformFilter, filter.go:272-312
+                        uint32_t m = min(min((meta ^ pv[0]) & pm[0], (meta ^ pv[1]) & pm[1]), min((meta ^ pv[2]) & pm[2], (meta ^ pv[3]) & pm[3]));
                         for (uint32_t i = 4; i < G.plat_cnt; i++) {
                             const pe_platform p = P.K.plats[G.plat_off + i];
-                            pm = pm || ((p.arch_id == 0u || p.arch_id == arch) && (p.os_id == 0u || p.os_id == os));
+                            const uint32_t qm = PE_NODE_HAS_PLATFORM | (p.os_id ? 0xFF00u : 0u) | (p.arch_id ? 0xFF0000u : 0u);
+                            const uint32_t qv = PE_NODE_HAS_PLATFORM | (p.os_id << 8) | (p.arch_id << 16);
+                            m = min(m, (meta ^ qv) & qm);
                         }
-                        ok = ok && pm && (meta & PE_NODE_HAS_PLATFORM);
+                        bad |= m;
+                    }
+                    if (HAS_RES && ((fm >> PE_F_RESOURCE) & 1u)) {   // ResourceFilter, filter.go:76-93
+                        const long long cpu = *reinterpret_cast<const long long *>(stage + P.off_cpu + (s * 32u + lane) * 8u);
+                        const long long mem = *reinterpret_cast<const long long *>(stage + P.off_mem + (s * 32u + lane) * 8u);
+                        bad |= (G.cpu_res > cpu) ? 1u : 0u;
+                        bad |= (G.mem_res > mem) ? 1u : 0u;
+                        for (uint32_t i = 0; i < G.gen_cnt; i++) {
+                            const pe_generic_want w = P.K.gens[G.gen_off + i];
+                            const long long cell = *reinterpret_cast<const long long *>(stage + (uint32_t)P.off_gen[w.kind] * 16u + (s * 32u + lane) * 8u);
+                            bad |= gen_enough(cell, w.value) ? 0u : 1u;
+                        }
                     }
                     uint32_t fails = 0;
                     if (HAS_EXTRA) {
-                        if (((fm >> PE_F_PLUGIN) & 1u) && (meta & PE_NODE_HAS_ENGINE)) {
+                        const uint32_t idx = s * 32u + lane;
+                        if (((fm >> PE_F_PLUGIN) & 1u) && (meta & PE_NODE_HAS_ENGINE)) {   // PluginFilter, filter.go:141-183
                             for (uint32_t i = 0; i < G.plug_cnt; i++) {
                                 const uint32_t sl = P.K.plugs[G.plug_off + i];
                                 const uint32_t wv = reinterpret_cast<const uint32_t *>(stage + (uint32_t)P.off_plugw[sl >> 5] * 16u)[idx];
-                                ok = ok && ((wv >> (sl & 31u)) & 1u);
+                                bad |= ((wv >> (sl & 31u)) & 1u) ^ 1u;
                             }
                             if (G.flags & PE_G_LOG_DRIVER) {
                                 const uint32_t sl = G.log_plugin;
                                 const uint32_t wv = reinterpret_cast<const uint32_t *>(stage + (uint32_t)P.off_plugw[sl >> 5] * 16u)[idx];
-                                ok = ok && (((wv >> (sl & 31u)) & 1u) || !(meta & PE_NODE_HAS_LOGPLUGIN));
+                                bad |= (((wv >> (sl & 31u)) & 1u) || !(meta & PE_NODE_HAS_LOGPLUGIN)) ? 0u : 1u;
                             }
                         }
                         if (f_con) {
-                            for (uint32_t i = 0; i < G.ip_cnt; i++) {
+                            for (uint32_t i = 0; i < G.ip_cnt; i++) {    // node.ip, constraint.go:127-146
                                 const pe_ip_constraint c = P.K.ips[G.ip_off + i];
                                 bool hit = (meta & PE_NODE_IP_VALID) != 0;
                                 if (hit && c.is_cidr) hit = ((meta & PE_NODE_IP_V4) != 0) == (c.is_v4 != 0);
@@ -256,32 +260,33 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
                                     hit = (a.x & c.mask[0]) == c.net[0] && (a.y & c.mask[1]) == c.net[1] &&
                                           (a.z & c.mask[2]) == c.net[2] && (a.w & c.mask[3]) == c.net[3];
                                 }
-                                ok = ok && (hit != (c.neq != 0));
+                                bad |= (hit != (c.neq != 0)) ? 0u : 1u;
                             }
                         }
-                        if ((fm >> PE_F_HOSTPORT) & 1u) {
+                        if ((fm >> PE_F_HOSTPORT) & 1u) {               // HostPortFilter, filter.go:342-353
                             for (uint32_t i = 0; i < G.port_cnt; i++) {
                                 const uint32_t sl = P.K.ports[G.port_off + i];
                                 const uint32_t wv = reinterpret_cast<const uint32_t *>(stage + (uint32_t)P.off_portw[sl >> 5] * 16u)[idx];
-                                ok = ok && !((wv >> (sl & 31u)) & 1u);
+                                bad |= (wv >> (sl & 31u)) & 1u;
                             }
                         }
-                        if ((fm >> PE_F_MAXREPLICAS) & 1u) ok = ok && ((unsigned long long)svc_n < G.max_replicas);
-                        if (G.fail_cnt && n < N) fails = fail_count(P.K, G, n);
+                        if ((fm >> PE_F_MAXREPLICAS) & 1u) bad |= ((unsigned long long)svc_n < G.max_replicas) ? 0u : 1u;   // filter.go:379-381
+                        if (G.fail_cnt && !bad) fails = fail_count(P.K, G, tile_base + idx);
                     }
-                    // rank prefix of nodeLess (scheduler.go:708-735)
-                    const unsigned long long pref = ok ? make_pref(fails, svc_n, s_total[idx]) : PE_PREF_NONE;
-                    if (__any_sync(0xFFFFFFFFu, pref < best)) {
+                    // rank prefix of nodeLess (scheduler.go:708-735): hi = (f5 << 24) | svc, lo = total
+                    const bool ok = bad == 0u;
+                    uint32_t hi = svc_n & 0xFFFFFFu;
+                    if (HAS_EXTRA) hi |= (fails >= 5u ? (fails > 255u ? 255u : fails) : 0u) << 24;
+                    const uint32_t lo = *reinterpret_cast<const uint32_t *>(row + o_total);
+                    const bool better = ok & ((hi < best_hi) | ((hi == best_hi) & (lo < best_lo)));
+                    if (__any_sync(0xFFFFFFFFu, better)) {
                         // a strictly better class starts here: everything emitted so far is stale
-                        const uint32_t hi = (uint32_t)(pref >> 32), lo = (uint32_t)pref;
-                        const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
-                        const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
-                        best = ((unsigned long long)mh << 32) | ml;
+                        const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, ok ? hi : 0xFFFFFFFFu);
+                        const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, (ok && hi == mh) ? lo : 0xFFFFFFFFu);
+                        best_hi = mh; best_lo = ml;
                         w0 = tile * steps + s;
-                        n_class = 0;
                     }
-                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, ok && pref == best);
-                    n_class += __popc(word);
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, ok & (hi == best_hi) & (lo == best_lo));
                     if (lane == (s & 31u)) myword = word;
                     if ((s & 31u) == 31u) Erow[tile * steps + (s & ~31u) + lane] = myword;
                 }
@@ -294,9 +299,9 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
     }
     if (active && lane == 0) {
         ScanResult r;
-        r.c0 = best;
+        r.c0 = (best_hi == 0xFFFFFFFFu && best_lo == 0xFFFFFFFFu) ? PE_PREF_NONE : (((unsigned long long)best_hi << 32) | best_lo);
         r.w0 = w0;
-        r.n_class = n_class;
+        r.n_class = 0;
         P.out[task] = r;
     }
 }

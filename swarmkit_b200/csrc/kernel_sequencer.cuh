@@ -16,10 +16,13 @@
 //    and left the bitmap of its best rank class.  Within a batch node state only
 //    gets worse, so the first class member not yet touched in this batch is the
 //    sequentially-correct argmin; it is found with one masked find-first over the
-//    bitmap.
-//  * generic path (any k; also the fall-back when the class was consumed): full
-//    table evaluation against the live state, radix-select of the k smallest rank
-//    keys, bitonic sort, sequential fill on staged rows, parallel write-back.
+//    bitmap.  Tasks are taken in chunks: descriptors and the first 32k-node
+//    window of each bitmap are staged in shared memory together, so the ordered
+//    part touches shared memory only.
+//  * generic path (any k; also the fall-back when a class was consumed): full
+//    table evaluation against the live state; k == 1: block arg-min; k > 1:
+//    radix-select of the k smallest rank keys, bitonic sort, sequential fill on
+//    staged rows, parallel write-back.
 #pragma once
 #include "kernels_common.cuh"
 
@@ -36,7 +39,10 @@ __device__ __forceinline__ bool key_less(const CandKey &a, const CandKey &b) {
 
 #define PE_SEQ_THREADS 1024
 #define PE_SEQ_KS 2048          // candidates staged in shared memory
+#define PE_SEQ_CHUNK 8          // k=1 tasks staged together on the fast path
+#define PE_SEQ_WIN 1024         // bitmap words staged per task (32k nodes)
 #define PE_MAX_GEN_WANTS 8
+#define PE_CTX_MAXC 16
 #define PE_ST_FAILED 1u
 #define PE_ST_BLOCKED 2u
 
@@ -61,13 +67,35 @@ struct SeqParams {
     DevCounters *ctr;
 };
 
+// Per-group evaluation context resolved once into shared memory so that a node
+// evaluation is one level of independent global loads.
+struct GroupCtx {
+    uint32_t *svccol;
+    const uint32_t *con_col[PE_CTX_MAXC];
+    uint32_t con_val[PE_CTX_MAXC];
+    uint32_t con_neq[PE_CTX_MAXC];
+    uint32_t usable;   // 1: every constraint is staged here (con_cnt <= PE_CTX_MAXC)
+};
+
+struct FastTask {      // staged descriptor of one k=1 task
+    unsigned long long c0;
+    long long cpu_res, mem_res;
+    uint32_t *svccol;
+    uint32_t w0, tie_start, task_off, simple, counts, ws;
+};
+
 struct SeqShared {
     pe_group G;
+    GroupCtx C;
+    FastTask ft[PE_SEQ_CHUNK];
     uint32_t red32[40];
     unsigned long long red64[40];
     uint32_t bins[256];
     uint32_t cnt8[8];
-    uint32_t best, sel_bin, sel_before, ncand, neutral, any_pass, done, dead;
+    uint32_t bestv[3];   // rotating slots: see block_min_pos
+    uint32_t sel_bin, sel_before, ncand, neutral, any_pass, done, dead;
+    unsigned long long best_pref;
+    uint32_t best_tie;
 };
 
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, SeqShared &S) {
@@ -113,12 +141,24 @@ __device__ __forceinline__ void block_or_and(unsigned long long &o64, unsigned l
     o64 = O; a64 = A; o32 = Ot; a32 = At;
 }
 
-// First set bit of (E & ~touched) in tie order, restricted to words >= w0.
-__device__ __forceinline__ uint32_t find_first(const uint32_t *Erow, uint32_t w0, uint32_t N, uint32_t ts,
-                                               const uint32_t *touched, SeqShared &S) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) S.best = PE_NONE;
+// Block-wide minimum of a candidate position; every thread gets the result.
+// Three rotating slots make it safe with ONE barrier per call: the slot used
+// by call i is re-armed during call i+1 (after that call's barrier) and used
+// again by call i+3, so a re-arm can never race with an atomicMin or a read.
+__device__ __forceinline__ uint32_t block_min_pos(uint32_t c, SeqShared &S, uint32_t &slot) {
+    c = __reduce_min_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0 && c != PE_NONE) atomicMin(&S.bestv[slot], c);
     __syncthreads();
+    const uint32_t r = S.bestv[slot];
+    const uint32_t prev = slot == 0 ? 2u : slot - 1u;
+    if (threadIdx.x == 0) S.bestv[prev] = PE_NONE;
+    slot = slot == 2 ? 0u : slot + 1u;
+    return r;
+}
+
+// First set bit of (E & ~touched) in tie order, restricted to words >= w0 (global-memory walk).
+__device__ __forceinline__ uint32_t find_first(const uint32_t *Erow, uint32_t w0, uint32_t N, uint32_t ts,
+                                               const uint32_t *touched, SeqShared &S, uint32_t &slot) {
     const uint32_t base_bit = w0 * 32u;
     for (int seg = 0; seg < 2; seg++) {
         uint32_t lo_bit, hi_bit;
@@ -134,15 +174,44 @@ __device__ __forceinline__ uint32_t find_first(const uint32_t *Erow, uint32_t w0
                 if (w == wlo) v &= 0xFFFFFFFFu << (lo_bit & 31u);
                 if (w == whi - 1 && (hi_bit & 31u)) v &= (1u << (hi_bit & 31u)) - 1u;
             }
-            uint32_t c = v ? w * 32u + (uint32_t)__ffs((int)v) - 1u : PE_NONE;
-            c = __reduce_min_sync(0xFFFFFFFFu, c);
-            if (lane == 0 && c != PE_NONE) atomicMin(&S.best, c);
-            __syncthreads();
-            const uint32_t b = S.best;
+            const uint32_t b = block_min_pos(v ? w * 32u + (uint32_t)__ffs((int)v) - 1u : PE_NONE, S, slot);
             if (b != PE_NONE) return b;
         }
     }
     return PE_NONE;
+}
+
+// Pipeline.Process for one node with the constraint columns pre-resolved.
+__device__ __forceinline__ uint32_t eval_ctx(const DevTable &T, const TickDev &K, const pe_group &g, const GroupCtx &C, uint32_t n,
+                                             uint32_t meta, uint32_t svc_n) {
+    if (!C.usable || (g.filter_mask & ~((1u << PE_F_READY) | (1u << PE_F_CONSTRAINT) | (1u << PE_F_PLATFORM))) || g.ip_cnt ||
+        (g.flags & PE_G_CONSTRAINT_NEVER))
+        return eval_ff(T, K, g, n, meta, svc_n);
+    // common case: Ready + attribute constraints + platform, all loads independent
+    if ((g.filter_mask & (1u << PE_F_READY)) && !(meta & PE_NODE_READY)) return 1 + PE_F_READY;
+    if (g.filter_mask & (1u << PE_F_CONSTRAINT)) {
+        uint32_t v[PE_CTX_MAXC];
+        const uint32_t cc = g.con_cnt;
+#pragma unroll
+        for (int e = 0; e < PE_CTX_MAXC; e++) v[e] = (uint32_t)e < cc ? C.con_col[e][n] : 0u;
+        bool ok = true;
+#pragma unroll
+        for (int e = 0; e < PE_CTX_MAXC; e++)
+            if ((uint32_t)e < cc) ok = ok && ((v[e] == C.con_val[e]) != (C.con_neq[e] != 0u));
+        if (!ok) return 1 + PE_F_CONSTRAINT;
+    }
+    if ((g.filter_mask & (1u << PE_F_PLATFORM)) && g.plat_cnt) {
+        bool ok = false;
+        if (meta & PE_NODE_HAS_PLATFORM) {
+            const uint32_t os = (meta >> 8) & 0xFF, arch = (meta >> 16) & 0xFF;
+            for (uint32_t i = 0; i < g.plat_cnt && !ok; i++) {
+                const pe_platform p = K.plats[g.plat_off + i];
+                ok = (p.arch_id == 0 || p.arch_id == arch) && (p.os_id == 0 || p.os_id == os);
+            }
+        }
+        if (!ok) return 1 + PE_F_PLATFORM;
+    }
+    return 0;
 }
 
 __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_constant__ SeqParams P) {
@@ -165,12 +234,89 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     uint8_t *st_flags_s = reinterpret_cast<uint8_t *>(st_placed_s + PE_SEQ_KS);
     uint32_t *touched_s = reinterpret_cast<uint32_t *>(st_flags_s + PE_SEQ_KS);
     uint32_t *touched = P.touched_in_smem ? touched_s : P.touched_g;
+    // the fast path's bitmap windows alias the candidate staging area (never live at the same time)
+    uint32_t *ebuf = reinterpret_cast<uint32_t *>(dyn_smem);
 
     for (uint32_t w = tid; w < P.touched_words; w += nth) touched[w] = 0;
-    if (tid == 0) S.neutral = 0;
+    if (tid == 0) { S.neutral = 0; S.bestv[0] = S.bestv[1] = S.bestv[2] = PE_NONE; }
+    uint32_t slot = 0;   // uniform across the block
+    unsigned long long n_fast = 0, n_slow = 0, n_placed = 0, n_evalg = 0;   // thread 0's private tallies
     __syncthreads();
 
-    for (uint32_t gi = P.g_begin; gi < P.g_end; gi++) {
+    uint32_t gi = P.g_begin;
+    while (gi < P.g_end) {
+        // ================= fast path: a chunk of k == 1 tasks =====================
+        if (P.scan != nullptr && !S.neutral) {
+            const uint32_t C = min((uint32_t)PE_SEQ_CHUNK, P.g_end - gi);
+            __syncthreads();
+            if (tid < C) {   // level A: descriptors
+                const pe_group g = K.groups[gi + tid];
+                const ScanResult sr = P.scan[gi + tid - P.g_begin];
+                FastTask f;
+                f.c0 = g.n_tasks == 1 ? sr.c0 : PE_PREF_NONE;
+                f.w0 = sr.w0;
+                f.tie_start = g.tie_start;
+                f.task_off = g.task_off;
+                f.cpu_res = g.cpu_res; f.mem_res = g.mem_res;
+                f.simple = (g.gen_cnt == 0 && g.port_cnt == 0) ? 1u : 0u;
+                f.counts = g.n_tasks == 1 ? (K.task_flags[g.task_off] & PE_T_COUNTS) : 0u;
+                f.svccol = T.svc[g.svc_id];
+                const uint32_t lo_bit = max(g.tie_start, sr.w0 * 32u);
+                f.ws = lo_bit >> 5;
+                S.ft[tid] = f;
+            }
+            __syncthreads();
+            // level B: the first PE_SEQ_WIN words of every class bitmap in the chunk
+            for (uint32_t c = 0; c < C; c++) {
+                const FastTask &f = S.ft[c];
+                const uint32_t w = f.ws + tid;
+                uint32_t v = 0;
+                if (f.c0 != PE_PREF_NONE && w < ((N + 31u) >> 5)) v = P.E[(size_t)(gi + c - P.g_begin) * P.e_stride + w];
+                ebuf[c * PE_SEQ_WIN + tid] = v;
+            }
+            __syncthreads();
+            uint32_t c = 0;
+            for (; c < C; c++) {
+                const FastTask &f = S.ft[c];
+                if (f.c0 == PE_PREF_NONE) break;          // nothing feasible at batch start (or k != 1): generic path
+                const uint32_t lo_bit = max(f.tie_start, f.w0 * 32u);
+                const uint32_t w = f.ws + tid;
+                uint32_t v = 0;
+                if (w < ((N + 31u) >> 5)) {
+                    v = ebuf[c * PE_SEQ_WIN + tid] & ~touched[w];
+                    if (tid == 0) v &= 0xFFFFFFFFu << (lo_bit & 31u);
+                    if (w == ((N + 31u) >> 5) - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
+                }
+                uint32_t n = block_min_pos(v ? w * 32u + (uint32_t)__ffs((int)v) - 1u : PE_NONE, S, slot);
+                if (n == PE_NONE) {
+                    // not inside the staged window: walk the rest of the bitmap (wraps when the tie order is rotated)
+                    n = find_first(P.E + (size_t)(gi + c - P.g_begin) * P.e_stride, f.w0, N, f.tie_start, touched, S, slot);
+                    if (n == PE_NONE) break;              // class consumed in this batch: generic path
+                }
+                if (tid == 0) {
+                    K.out_node[f.task_off] = n;
+                    if (f.simple) {                        // NodeInfo.addTask, nodeinfo.go:125-153, as fire-and-forget reductions
+                        if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-f.cpu_res));
+                        if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-f.mem_res));
+                        if (f.counts) { atomicAdd(&T.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
+                    } else {
+                        add_task_global(T, K, K.groups[gi + c], n, f.counts != 0, P.ctr);
+                    }
+                    touched[n >> 5] |= 1u << (n & 31u);
+                    if (!f.counts) S.neutral = 1;          // rank did not move: later class bitmaps may hide this node
+                    n_fast++; n_placed++;
+                }
+                if (tid < 8) K.out_fail[(size_t)(gi + c) * PE_NUM_FILTERS + tid] = 0;
+                __syncthreads();
+                if (S.neutral) { c++; break; }
+            }
+            gi += c;
+            if (c == C) continue;                          // whole chunk placed from the bitmaps
+            if (gi >= P.g_end) break;
+            // fall through: group gi takes the generic path
+        }
+
+        // ================= generic path (one group) ===============================
         __syncthreads();
         if (tid < sizeof(pe_group) / 4) reinterpret_cast<uint32_t *>(&S.G)[tid] = reinterpret_cast<const uint32_t *>(&K.groups[gi])[tid];
         if (tid < 8) S.cnt8[tid] = 0;
@@ -178,32 +324,79 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
         const pe_group &G = S.G;
         const uint32_t k = G.n_tasks;
         uint32_t *ofail = K.out_fail + (size_t)gi * PE_NUM_FILTERS;
+        const uint32_t this_gi = gi;
+        gi++;
         if (k == 0) { if (tid < 8) ofail[tid] = 0; continue; }
-        uint32_t *svccol = T.svc[G.svc_id];
+        // resolve the evaluation context
+        if (tid < PE_CTX_MAXC && tid < G.con_cnt) {
+            const pe_constraint c = K.cons[G.con_off + tid];
+            S.C.con_col[tid] = T.attr[c.col];
+            S.C.con_val[tid] = c.value;
+            S.C.con_neq[tid] = c.neq;
+        }
+        if (tid == 32) { S.C.svccol = T.svc[G.svc_id]; S.C.usable = G.con_cnt <= PE_CTX_MAXC ? 1u : 0u; }
+        __syncthreads();
+        uint32_t *svccol = S.C.svccol;
 
-        // ================= fast path ==========================================
-        if (P.scan != nullptr && k == 1 && !S.neutral) {
-            const ScanResult sr = P.scan[gi - P.g_begin];
-            if (sr.c0 != PE_PREF_NONE) {
-                const uint32_t *Erow = P.E + (size_t)(gi - P.g_begin) * P.e_stride;
-                const uint32_t n = find_first(Erow, sr.w0, N, G.tie_start, touched, S);
-                if (n != PE_NONE) {
-                    if (tid == 0) {
-                        const bool counts = (K.task_flags[G.task_off] & PE_T_COUNTS) != 0;
-                        K.out_node[G.task_off] = n;
-                        add_task_global(T, K, G, n, counts, P.ctr);
-                        touched[n >> 5] |= 1u << (n & 31u);
-                        if (!counts) S.neutral = 1;  // rank did not move: later class bitmaps may hide this node
-                        P.ctr->fast_path++;
-                        P.ctr->placements++;
-                    }
-                    if (tid < 8) ofail[tid] = 0;
-                    continue;
+        if (k == 1) {
+            // ---- one task: block arg-min over the live table (nodeset.go:107-120 with a heap of one)
+            unsigned long long bp = ~0ull;
+            uint32_t bt = ~0u, bn = PE_NONE, myF = 0;
+            uint32_t c[PE_NUM_FILTERS];
+            for (int f = 0; f < PE_NUM_FILTERS; f++) c[f] = 0;
+#pragma unroll 2
+            for (uint32_t n = tid; n < N; n += nth) {
+                const uint32_t meta = T.meta[n];
+                if (!(meta & PE_NODE_VALID)) continue;
+                const uint32_t sv = svccol[n];
+                const uint32_t tot = T.total[n];
+                const uint32_t ff = eval_ctx(T, K, G, S.C, n, meta, sv);
+                for (int f = 0; f < PE_NUM_FILTERS; f++) c[f] += (ff == (uint32_t)(f + 1));
+                if (ff == 0) {
+                    const uint32_t fails = G.fail_cnt ? fail_count(K, G, n) : 0u;
+                    const unsigned long long pref = make_pref(fails, sv, tot);
+                    const uint32_t tp = tie_pos(n, G.tie_start, N);
+                    myF++;
+                    if (pref < bp || (pref == bp && tp < bt)) { bp = pref; bt = tp; bn = n; }
                 }
             }
+            // block arg-min on (pref, tie)
+            const uint32_t hi = (uint32_t)(bp >> 32), lo = (uint32_t)bp;
+            uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+            uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
+            uint32_t mt = __reduce_min_sync(0xFFFFFFFFu, (hi == mh && lo == ml) ? bt : 0xFFFFFFFFu);
+            if (lane == 0) { S.red64[warp] = ((unsigned long long)mh << 32) | ml; S.red32[warp] = mt; }
+            for (int f = 0; f < PE_NUM_FILTERS; f++) {
+                const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, c[f]);
+                if (lane == 0 && s) atomicAdd(&S.cnt8[f], s);
+            }
+            __syncthreads();
+            unsigned long long gp = ~0ull; uint32_t gt = ~0u;
+            for (uint32_t w = 0; w < (nth >> 5); w++) {
+                const unsigned long long p = S.red64[w]; const uint32_t t = S.red32[w];
+                if (p < gp || (p == gp && t < gt)) { gp = p; gt = t; }
+            }
+            const bool mine = bn != PE_NONE && bp == gp && bt == gt;   // unique: tie positions are distinct
+            if (gp == ~0ull) {
+                if (tid == 0) { K.out_node[G.task_off] = PE_NONE; n_slow++; n_evalg += N; }
+                __syncthreads();
+                if (tid < 8) ofail[tid] = S.cnt8[tid];
+            } else {
+                if (mine) {
+                    const bool counts = (K.task_flags[G.task_off] & PE_T_COUNTS) != 0;
+                    K.out_node[G.task_off] = bn;
+                    add_task_global(T, K, G, bn, counts, P.ctr);
+                    if (P.touched_words) atomicOr(&touched[bn >> 5], 1u << (bn & 31u));
+                    if (!counts) S.neutral = 1;
+                }
+                if (tid == 0) { n_slow++; n_placed++; n_evalg += N; }
+                if (tid < 8) ofail[tid] = 0;
+            }
+            (void)myF; (void)this_gi;
+            __syncthreads();
+            continue;
         }
 
-        // ================= generic path =======================================
         // ---- 1. evaluate every node against the live state (nodeset.go:57-121)
         uint32_t myF = 0;
         unsigned long long o64 = 0, a64 = ~0ull;
@@ -212,7 +405,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             const uint32_t meta = T.meta[n];
             if (!(meta & PE_NODE_VALID)) { P.ff8[n] = 0xFF; continue; }
             const uint32_t sv = svccol[n];
-            const uint32_t ff = eval_ff(T, K, G, n, meta, sv);
+            const uint32_t ff = eval_ctx(T, K, G, S.C, n, meta, sv);
             const uint32_t fails = G.fail_cnt ? fail_count(K, G, n) : 0u;
             const unsigned long long pref = make_pref(fails, sv, T.total[n]);
             P.ff8[n] = (uint8_t)ff;
@@ -224,7 +417,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             }
         }
         const uint32_t F = block_sum(myF, S);
-        if (tid == 0) { P.ctr->evals_generic += N; P.ctr->slow_path++; }
+        if (tid == 0) { n_evalg += N; n_slow++; }
         const uint32_t m = F < k ? F : k;
 
         // ---- 2. radix-select the k-th smallest (pref, tie) key among feasible nodes
@@ -271,10 +464,10 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                     }
                     const uint32_t excl = incl - sum;
                     if (rank > excl && rank <= incl) {
-                        uint32_t c = excl;
+                        uint32_t cc = excl;
                         for (int j = 0; j < 8; j++) {
-                            if (rank <= c + loc[j]) { S.sel_bin = lane * 8 + j; S.sel_before = c; break; }
-                            c += loc[j];
+                            if (rank <= cc + loc[j]) { S.sel_bin = lane * 8 + j; S.sel_before = cc; break; }
+                            cc += loc[j];
                         }
                     }
                 }
@@ -408,7 +601,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             S.any_pass = any_pass;
             if (neutral) S.neutral = 1;
             for (int f = 0; f < PE_NUM_FILTERS; f++) S.cnt8[f] = cnt[f];
-            P.ctr->placements += done;
+            n_placed += done;
         }
         __syncthreads();
         const uint32_t done = S.done;
@@ -421,7 +614,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             T.mem[n] = st_mem[i];
             T.total[n] = st_tot[i];
             svccol[n] = st_svc[i];
-            if (st_svc[i] >= 0xFFFFFFu) atomicOr(&P.ctr->error, PE_DEV_ERR_SVC_OVERFLOW);
+            if (st_svc[i] >= 0xFFFFF0u) atomicOr(&P.ctr->error, PE_DEV_ERR_SVC_OVERFLOW);
             for (uint32_t w = 0; w < G.gen_cnt; w++)
                 if (gen_first_occurrence(K, G, w))
                     T.gen[K.gens[G.gen_off + w].kind][n] = P.st_gen_g[(size_t)w * P.st_cap + i];
@@ -479,10 +672,19 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             if (tid < 8) ofail[tid] = 0;
         }
     }
+    if (tid == 0) {
+        P.ctr->fast_path += n_fast;
+        P.ctr->slow_path += n_slow;
+        P.ctr->placements += n_placed;
+        P.ctr->evals_generic += n_evalg;
+    }
 }
 
 static inline size_t seq_dyn_smem_bytes(uint32_t touched_words_in_smem) {
-    return (size_t)PE_SEQ_KS * (sizeof(CandKey) + 8 + 8 + 4 + 4 + 4 + 1) + (size_t)touched_words_in_smem * 4 + 16;
+    size_t a = (size_t)PE_SEQ_KS * (sizeof(CandKey) + 8 + 8 + 4 + 4 + 4 + 1);
+    size_t b = (size_t)PE_SEQ_CHUNK * PE_SEQ_WIN * 4;   // bitmap windows alias the staging area
+    (void)b;
+    return a + (size_t)touched_words_in_smem * 4 + 16;
 }
 
 }  // namespace pe

@@ -1,0 +1,196 @@
+"""Object-level test harness: drives a scheduler implementation that speaks the
+JSON event protocol (oracle/sched_oracle.cpp, and the product's host shim
+swarmkit_b200/csrc/scheduler_host.cpp) the way the reference's tests drive
+scheduler.Run through a MemoryStore (manager/scheduler/scheduler_test.go:95-120):
+a tiny dict "store", events into the scheduler, a tick per committed
+transaction, decisions written back to the store and echoed as update events."""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import json
+
+
+class JsonScheduler:
+    """ctypes binding for {prefix}_create / _apply / _free / _destroy."""
+
+    def __init__(self, lib_path: str, prefix: str):
+        self.lib = C.CDLL(lib_path)
+        self._create = getattr(self.lib, prefix + "_create")
+        self._apply = getattr(self.lib, prefix + "_apply")
+        self._free = getattr(self.lib, prefix + "_free")
+        self._destroy = getattr(self.lib, prefix + "_destroy")
+        self._create.restype = C.c_void_p
+        self._apply.restype = C.c_void_p
+        self._apply.argtypes = [C.c_void_p, C.c_char_p]
+        self._free.argtypes = [C.c_void_p]
+        self._destroy.argtypes = [C.c_void_p]
+        self.h = self._create()
+        if not self.h:
+            raise RuntimeError("scheduler create failed")
+
+    def apply(self, ev: dict) -> dict:
+        p = self._apply(self.h, json.dumps(ev).encode())
+        try:
+            out = json.loads(C.string_at(p).decode())
+        finally:
+            self._free(p)
+        if "error" in out:
+            raise RuntimeError(out["error"])
+        return out
+
+    def close(self):
+        if self.h:
+            self._destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------- object builders
+def node(id, state="READY", availability="ACTIVE", labels=None, role="WORKER", addr="", description=None, version=0):
+    return {"id": id, "role": role, "version": version, "spec": {"availability": availability, "labels": labels},
+            "status": {"state": state, "addr": addr}, "description": description}
+
+
+def description(hostname="", platform=None, resources=None, engine=None):
+    return {"hostname": hostname, "platform": platform, "resources": resources, "engine": engine}
+
+
+def resources(nano_cpus=0, memory_bytes=0, generic=()):
+    return {"nano_cpus": int(nano_cpus), "memory_bytes": int(memory_bytes), "generic": list(generic)}
+
+
+def discrete(kind, value):
+    return {"kind": kind, "value": int(value)}
+
+
+def named(kind, value):
+    return {"kind": kind, "named": value}
+
+
+def engine(labels=None, plugins=()):
+    return {"labels": labels, "plugins": [{"type": t, "name": n} for t, n in plugins]}
+
+
+def task(id, service_id="", state="PENDING", desired_state="RUNNING", node_id="", spec_version=None, reservations=None,
+         placement=None, mounts=None, log_driver=None, networks=(), ports=None, slot=0):
+    spec = {"resources": {"reservations": reservations} if reservations is not None else None, "placement": placement,
+            "container": {"mounts": mounts or []}, "log_driver": {"name": log_driver} if log_driver is not None else None}
+    return {"id": id, "service_id": service_id, "slot": slot, "node_id": node_id, "desired_state": desired_state,
+            "status": {"state": state, "err": "", "message": ""}, "spec_version": spec_version, "spec": spec,
+            "networks": [{"driver": d} for d in networks],
+            "endpoint": {"ports": ports} if ports is not None else None, "assigned_generic": []}
+
+
+def placement(constraints=(), preferences=(), platforms=(), max_replicas=0):
+    return {"constraints": list(constraints), "preferences": list(preferences),
+            "platforms": [{"arch": a, "os": o} for a, o in platforms], "max_replicas": max_replicas}
+
+
+def host_port(port, protocol="TCP"):
+    return {"protocol": protocol, "published_port": port, "publish_mode": "HOST"}
+
+
+class Cluster:
+    """A dict 'store' plus one scheduler under test."""
+
+    def __init__(self, sched: JsonScheduler, nodes=(), tasks=(), services=(), now_ns=10**18):
+        self.s = sched
+        self.now = now_ns
+        self.nodes = {n["id"]: copy.deepcopy(n) for n in nodes}
+        self.tasks = {t["id"]: copy.deepcopy(t) for t in tasks}
+        self.services = {}
+        for sv in services:
+            sid, ver = (sv, None) if isinstance(sv, str) else sv
+            self.services[sid] = ver
+        self.s.apply({"op": "init", "now_ns": self.now, "nodes": list(self.nodes.values()), "tasks": list(self.tasks.values()),
+                      "services": [{"id": k, "spec_version": v} for k, v in self.services.items()]})
+
+    # --- store mutations (each echoes the event the MemoryStore would publish)
+    def set_service(self, sid, spec_version=None):
+        self.services[sid] = spec_version
+        self.s.apply({"op": "set_service", "id": sid, "spec_version": spec_version})
+
+    def create_node(self, n):
+        self.nodes[n["id"]] = copy.deepcopy(n)
+        self.s.apply({"op": "create_node", "now_ns": self.now, "node": n})
+
+    def update_node(self, n):
+        self.nodes[n["id"]] = copy.deepcopy(n)
+        self.s.apply({"op": "update_node", "now_ns": self.now, "node": n})
+
+    def delete_node(self, nid):
+        self.nodes.pop(nid, None)
+        self.s.apply({"op": "delete_node", "id": nid})
+
+    def create_task(self, t):
+        self.tasks[t["id"]] = copy.deepcopy(t)
+        self.s.apply({"op": "create_task", "now_ns": self.now, "task": t})
+
+    def update_task(self, t):
+        self.tasks[t["id"]] = copy.deepcopy(t)
+        self.s.apply({"op": "update_task", "now_ns": self.now, "task": t})
+
+    def delete_task(self, tid):
+        t = self.tasks.pop(tid, None)
+        ev = {"op": "delete_task", "id": tid}
+        if t is not None:
+            ev["task"] = t
+        self.s.apply(ev)
+
+    def advance(self, seconds: float):
+        self.now += int(seconds * 1e9)
+
+    # --- Scheduler.tick + applySchedulingDecisions + the echo of EventUpdateTask
+    def _commit(self, decisions):
+        out = {}
+        for d in decisions:
+            t = self.tasks.get(d["id"])
+            if t is None:
+                continue
+            t = copy.deepcopy(t)
+            t["node_id"] = d["node_id"]
+            t["status"] = {"state": d["state"], "err": d["err"], "message": d["message"]}
+            t["assigned_generic"] = d.get("assigned_generic", [])
+            self.tasks[t["id"]] = t
+            out[d["id"]] = d
+        for d in decisions:
+            if d["id"] in self.tasks:
+                self.s.apply({"op": "update_task", "now_ns": self.now, "task": self.tasks[d["id"]]})
+        return out
+
+    def tick(self, fail_commit=()):
+        r = self.s.apply({"op": "tick", "now_ns": self.now, "fail_commit": list(fail_commit)})
+        ds = [d for d in r["decisions"] if d["id"] not in set(fail_commit)]
+        return self._commit(ds)
+
+    def preassigned(self, fail_commit=()):
+        r = self.s.apply({"op": "preassigned", "now_ns": self.now, "fail_commit": list(fail_commit)})
+        ds = [d for d in r["decisions"] if d["id"] not in set(fail_commit)]
+        return self._commit(ds)
+
+    def run(self):
+        """What Scheduler.Run does on start and after each commit: preassigned first, then tick."""
+        out = self.preassigned()
+        out.update(self.tick())
+        return out
+
+    def snapshot(self):
+        return self.s.apply({"op": "snapshot"})
+
+    def assignments(self, decisions):
+        """task id -> node id for the decisions that assigned a node."""
+        return {k: d["node_id"] for k, d in decisions.items() if d["state"] == "ASSIGNED"}
+
+
+def count_by_node(assign: dict, prefix: str = "") -> dict:
+    out = {}
+    for tid, nid in assign.items():
+        if tid.startswith(prefix):
+            out[nid] = out.get(nid, 0) + 1
+    return out
