@@ -195,7 +195,8 @@ typedef struct pe_stats {
     uint64_t evals_generic;    /* ... by the sequencer's full-table path                      */
     uint64_t scan_bytes;       /* algorithmic bytes those scan evaluations read   */
     uint64_t placements;       /* tasks given a node                                          */
-    uint64_t fast_path;        /* k=1 groups resolved from the scan's candidate bitmap        */
+    uint64_t fast_path;        /* k=1 groups resolved from the scan's best-class bitmap       */
+    uint64_t medium_path;      /* ... from the second class + touched members of the first    */
     uint64_t slow_path;        /* groups that took the sequencer's full-table path            */
     uint64_t kernel_launches;  /* engine kernels launched                                     */
     uint64_t scan_launches;

@@ -432,20 +432,24 @@ static void sanitize(const List &nodeRes, List &avail) {
     kept.insert(kept.end(), sanitized.begin(), sanitized.end());
     avail.swap(kept);
 }
-// Reclaim, resource_management.go:75-122
-static void reclaim(List &avail, const List &taskAssigned, const List &nodeRes) {
+// reclaimResources, resource_management.go:86-122
+static void reclaim_resources(List &avail, const List &taskAssigned) {
     for (auto &res : taskAssigned) {
         if (!res.named) {
             List nrs = get_resource(res.kind, avail);
-            if (nrs.empty()) { avail.push_back(res); nrs = get_resource(res.kind, avail); /* fallthrough: len == 1 below adds again */
-                // NOTE: the reference appends a copy and then (len(nrs) was 0) `continue`s: restate exactly
-                continue; }
-            if (nrs.size() != 1) continue;
-            for (auto &na : avail) if (na.kind == res.kind) { if (na.named) break; na.amount += res.amount; break; }
+            // "If the resource went down to 0 it's no longer in the available list"
+            if (nrs.empty()) avail.push_back(res);
+            if (nrs.size() != 1) continue;   // (also taken right after the append above: len(nrs) was 0)
+            for (auto &na : avail)
+                if (na.kind == res.kind) { if (!na.named) na.amount += res.amount; break; }
         } else {
             avail.push_back(res);
         }
     }
+}
+// Reclaim, resource_management.go:75-84
+static void reclaim(List &avail, const List &taskAssigned, const List &nodeRes) {
+    reclaim_resources(avail, taskAssigned);
     sanitize(nodeRes, avail);
 }
 }  // namespace genericresource
@@ -1236,6 +1240,42 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         mj::Value pp = mj::Value::array();
         for (auto &kv : S.pendingPreassignedTasks) pp.push(mj::Value::string(kv.first));
         out.set("pending_preassigned", pp);
+    } else if (op == "nodeinfo") {
+        // NodeInfo unit probe (nodeinfo_test.go): newNodeInfo(node, tasks, available) then add/remove calls
+        std::vector<TaskP> tasks;
+        for (auto &t : ev.at("tasks").a) tasks.push_back(task(t));
+        NodeInfo ni = newNodeInfo(node(ev.at("node")), tasks, resources(ev.at("available")), S.now);
+        mj::Value res = mj::Value::array();
+        for (auto &o : ev.at("ops").a) {
+            TaskP t = task(o.at("task"));
+            bool r = o.at("op").as_str() == "add" ? ni.addTask(t) : ni.removeTask(*t);
+            res.push(mj::Value::boolean(r));
+        }
+        out.set("results", res);
+        out.set("available", resources_json(ni.AvailableResources));
+        out.set("active_tasks", mj::Value::integer(ni.ActiveTasksCount));
+    } else if (op == "tree") {
+        // nodeSet.tree probe (nodeset_test.go): nodes carry by_service counts; filter and less are constants
+        Scheduler T2;
+        for (auto &nv : ev.at("nodes").a) {
+            NodeInfo ni; ni.Node = node(nv);
+            for (auto &kv : nv.at("by_service").o) ni.ActiveTasksCountByService[kv.first] = (int)kv.second.as_int();
+            T2.nodeSet[ni.Node->ID] = ni;
+        }
+        api::Task dummy; T2.pipeline.SetTask(dummy);
+        std::vector<std::string> prefs; for (auto &p : ev.at("preferences").a) prefs.push_back(p.as_str());
+        NodeLess nl = [](const NodeInfo &, const NodeInfo &) { return true; };
+        DecisionTree tr = T2.tree(ev.at("service_id").as_str(), prefs, (int)ev.at("max_assignments").as_int(), nl);
+        std::function<mj::Value(const DecisionTree &)> dumpt = [&](const DecisionTree &d) {
+            mj::Value o = mj::Value::object();
+            o.set("tasks", mj::Value::integer(d.tasks));
+            o.set("nodes", mj::Value::integer((int64_t)d.heap.size()));
+            mj::Value nx = mj::Value::object();
+            for (auto &kv : d.next) nx.set(kv.first, dumpt(*kv.second));
+            o.set("next", nx);
+            return o;
+        };
+        out.set("tree", dumpt(tr));
     } else if (op == "parse_constraints") {
         std::vector<std::string> env; for (auto &c : ev.at("constraints").a) env.push_back(c.as_str());
         std::vector<constraint::Constraint> cs;
@@ -1265,6 +1305,9 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         } else if (fn == "reclaim") {
             api::Resources assigned = resources(ev.at("assigned")), noderes = resources(ev.at("node"));
             genericresource::reclaim(avail.Generic, assigned.Generic, noderes.Generic);
+        } else if (fn == "reclaim_resources") {
+            api::Resources assigned = resources(ev.at("assigned"));
+            genericresource::reclaim_resources(avail.Generic, assigned.Generic);
         } else if (fn == "consume") {
             api::Resources res = resources(ev.at("res"));
             genericresource::consume_node_resources(avail.Generic, res.Generic);

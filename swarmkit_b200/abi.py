@@ -85,7 +85,7 @@ class pe_tick(C.Structure):
 
 class pe_stats(C.Structure):
     _fields_ = [("evals", C.c_uint64), ("evals_generic", C.c_uint64), ("scan_bytes", C.c_uint64),
-                ("placements", C.c_uint64), ("fast_path", C.c_uint64), ("slow_path", C.c_uint64),
+                ("placements", C.c_uint64), ("fast_path", C.c_uint64), ("medium_path", C.c_uint64), ("slow_path", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("sequencer_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("run_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]

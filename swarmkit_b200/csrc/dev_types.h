@@ -46,14 +46,19 @@ struct TickDev {
 };
 
 // Per-task result of the batched k=1 scan.
+// The scan keeps the two smallest rank classes of every task: bitmap rows
+// 2*task + row0 (best class) and 2*task + (row0 ^ 1) (second class).
 struct ScanResult {
     unsigned long long c0;  // smallest (f5, svc, total) prefix among feasible nodes; PE_PREF_NONE if none
-    uint32_t w0;            // first valid word of the class bitmap (earlier words are stale)
-    uint32_t n_class;       // nodes in the class
+    unsigned long long c1;  // second smallest prefix; PE_PREF_NONE if there is no second class
+    uint32_t w0;            // first valid word of the best-class bitmap (earlier words are stale)
+    uint32_t w1;            // first valid word of the second-class bitmap
+    uint32_t row0;          // physical row (0/1) holding the best class
+    uint32_t pad;
 };
 
 struct DevCounters {
-    unsigned long long fast_path, slow_path, placements, evals_generic;
+    unsigned long long fast_path, medium_path, slow_path, placements, evals_generic;
     uint32_t error;
     uint32_t pad;
 };

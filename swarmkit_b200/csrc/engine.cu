@@ -107,7 +107,7 @@ struct pe_engine {
         max_batch = cfg->max_batch;
         CU(cudaMalloc(&d_ctr, sizeof(DevCounters)));
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
-        CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(16384)));
+        CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(12288)));
         for (auto fn : scan_variants()) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         int32_t rc = ensure_cap(cfg->node_capacity ? cfg->node_capacity : 1);
         if (rc) return rc;
@@ -495,7 +495,7 @@ struct pe_engine {
         P.st_placed_g = st_placed_g; P.st_flags_g = st_flags_g; P.st_gen_g = st_gen_g; P.st_cap = st_cap;
         P.touched_g = touched_g;
         P.touched_words = with_scan ? (n_nodes + 31) / 32 : 0;
-        P.touched_in_smem = P.touched_words <= 16384 ? 1 : 0;
+        P.touched_in_smem = P.touched_words <= 12288 ? 1 : 0;   // <= 48 KB of shared memory
         P.ctr = d_ctr;
         size_t dyn = seq_dyn_smem_bytes(P.touched_in_smem ? P.touched_words : 0);
         EvPair *ev = ev_begin(1);
@@ -620,7 +620,7 @@ struct pe_engine {
         const uint32_t Bmax = max_batch ? max_batch : wave;
         const bool spec = !(cfg_flags & PE_CFG_NO_SPECULATION) && n_nodes > 0;
         if (spec) {
-            size_t need = (size_t)Bmax * e_stride();
+            size_t need = (size_t)Bmax * 2u * e_stride();   // two class rows per task
             if (need > E_words) {
                 void *p = E; size_t c = E_words * 4;
                 if ((rc = ensure_buf(p, c, need * 4))) return rc;
@@ -676,7 +676,7 @@ struct pe_engine {
         DevCounters c;
         CU(cudaMemcpy(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost));
         CU(cudaMemset(d_ctr, 0, sizeof c));
-        stats.fast_path += c.fast_path; stats.slow_path += c.slow_path;
+        stats.fast_path += c.fast_path; stats.medium_path += c.medium_path; stats.slow_path += c.slow_path;
         stats.placements += c.placements; stats.evals_generic += c.evals_generic;
         ev_collect();
         if (c.error & PE_DEV_ERR_SVC_OVERFLOW) { err = "a per-service task count reached 2^24 - 1 on one node"; return PE_ERR_OVERFLOW; }

@@ -167,9 +167,12 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
     }
     const uint32_t o_meta = P.off_meta + lane * 4u, o_total = P.off_total + lane * 4u;
 
-    uint32_t best_hi = 0xFFFFFFFFu, best_lo = 0xFFFFFFFFu;
-    uint32_t w0 = 0, myword = 0;
-    uint32_t *Erow = P.E + (size_t)task * P.e_stride;
+    // the two smallest rank classes seen so far (hi:lo), where their bitmaps start,
+    // which physical row holds the best one, and this lane's word of each for the
+    // current 32-step block
+    uint32_t b1h = 0xFFFFFFFFu, b1l = 0xFFFFFFFFu, b2h = 0xFFFFFFFFu, b2l = 0xFFFFFFFFu;
+    uint32_t w01 = 0, w02 = 0, rowsel = 0, my1 = 0, my2 = 0;
+    uint32_t *Erows = P.E + (size_t)task * 2u * P.e_stride;
     const uint32_t steps = TN >> 5;
 
     for (uint32_t tile = 0; tile < P.n_tiles; tile++) {
@@ -278,30 +281,60 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
                     uint32_t hi = svc_n & 0xFFFFFFu;
                     if (HAS_EXTRA) hi |= (fails >= 5u ? (fails > 255u ? 255u : fails) : 0u) << 24;
                     const uint32_t lo = *reinterpret_cast<const uint32_t *>(row + o_total);
-                    const bool better = ok & ((hi < best_hi) | ((hi == best_hi) & (lo < best_lo)));
-                    if (__any_sync(0xFFFFFFFFu, better)) {
-                        // a strictly better class starts here: everything emitted so far is stale
+                    const bool eq1 = (hi == b1h) & (lo == b1l);
+                    const bool lt1 = ok & ((hi < b1h) | ((hi == b1h) & (lo < b1l)));
+                    const uint32_t curw = tile * steps + s;
+                    if (__any_sync(0xFFFFFFFFu, lt1)) {
+                        // a strictly better class starts in this step
                         const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, ok ? hi : 0xFFFFFFFFu);
                         const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, (ok && hi == mh) ? lo : 0xFFFFFFFFu);
-                        best_hi = mh; best_lo = ml;
-                        w0 = tile * steps + s;
+                        const bool gt = ok & !((hi == mh) & (lo == ml));
+                        const uint32_t sh = __reduce_min_sync(0xFFFFFFFFu, gt ? hi : 0xFFFFFFFFu);
+                        const uint32_t sl = __reduce_min_sync(0xFFFFFFFFu, (gt && hi == sh) ? lo : 0xFFFFFFFFu);
+                        const bool had = !(b1h == 0xFFFFFFFFu && b1l == 0xFFFFFFFFu);
+                        const bool old_le = (b1h < sh) | ((b1h == sh) & (b1l <= sl));
+                        if (had && old_le) {
+                            // the old best class becomes the second class and keeps its row
+                            b2h = b1h; b2l = b1l; w02 = w01;
+                            rowsel ^= 1u;
+                            const uint32_t t = my1; my1 = my2; my2 = t;
+                        } else {
+                            b2h = sh; b2l = sl; w02 = curw;     // (possibly none)
+                        }
+                        b1h = mh; b1l = ml; w01 = curw;
+                    } else {
+                        const bool lt2 = ok & !eq1 & ((hi < b2h) | ((hi == b2h) & (lo < b2l)));
+                        if (__any_sync(0xFFFFFFFFu, lt2)) {
+                            // a class between the best and the second starts here
+                            const uint32_t sh = __reduce_min_sync(0xFFFFFFFFu, lt2 ? hi : 0xFFFFFFFFu);
+                            const uint32_t sl = __reduce_min_sync(0xFFFFFFFFu, (lt2 && hi == sh) ? lo : 0xFFFFFFFFu);
+                            b2h = sh; b2l = sl; w02 = curw;
+                        }
                     }
-                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, ok & (hi == best_hi) & (lo == best_lo));
-                    if (lane == (s & 31u)) myword = word;
-                    if ((s & 31u) == 31u) Erow[tile * steps + (s & ~31u) + lane] = myword;
+                    const uint32_t word1 = __ballot_sync(0xFFFFFFFFu, ok & (hi == b1h) & (lo == b1l));
+                    const uint32_t word2 = __ballot_sync(0xFFFFFFFFu, ok & (hi == b2h) & (lo == b2l));
+                    if (lane == (s & 31u)) { my1 = word1; my2 = word2; }
+                    if ((s & 31u) == 31u) {
+                        const uint32_t wi = tile * steps + (s & ~31u) + lane;
+                        Erows[(size_t)rowsel * P.e_stride + wi] = my1;
+                        Erows[(size_t)(rowsel ^ 1u) * P.e_stride + wi] = my2;
+                    }
                 }
             }
             if (steps < 32u) {  // tiles shorter than 32 steps: flush what we have
-                if (lane < steps) Erow[tile * steps + lane] = myword;
+                if (lane < steps) {
+                    Erows[(size_t)rowsel * P.e_stride + tile * steps + lane] = my1;
+                    Erows[(size_t)(rowsel ^ 1u) * P.e_stride + tile * steps + lane] = my2;
+                }
             }
         }
         __syncthreads();   // everyone is done with this stage before it is refilled
     }
     if (active && lane == 0) {
         ScanResult r;
-        r.c0 = (best_hi == 0xFFFFFFFFu && best_lo == 0xFFFFFFFFu) ? PE_PREF_NONE : (((unsigned long long)best_hi << 32) | best_lo);
-        r.w0 = w0;
-        r.n_class = 0;
+        r.c0 = ((unsigned long long)b1h << 32) | b1l;   // all ones = PE_PREF_NONE
+        r.c1 = ((unsigned long long)b2h << 32) | b2l;
+        r.w0 = w01; r.w1 = w02; r.row0 = rowsel; r.pad = 0;
         P.out[task] = r;
     }
 }

@@ -39,12 +39,38 @@ __device__ __forceinline__ bool key_less(const CandKey &a, const CandKey &b) {
 
 #define PE_SEQ_THREADS 1024
 #define PE_SEQ_KS 2048          // candidates staged in shared memory
-#define PE_SEQ_CHUNK 8          // k=1 tasks staged together on the fast path
+#define PE_SEQ_RING 16          // fast-mode ring slots
+#define PE_SEQ_NPW 15           // producer warps (warps 1..NPW)
 #define PE_SEQ_WIN 1024         // bitmap words staged per task (32k nodes)
 #define PE_MAX_GEN_WANTS 8
 #define PE_CTX_MAXC 16
 #define PE_ST_FAILED 1u
 #define PE_ST_BLOCKED 2u
+
+
+__device__ __forceinline__ uint32_t seq_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sq_mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(seq_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sq_mbar_inval(unsigned long long *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(seq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sq_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(seq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool sq_mbar_try_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(seq_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void sq_mbar_wait(unsigned long long *bar, uint32_t parity) {
+    while (!sq_mbar_try_wait(bar, parity)) {}
+}
 
 struct SeqParams {
     DevTable T;
@@ -81,13 +107,15 @@ struct FastTask {      // staged descriptor of one k=1 task
     unsigned long long c0;
     long long cpu_res, mem_res;
     uint32_t *svccol;
-    uint32_t w0, tie_start, task_off, simple, counts, ws;
+    uint32_t w0, tie_start, task_off, simple, counts, ws, row0;
 };
 
 struct SeqShared {
     pe_group G;
     GroupCtx C;
-    FastTask ft[PE_SEQ_CHUNK];
+    FastTask ft[PE_SEQ_RING];
+    unsigned long long full_bar[PE_SEQ_RING], empty_bar[PE_SEQ_RING];
+    uint32_t stop, resume, stop_reason, bars_live;
     uint32_t red32[40];
     unsigned long long red64[40];
     uint32_t bins[256];
@@ -234,86 +262,142 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     uint8_t *st_flags_s = reinterpret_cast<uint8_t *>(st_placed_s + PE_SEQ_KS);
     uint32_t *touched_s = reinterpret_cast<uint32_t *>(st_flags_s + PE_SEQ_KS);
     uint32_t *touched = P.touched_in_smem ? touched_s : P.touched_g;
-    // the fast path's bitmap windows alias the candidate staging area (never live at the same time)
-    uint32_t *ebuf = reinterpret_cast<uint32_t *>(dyn_smem);
+    uint32_t *ring = touched_s + (P.touched_in_smem ? ((P.touched_words + 3u) & ~3u) : 0u);   // [PE_SEQ_RING][PE_SEQ_WIN]
 
     for (uint32_t w = tid; w < P.touched_words; w += nth) touched[w] = 0;
-    if (tid == 0) { S.neutral = 0; S.bestv[0] = S.bestv[1] = S.bestv[2] = PE_NONE; }
+    if (tid == 0) { S.neutral = 0; S.bars_live = 0; S.bestv[0] = S.bestv[1] = S.bestv[2] = PE_NONE; }
     uint32_t slot = 0;   // uniform across the block
-    unsigned long long n_fast = 0, n_slow = 0, n_placed = 0, n_evalg = 0;   // thread 0's private tallies
+    unsigned long long n_fast = 0, n_medium = 0, n_slow = 0, n_placed = 0, n_evalg = 0;   // thread 0's private tallies
     __syncthreads();
 
     uint32_t gi = P.g_begin;
     while (gi < P.g_end) {
-        // ================= fast path: a chunk of k == 1 tasks =====================
+        // ================= fast mode: warp-specialised pipeline over k == 1 tasks ====
+        // Warps 1..NPW prefetch (descriptor + first PE_SEQ_WIN words of the best-class
+        // bitmap) into a ring of shared-memory slots; warp 0 consumes the slots IN
+        // ORDER, so the ordered part touches shared memory only.  Hand-off uses
+        // mbarriers (full/empty per slot).  The mode ends at the first task the
+        // bitmaps cannot resolve; that task takes the block-wide path below.
         if (P.scan != nullptr && !S.neutral) {
-            const uint32_t C = min((uint32_t)PE_SEQ_CHUNK, P.g_end - gi);
             __syncthreads();
-            if (tid < C) {   // level A: descriptors
-                const pe_group g = K.groups[gi + tid];
-                const ScanResult sr = P.scan[gi + tid - P.g_begin];
-                FastTask f;
-                f.c0 = g.n_tasks == 1 ? sr.c0 : PE_PREF_NONE;
-                f.w0 = sr.w0;
-                f.tie_start = g.tie_start;
-                f.task_off = g.task_off;
-                f.cpu_res = g.cpu_res; f.mem_res = g.mem_res;
-                f.simple = (g.gen_cnt == 0 && g.port_cnt == 0) ? 1u : 0u;
-                f.counts = g.n_tasks == 1 ? (K.task_flags[g.task_off] & PE_T_COUNTS) : 0u;
-                f.svccol = T.svc[g.svc_id];
-                const uint32_t lo_bit = max(g.tie_start, sr.w0 * 32u);
-                f.ws = lo_bit >> 5;
-                S.ft[tid] = f;
+            if (tid == 0) {
+                for (int r = 0; r < PE_SEQ_RING; r++) {
+                    if (S.bars_live) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.empty_bar[r]); }
+                    sq_mbar_init(&S.full_bar[r], 1);
+                    sq_mbar_init(&S.empty_bar[r], 1);
+                }
+                S.bars_live = 1;
+                S.stop = 0;
+                S.resume = P.g_end;
+                S.stop_reason = 0;
             }
             __syncthreads();
-            // level B: the first PE_SEQ_WIN words of every class bitmap in the chunk
-            for (uint32_t c = 0; c < C; c++) {
-                const FastTask &f = S.ft[c];
-                const uint32_t w = f.ws + tid;
-                uint32_t v = 0;
-                if (f.c0 != PE_PREF_NONE && w < ((N + 31u) >> 5)) v = P.E[(size_t)(gi + c - P.g_begin) * P.e_stride + w];
-                ebuf[c * PE_SEQ_WIN + tid] = v;
-            }
-            __syncthreads();
-            uint32_t c = 0;
-            for (; c < C; c++) {
-                const FastTask &f = S.ft[c];
-                if (f.c0 == PE_PREF_NONE) break;          // nothing feasible at batch start (or k != 1): generic path
-                const uint32_t lo_bit = max(f.tie_start, f.w0 * 32u);
-                const uint32_t w = f.ws + tid;
-                uint32_t v = 0;
-                if (w < ((N + 31u) >> 5)) {
-                    v = ebuf[c * PE_SEQ_WIN + tid] & ~touched[w];
-                    if (tid == 0) v &= 0xFFFFFFFFu << (lo_bit & 31u);
-                    if (w == ((N + 31u) >> 5) - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
-                }
-                uint32_t n = block_min_pos(v ? w * 32u + (uint32_t)__ffs((int)v) - 1u : PE_NONE, S, slot);
-                if (n == PE_NONE) {
-                    // not inside the staged window: walk the rest of the bitmap (wraps when the tie order is rotated)
-                    n = find_first(P.E + (size_t)(gi + c - P.g_begin) * P.e_stride, f.w0, N, f.tie_start, touched, S, slot);
-                    if (n == PE_NONE) break;              // class consumed in this batch: generic path
-                }
-                if (tid == 0) {
-                    K.out_node[f.task_off] = n;
-                    if (f.simple) {                        // NodeInfo.addTask, nodeinfo.go:125-153, as fire-and-forget reductions
-                        if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-f.cpu_res));
-                        if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-f.mem_res));
-                        if (f.counts) { atomicAdd(&T.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
-                    } else {
-                        add_task_global(T, K, K.groups[gi + c], n, f.counts != 0, P.ctr);
+            const uint32_t start = gi;
+            const uint32_t nwords = (N + 31u) >> 5;
+            volatile uint32_t *vstop = &S.stop;
+            if (warp == 0) {
+                // ---------------- consumer: strictly in task order
+                uint32_t i = 0, reason = 0;
+                for (; start + i < P.g_end; i++) {
+                    const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
+                    sq_mbar_wait(&S.full_bar[slot], round & 1u);
+                    const FastTask f = S.ft[slot];
+                    if (f.c0 == PE_PREF_NONE) { reason = 1; break; }      // nothing feasible when the batch began, or k != 1
+                    const uint32_t lo_bit = max(f.tie_start, f.w0 * 32u);
+                    const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - f.ws);
+                    const uint32_t *buf = ring + slot * PE_SEQ_WIN;
+                    uint32_t n = PE_NONE;
+                    for (uint32_t j = 0; j < nwin; j += 32u) {
+                        const uint32_t w = f.ws + j + lane;
+                        uint32_t v = 0;
+                        if (j + lane < nwin) {
+                            v = buf[j + lane] & ~touched[w];
+                            if (j + lane == 0) v &= 0xFFFFFFFFu << (lo_bit & 31u);
+                            if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
+                        }
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0u);
+                        if (b) {
+                            const int src = __ffs((int)b) - 1;
+                            const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
+                            n = (f.ws + j + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
+                            break;
+                        }
                     }
-                    touched[n >> 5] |= 1u << (n & 31u);
-                    if (!f.counts) S.neutral = 1;          // rank did not move: later class bitmaps may hide this node
-                    n_fast++; n_placed++;
+                    if (n == PE_NONE) { reason = 2; break; }               // not inside the staged window
+                    if (lane == 0) {
+                        K.out_node[f.task_off] = n;
+                        if (f.simple) {                // NodeInfo.addTask, nodeinfo.go:125-153, as fire-and-forget reductions
+                            if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-f.cpu_res));
+                            if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-f.mem_res));
+                            if (f.counts) { atomicAdd(&T.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
+                        } else {
+                            add_task_global(T, K, K.groups[start + i], n, f.counts != 0, P.ctr);
+                        }
+                        touched[n >> 5] |= 1u << (n & 31u);
+                        n_fast++; n_placed++;
+                    }
+                    if (lane < 8) K.out_fail[(size_t)(start + i) * PE_NUM_FILTERS + lane] = 0;
+                    __syncwarp();
+                    if (lane == 0) sq_mbar_arrive(&S.empty_bar[slot]);
+                    if (!f.counts) { reason = 3; i++; break; }             // rank did not move: later class bitmaps may hide this node
                 }
-                if (tid < 8) K.out_fail[(size_t)(gi + c) * PE_NUM_FILTERS + tid] = 0;
-                __syncthreads();
-                if (S.neutral) { c++; break; }
+                if (lane == 0) {
+                    S.resume = start + i;
+                    S.stop_reason = reason;
+                    if (reason == 3) S.neutral = 1;
+                    __threadfence_block();
+                    *vstop = 1;
+                }
+            } else if (warp <= PE_SEQ_NPW) {
+                // ---------------- producers
+                for (uint32_t i = warp - 1; start + i < P.g_end; i += PE_SEQ_NPW) {
+                    const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
+                    bool stopped = false;
+                    while (!sq_mbar_try_wait(&S.empty_bar[slot], (round & 1u) ^ 1u)) {
+                        if (*vstop) { stopped = true; break; }
+                    }
+                    if (stopped || *vstop) break;
+                    const uint32_t gq = start + i;
+                    uint32_t ws = 0, valid = 0, row0 = 0;
+                    if (lane == 0) {
+                        const pe_group g = K.groups[gq];
+                        const ScanResult sr = P.scan[gq - P.g_begin];
+                        FastTask f;
+                        f.c0 = g.n_tasks == 1 ? sr.c0 : PE_PREF_NONE;
+                        f.w0 = sr.w0; f.row0 = sr.row0;
+                        f.tie_start = g.tie_start;
+                        f.task_off = g.task_off;
+                        f.cpu_res = g.cpu_res; f.mem_res = g.mem_res;
+                        f.simple = (g.gen_cnt == 0 && g.port_cnt == 0) ? 1u : 0u;
+                        f.counts = g.n_tasks == 1 ? (K.task_flags[g.task_off] & PE_T_COUNTS) : 0u;
+                        f.svccol = T.svc[g.svc_id];
+                        f.ws = max(g.tie_start, sr.w0 * 32u) >> 5;
+                        S.ft[slot] = f;
+                        ws = f.ws; valid = f.c0 != PE_PREF_NONE; row0 = f.row0;
+                    }
+                    ws = __shfl_sync(0xFFFFFFFFu, ws, 0);
+                    valid = __shfl_sync(0xFFFFFFFFu, valid, 0);
+                    row0 = __shfl_sync(0xFFFFFFFFu, row0, 0);
+                    if (valid) {
+                        const uint32_t *src = P.E + ((size_t)(gq - P.g_begin) * 2u + row0) * P.e_stride + ws;
+                        uint32_t *dst = ring + slot * PE_SEQ_WIN;
+                        const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - ws);
+                        for (uint32_t j = 0; j < nwin; j += 256u) {
+                            uint32_t v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { const uint32_t x = j + u * 32u + lane; v[u] = x < nwin ? src[x] : 0u; }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { const uint32_t x = j + u * 32u + lane; if (x < PE_SEQ_WIN) dst[x] = v[u]; }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) sq_mbar_arrive(&S.full_bar[slot]);
+                }
             }
-            gi += c;
-            if (c == C) continue;                          // whole chunk placed from the bitmaps
+            __syncthreads();
+            gi = S.resume;
             if (gi >= P.g_end) break;
-            // fall through: group gi takes the generic path
+            // group gi takes the block-wide path
         }
 
         // ================= generic path (one group) ===============================
@@ -338,6 +422,87 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
         __syncthreads();
         uint32_t *svccol = S.C.svccol;
 
+        if (k == 1 && P.scan != nullptr && !S.neutral) {
+            // ---- medium path: the best class of this task was consumed earlier in the
+            // batch.  Every node outside the two recorded classes ranked strictly worse
+            // than the second class when the batch began and ranks can only have grown,
+            // so the arg-min is either the first untouched member of the second class or
+            // a touched member of the best class re-evaluated against the live state.
+            const ScanResult sr = P.scan[this_gi - P.g_begin];
+            if (sr.c0 != PE_PREF_NONE) {
+                // (i) the best class may continue beyond the window the pipeline staged
+                const uint32_t *E1w = P.E + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * P.e_stride;
+                const uint32_t n1 = find_first(E1w, sr.w0, N, G.tie_start, touched, S, slot);
+                if (n1 != PE_NONE) {
+                    if (tid == 0) {
+                        const bool counts = (K.task_flags[G.task_off] & PE_T_COUNTS) != 0;
+                        K.out_node[G.task_off] = n1;
+                        add_task_global(T, K, G, n1, counts, P.ctr);
+                        touched[n1 >> 5] |= 1u << (n1 & 31u);
+                        if (!counts) S.neutral = 1;
+                        n_fast++; n_placed++;
+                    }
+                    if (tid < 8) ofail[tid] = 0;
+                    __syncthreads();
+                    continue;
+                }
+            }
+            // (ii) best class consumed: second class + touched members of the best class
+            if (sr.c0 != PE_PREF_NONE && sr.c1 != PE_PREF_NONE) {
+                const uint32_t *E1 = P.E + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * P.e_stride;
+                const uint32_t *E2 = P.E + ((size_t)(this_gi - P.g_begin) * 2u + (sr.row0 ^ 1u)) * P.e_stride;
+                const uint32_t n2 = find_first(E2, sr.w1, N, G.tie_start, touched, S, slot);
+                if (n2 != PE_NONE) {
+                    unsigned long long bp = sr.c1;
+                    uint32_t bt = tie_pos(n2, G.tie_start, N), bn = n2;
+                    const uint32_t nw = (N + 31u) >> 5;
+                    for (uint32_t w = sr.w0 + tid; w < nw; w += nth) {
+                        uint32_t v = E1[w] & touched[w];
+                        if (w == nw - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
+                        while (v) {
+                            const uint32_t n = w * 32u + (uint32_t)__ffs((int)v) - 1u;
+                            v &= v - 1u;
+                            const uint32_t meta = T.meta[n];
+                            const uint32_t sv = svccol[n];
+                            if (eval_ctx(T, K, G, S.C, n, meta, sv) != 0) continue;
+                            const uint32_t fails = G.fail_cnt ? fail_count(K, G, n) : 0u;
+                            const unsigned long long pref = make_pref(fails, sv, T.total[n]);
+                            const uint32_t tp = tie_pos(n, G.tie_start, N);
+                            if (pref < bp || (pref == bp && tp < bt)) { bp = pref; bt = tp; bn = n; }
+                        }
+                    }
+                    const uint32_t hi = (uint32_t)(bp >> 32), lo = (uint32_t)bp;
+                    const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+                    const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
+                    const uint32_t mt = __reduce_min_sync(0xFFFFFFFFu, (hi == mh && lo == ml) ? bt : 0xFFFFFFFFu);
+                    __syncthreads();
+                    if (lane == 0) { S.red64[warp] = ((unsigned long long)mh << 32) | ml; S.red32[warp] = mt; }
+                    __syncthreads();
+                    unsigned long long gp = ~0ull; uint32_t gt = ~0u;
+                    for (uint32_t w = 0; w < (nth >> 5); w++) {
+                        const unsigned long long p = S.red64[w]; const uint32_t t = S.red32[w];
+                        if (p < gp || (p == gp && t < gt)) { gp = p; gt = t; }
+                    }
+                    // every thread starts from (c1, n2), so several may hold the winner: lowest thread commits
+                    const uint32_t who = __reduce_min_sync(0xFFFFFFFFu, (bp == gp && bt == gt) ? tid : 0xFFFFFFFFu);
+                    if (lane == 0) S.red32[warp] = who;
+                    __syncthreads();
+                    uint32_t winner = 0xFFFFFFFFu;
+                    for (uint32_t w = 0; w < (nth >> 5); w++) winner = min(winner, S.red32[w]);
+                    if (tid == winner) {
+                        const bool counts = (K.task_flags[G.task_off] & PE_T_COUNTS) != 0;
+                        K.out_node[G.task_off] = bn;
+                        add_task_global(T, K, G, bn, counts, P.ctr);
+                        touched[bn >> 5] |= 1u << (bn & 31u);
+                        if (!counts) S.neutral = 1;
+                    }
+                    if (tid == 0) { n_medium++; n_placed++; }
+                    if (tid < 8) ofail[tid] = 0;
+                    __syncthreads();
+                    continue;
+                }
+            }
+        }
         if (k == 1) {
             // ---- one task: block arg-min over the live table (nodeset.go:107-120 with a heap of one)
             unsigned long long bp = ~0ull;
@@ -674,6 +839,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     }
     if (tid == 0) {
         P.ctr->fast_path += n_fast;
+        P.ctr->medium_path += n_medium;
         P.ctr->slow_path += n_slow;
         P.ctr->placements += n_placed;
         P.ctr->evals_generic += n_evalg;
@@ -682,9 +848,8 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
 
 static inline size_t seq_dyn_smem_bytes(uint32_t touched_words_in_smem) {
     size_t a = (size_t)PE_SEQ_KS * (sizeof(CandKey) + 8 + 8 + 4 + 4 + 4 + 1);
-    size_t b = (size_t)PE_SEQ_CHUNK * PE_SEQ_WIN * 4;   // bitmap windows alias the staging area
-    (void)b;
-    return a + (size_t)touched_words_in_smem * 4 + 16;
+    size_t b = (size_t)PE_SEQ_RING * PE_SEQ_WIN * 4;    // fast-mode ring
+    return a + (((size_t)touched_words_in_smem + 3) & ~(size_t)3) * 4 + b + 16;
 }
 
 }  // namespace pe
