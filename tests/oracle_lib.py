@@ -26,6 +26,11 @@ def build_sched() -> str:
     return _make("liboracle_sched.so")
 
 
+def build_shim_on_oracle() -> str:
+    """The product's host shim compiled against the oracle ABI (test-only artifact)."""
+    return _make("libshim_on_oracle.so")
+
+
 class OracleEngine(FlatABI):
     """The flat CPU oracle behind the same ABI as the CUDA engine (prefix ope_)."""
 

@@ -1,0 +1,75 @@
+"""CPU-only checks of the host logic (no GPU): the product's host shim compiled
+against the oracle's ABI (oracle/_build/libshim_on_oracle.so, test-only) must
+(a) replay the reference's known-answer tests and (b) agree decision-for-decision
+with the object-level oracle on random event streams.  This pins the encoded
+(flat) oracle to the object-level oracle, and exercises the shim's encoder."""
+import inspect
+
+import pytest
+
+from tests import known_answers as KA
+from tests.oracle_lib import build_sched, build_shim_on_oracle
+from tests.sched_harness import Cluster, JsonScheduler
+from tests.test_mirror_gpu import UNSUPPORTED, _rand_node, _rand_task  # generators only; nothing GPU is touched at import
+
+import random
+
+
+def make_shim():
+    return JsonScheduler(build_shim_on_oracle(), "sso")
+
+
+def make_oracle():
+    return JsonScheduler(build_sched(), "so")
+
+
+SCENARIOS = [(n, f) for n, f in inspect.getmembers(KA, inspect.isfunction) if n.startswith("scenario_")]
+
+
+@pytest.mark.parametrize("name,fn", SCENARIOS, ids=[n for n, _ in SCENARIOS])
+def test_known_answer_through_shim(name, fn):
+    params = list(inspect.signature(fn).parameters)
+    if name in UNSUPPORTED:
+        with pytest.raises(RuntimeError, match="placement preferences are not supported"):
+            fn(make_shim, False) if "use_spec_version" in params else fn(make_shim)
+        return
+    if "use_spec_version" in params:
+        for v in (False, True):
+            fn(make_shim, v)
+    else:
+        fn(make_shim)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_event_stream_flat_vs_object(seed):
+    rng = random.Random(seed)
+    n_nodes, n_services = rng.randint(5, 60), rng.randint(2, 8)
+    nodes = [_rand_node(rng, i) for i in range(n_nodes)]
+    tasks = [_rand_task(rng, i, n_services) for i in range(rng.randint(10, 120))]
+    services = [(f"svc{s}", (2 if s % 3 else None)) for s in range(n_services)]
+    cm = Cluster(make_shim(), nodes=nodes, tasks=tasks, services=services)
+    co = Cluster(make_oracle(), nodes=nodes, tasks=tasks, services=services)
+    next_task = len(tasks)
+    for step in range(10):
+        dm, do = cm.run(), co.run()
+        assert dm == do, f"seed {seed} step {step}: decisions differ"
+        sm, so = cm.s.apply({"op": "device_check"}), co.snapshot()
+        assert sm["mismatch"] == []
+        assert sm["nodes"] == so["nodes"] and sm["unassigned"] == so["unassigned"]
+        for c in (cm, co):
+            r2 = random.Random(seed * 100 + step)
+            for j in range(r2.randint(3, 25)):
+                c.create_task(_rand_task(r2, next_task + j, n_services))
+            running = [t for t in c.tasks.values() if t["status"]["state"] == "ASSIGNED"]
+            for t in r2.sample(running, min(len(running), r2.randint(0, 6))):
+                t = dict(t)
+                t["status"] = dict(t["status"], state=r2.choice(["FAILED", "SHUTDOWN", "RUNNING"]))
+                c.update_task(t)
+            if r2.random() < 0.5:
+                c.update_node(_rand_node(r2, r2.randrange(n_nodes)))
+            if r2.random() < 0.3:
+                c.create_node(_rand_node(r2, n_nodes + step))
+            if r2.random() < 0.2 and len(c.nodes) > 3:
+                c.delete_node(r2.choice(sorted(c.nodes)))
+            c.advance(r2.choice([1, 30, 200]))
+        next_task += 25
