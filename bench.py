@@ -240,14 +240,9 @@ def main():
     h2d = (s_after["h2d_bytes"] - s_before["h2d_bytes"]) // (1 + args.steps)
     d2h = (s_after["d2h_bytes"] - s_before["d2h_bytes"]) // (1 + args.steps)
 
-    # ---- max over ranks
-    t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([placed_total, e2e_placed], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms, wall_ms, e2e_ms = t.tolist()
-    placed_all, e2e_all = cnt.tolist()
+    # ---- max over ranks of the times, sum over ranks of the work (swarmkit_b200/dist.py)
+    from swarmkit_b200.dist import reduce_step
+    (dev_ms, wall_ms, e2e_ms), (placed_all, e2e_all) = reduce_step([dev_ms, wall_ms, e2e_ms], [placed_total, e2e_placed])
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -266,7 +261,8 @@ def main():
             "placed_per_step": placed_all / args.steps / world,
             "evals_per_s_per_gpu": st["evals"] / scan_s if scan_s > 0 else None,
             "split_ms_per_step": {"scan": st["scan_ms"] / args.steps, "sequencer": st["sequencer_ms"] / args.steps},
-            "paths": {"fast": st["fast_path"], "slow": st["slow_path"]},
+            "paths": {"fast": st["fast_path"], "medium": st["medium_path"], "slow": st["slow_path"]},
+            "sequencer_cycles": {"fast": st["seq_cycles_fast"], "medium": st["seq_cycles_medium"], "generic": st["seq_cycles_generic"]},
             "e2e": {"value": e2e_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(st["kernel_launches"]),

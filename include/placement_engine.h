@@ -205,6 +205,7 @@ typedef struct pe_stats {
     double h2d_ms, d2h_ms;
     double run_ms;             /* CUDA-event time from the first to the last kernel of pe_tick_run */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t seq_cycles_fast, seq_cycles_medium, seq_cycles_generic; /* SM cycles of the sequencer per mode */
 } pe_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */

@@ -88,7 +88,8 @@ class pe_stats(C.Structure):
                 ("placements", C.c_uint64), ("fast_path", C.c_uint64), ("medium_path", C.c_uint64), ("slow_path", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("sequencer_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("run_ms", C.c_double),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("seq_cycles_fast", C.c_uint64),
+                ("seq_cycles_medium", C.c_uint64), ("seq_cycles_generic", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

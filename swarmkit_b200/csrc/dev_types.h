@@ -15,6 +15,9 @@
 
 // Status bits the kernels raise in DevStatus::error.
 #define PE_DEV_ERR_SVC_OVERFLOW 0x1u  // a per-service count reached 2^24
+#define PE_DEV_ERR_WD_CONSUMER 0x10u  // watchdog: sequencer consumer waited > 1 s for a ring slot
+#define PE_DEV_ERR_WD_DRAIN 0x20u     // watchdog: drain of an armed ring slot
+#define PE_DEV_ERR_WD_SCAN 0x40u      // watchdog: scan kernel waited > 1 s for a node tile
 
 struct DevTable {
     uint32_t n_nodes;   // rows covered by scans (N)
@@ -54,11 +57,24 @@ struct ScanResult {
     uint32_t w0;            // first valid word of the best-class bitmap (earlier words are stale)
     uint32_t w1;            // first valid word of the second-class bitmap
     uint32_t row0;          // physical row (0/1) holding the best class
+    uint32_t n0, n1;        // members of the best / second class (the first PE_LIST_CAP of each are listed)
     uint32_t pad;
+    // what the sequencer's fast path needs to commit, so that it reads ONE record per task
+    uint32_t tie_start;
+    uint32_t task_off;
+    uint32_t flags;         // PE_SR_*
+    long long cpu_res, mem_res;
+    uint32_t *svccol;       // the task's per-service counter column
 };
+#define PE_SR_SIMPLE 1u     // no generic resources / host ports: the reservation is four reductions
+#define PE_SR_COUNTS 2u     // DesiredState <= COMPLETED: bumps the spread counters
+#define PE_SR_K1 4u         // the group really has exactly one task
 
 struct DevCounters {
     unsigned long long fast_path, medium_path, slow_path, placements, evals_generic;
+    unsigned long long cyc_fast, cyc_medium, cyc_generic;   // SM cycles the sequencer spent in each mode
+    unsigned long long cyc_cons_wait, cyc_cons_work, stops[5], iters;   // consumer warp: waiting on producers / working; fast-mode exits by reason
     uint32_t error;
     uint32_t pad;
+    uint32_t marks[16];   // debug breadcrumbs of the sequencer pipeline
 };

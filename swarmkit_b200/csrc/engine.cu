@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -80,6 +81,7 @@ struct pe_engine {
     uint8_t *st_flags_g = nullptr;
     uint32_t *touched_g = nullptr;
     uint32_t *E = nullptr; size_t E_words = 0;
+    uint32_t *Lbuf = nullptr; size_t L_words = 0;   // class member lists
     ScanResult *scan_out = nullptr; uint32_t scan_out_cap = 0;
     DevCounters *d_ctr = nullptr;
     void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
@@ -143,7 +145,7 @@ struct pe_engine {
         for (auto p : gen) fr(p);
         for (auto p : d_tab) fr(p);
         fr(tick_buf); fr(d_out_node); fr(d_out_fail); fr(ff8); fr(pref64); fr(cand_g); fr(st_cpu_g); fr(st_mem_g); fr(st_gen_g);
-        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(scan_out); fr(d_ctr); fr(up_buf);
+        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf);
         for (auto &p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         if (stream) cudaStreamDestroy(stream);
     }
@@ -489,7 +491,7 @@ struct pe_engine {
         P.T = table(); P.K = K;
         P.g_begin = g0; P.g_end = g1;
         P.scan = with_scan ? scan_out : nullptr;
-        P.E = E; P.e_stride = e_stride();
+        P.E = E; P.e_stride = e_stride(); P.L = Lbuf;
         P.ff8 = ff8; P.pref64 = pref64; P.cand_g = cand_g;
         P.st_cpu_g = st_cpu_g; P.st_mem_g = st_mem_g; P.st_svc_g = st_svc_g; P.st_tot_g = st_tot_g;
         P.st_placed_g = st_placed_g; P.st_flags_g = st_flags_g; P.st_gen_g = st_gen_g; P.st_cap = st_cap;
@@ -497,6 +499,7 @@ struct pe_engine {
         P.touched_words = with_scan ? (n_nodes + 31) / 32 : 0;
         P.touched_in_smem = P.touched_words <= 12288 ? 1 : 0;   // <= 48 KB of shared memory
         P.ctr = d_ctr;
+        P.dbg_flags = getenv("PE_SEQ_FLAGS") ? (uint32_t)atoi(getenv("PE_SEQ_FLAGS")) : 0u;
         size_t dyn = seq_dyn_smem_bytes(P.touched_in_smem ? P.touched_words : 0);
         EvPair *ev = ev_begin(1);
         k_sequencer<<<1, PE_SEQ_THREADS, dyn, stream>>>(P);
@@ -608,7 +611,7 @@ struct pe_engine {
         P.n_nodes = n_nodes;
         P.g_begin = g0; P.n_tasks = B;
         P.svc = reinterpret_cast<uint32_t *const *>(d_tab[2]);
-        P.out = scan_out; P.E = E; P.e_stride = e_stride();
+        P.out = scan_out; P.E = E; P.e_stride = e_stride(); P.L = Lbuf;
         return true;
     }
 
@@ -625,6 +628,11 @@ struct pe_engine {
                 void *p = E; size_t c = E_words * 4;
                 if ((rc = ensure_buf(p, c, need * 4))) return rc;
                 E = reinterpret_cast<uint32_t *>(p); E_words = c / 4;
+            }
+            if ((size_t)Bmax * 2u * PE_LIST_CAP > L_words) {
+                void *p = Lbuf; size_t c = L_words * 4;
+                if ((rc = ensure_buf(p, c, (size_t)Bmax * 2u * PE_LIST_CAP * 4))) return rc;
+                Lbuf = reinterpret_cast<uint32_t *>(p); L_words = c / 4;
             }
             if (Bmax > scan_out_cap) {
                 void *p = scan_out; size_t c = (size_t)scan_out_cap * sizeof(ScanResult);
@@ -678,7 +686,13 @@ struct pe_engine {
         CU(cudaMemset(d_ctr, 0, sizeof c));
         stats.fast_path += c.fast_path; stats.medium_path += c.medium_path; stats.slow_path += c.slow_path;
         stats.placements += c.placements; stats.evals_generic += c.evals_generic;
+        stats.seq_cycles_fast += c.cyc_fast; stats.seq_cycles_medium += c.cyc_medium; stats.seq_cycles_generic += c.cyc_generic;
+        if (getenv("PE_DEBUG_SEQ")) fprintf(stderr, "[seq] wait %llu work %llu iters %llu stops end=%llu none=%llu window=%llu neutral=%llu exhausted=%llu\n", c.cyc_cons_wait, c.cyc_cons_work, c.iters, c.stops[0], c.stops[1], c.stops[2], c.stops[3], c.stops[4]);
         ev_collect();
+        if (c.error & (PE_DEV_ERR_WD_CONSUMER | PE_DEV_ERR_WD_DRAIN | PE_DEV_ERR_WD_SCAN)) {
+            char b[400]; snprintf(b, sizeof b, "device watchdog fired (code 0x%x): a kernel pipeline stalled; marks start=%u end=%u pstage=%u stopped=%u vstop=%u nlist=%u nclass=%u c0hi=%u | cons task=%u slot=%u round=%u", c.error, c.marks[0], c.marks[1], c.marks[2], c.marks[3], c.marks[4], c.marks[5], c.marks[6], c.marks[7], c.marks[8], c.marks[9], c.marks[10]);
+            err = b; return PE_ERR_CUDA;
+        }
         if (c.error & PE_DEV_ERR_SVC_OVERFLOW) { err = "a per-service task count reached 2^24 - 1 on one node"; return PE_ERR_OVERFLOW; }
         return PE_OK;
     }

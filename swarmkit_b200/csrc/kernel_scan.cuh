@@ -33,6 +33,7 @@ namespace pe {
 #define PE_SCAN_MAXATTR 96
 #define PE_SCAN_MAXGENK 16
 #define PE_SCAN_MAXW 8         // port / plugin bit words
+#define PE_LIST_CAP 1024       // class members listed explicitly per class (the sequencer's fast path reads these)
 
 struct ScanCol {
     const void *base;
@@ -55,6 +56,7 @@ struct ScanParams {
     ScanResult *out;
     uint32_t *E;
     uint32_t e_stride;
+    uint32_t *L;          // member lists: [task][2][PE_LIST_CAP] node indices of the first members of each class
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,6 +174,9 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
     // current 32-step block
     uint32_t b1h = 0xFFFFFFFFu, b1l = 0xFFFFFFFFu, b2h = 0xFFFFFFFFu, b2l = 0xFFFFFFFFu;
     uint32_t w01 = 0, w02 = 0, rowsel = 0, my1 = 0, my2 = 0;
+    uint32_t cnt1 = 0, cnt2 = 0;                         // members of each class so far
+    uint32_t *Lrows = P.L + (size_t)task * 2u * PE_LIST_CAP;
+    const uint32_t lane_lt = (1u << lane) - 1u;
     uint32_t *Erows = P.E + (size_t)task * 2u * P.e_stride;
     const uint32_t steps = TN >> 5;
 
@@ -298,10 +303,13 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
                             b2h = b1h; b2l = b1l; w02 = w01;
                             rowsel ^= 1u;
                             const uint32_t t = my1; my1 = my2; my2 = t;
+                            cnt2 = cnt1;
                         } else {
                             b2h = sh; b2l = sl; w02 = curw;     // (possibly none)
+                            cnt2 = 0;
                         }
                         b1h = mh; b1l = ml; w01 = curw;
+                        cnt1 = 0;
                     } else {
                         const bool lt2 = ok & !eq1 & ((hi < b2h) | ((hi == b2h) & (lo < b2l)));
                         if (__any_sync(0xFFFFFFFFu, lt2)) {
@@ -309,10 +317,23 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
                             const uint32_t sh = __reduce_min_sync(0xFFFFFFFFu, lt2 ? hi : 0xFFFFFFFFu);
                             const uint32_t sl = __reduce_min_sync(0xFFFFFFFFu, (lt2 && hi == sh) ? lo : 0xFFFFFFFFu);
                             b2h = sh; b2l = sl; w02 = curw;
+                            cnt2 = 0;
                         }
                     }
                     const uint32_t word1 = __ballot_sync(0xFFFFFFFFu, ok & (hi == b1h) & (lo == b1l));
                     const uint32_t word2 = __ballot_sync(0xFFFFFFFFu, ok & (hi == b2h) & (lo == b2l));
+                    // explicit member lists (node order) while they are short: what the sequencer's
+                    // ordered fast path actually walks
+                    if (cnt1 < PE_LIST_CAP && word1) {
+                        const uint32_t at = cnt1 + __popc(word1 & lane_lt);
+                        if (((word1 >> lane) & 1u) && at < PE_LIST_CAP) Lrows[rowsel * PE_LIST_CAP + at] = tile_base + s * 32u + lane;
+                    }
+                    if (cnt2 < PE_LIST_CAP && word2) {
+                        const uint32_t at = cnt2 + __popc(word2 & lane_lt);
+                        if (((word2 >> lane) & 1u) && at < PE_LIST_CAP) Lrows[(rowsel ^ 1u) * PE_LIST_CAP + at] = tile_base + s * 32u + lane;
+                    }
+                    cnt1 += __popc(word1);
+                    cnt2 += __popc(word2);
                     if (lane == (s & 31u)) { my1 = word1; my2 = word2; }
                     if ((s & 31u) == 31u) {
                         const uint32_t wi = tile * steps + (s & ~31u) + lane;
@@ -334,7 +355,13 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
         ScanResult r;
         r.c0 = ((unsigned long long)b1h << 32) | b1l;   // all ones = PE_PREF_NONE
         r.c1 = ((unsigned long long)b2h << 32) | b2l;
-        r.w0 = w01; r.w1 = w02; r.row0 = rowsel; r.pad = 0;
+        r.w0 = w01; r.w1 = w02; r.row0 = rowsel;
+        r.n0 = cnt1; r.n1 = cnt2;
+        r.tie_start = G.tie_start; r.task_off = G.task_off;
+        r.flags = ((G.gen_cnt == 0 && G.port_cnt == 0) ? PE_SR_SIMPLE : 0u) | (G.n_tasks == 1 ? PE_SR_K1 : 0u) |
+                  ((G.n_tasks >= 1 && (P.K.task_flags[G.task_off] & PE_T_COUNTS)) ? PE_SR_COUNTS : 0u);
+        r.cpu_res = G.cpu_res; r.mem_res = G.mem_res;
+        r.svccol = const_cast<uint32_t *>(svccol);
         P.out[task] = r;
     }
 }

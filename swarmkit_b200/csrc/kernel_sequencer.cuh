@@ -40,7 +40,7 @@ __device__ __forceinline__ bool key_less(const CandKey &a, const CandKey &b) {
 #define PE_SEQ_THREADS 1024
 #define PE_SEQ_KS 2048          // candidates staged in shared memory
 #define PE_SEQ_RING 16          // fast-mode ring slots
-#define PE_SEQ_NPW 15           // producer warps (warps 1..NPW)
+#define PE_SEQ_NPW 8            // producer warps (warps 1..NPW)
 #define PE_SEQ_WIN 1024         // bitmap words staged per task (32k nodes)
 #define PE_MAX_GEN_WANTS 8
 #define PE_CTX_MAXC 16
@@ -58,6 +58,11 @@ __device__ __forceinline__ void sq_mbar_inval(unsigned long long *bar) {
 __device__ __forceinline__ void sq_mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(seq_smem_u32(bar)) : "memory");
 }
+// Arrive without release ordering: the consumer's empty-slot signal must not wait for its
+// outstanding global reductions / stores to be acknowledged (that costs ~1 us per task).
+__device__ __forceinline__ void sq_mbar_arrive_relaxed(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(seq_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool sq_mbar_try_wait(unsigned long long *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -68,8 +73,25 @@ __device__ __forceinline__ bool sq_mbar_try_wait(unsigned long long *bar, uint32
         "}\n" : "=r"(ok) : "r"(seq_smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void sq_mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(seq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void sq_tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(seq_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(seq_smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void sq_mbar_wait(unsigned long long *bar, uint32_t parity) {
     while (!sq_mbar_try_wait(bar, parity)) {}
+}
+// Same, but gives up after ~1 s and raises a device error instead of hanging the GPU.
+__device__ __forceinline__ bool sq_mbar_wait_wd(unsigned long long *bar, uint32_t parity, DevCounters *ctr, uint32_t code) {
+    const long long t0 = clock64();
+    while (!sq_mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) { atomicOr(&ctr->error, code); return false; }
+    }
+    return true;
 }
 
 struct SeqParams {
@@ -77,8 +99,9 @@ struct SeqParams {
     TickDev K;
     uint32_t g_begin, g_end;
     const ScanResult *scan;  // [g_end - g_begin] or nullptr
-    const uint32_t *E;       // class bitmaps, e_stride words per task
+    const uint32_t *E;       // class bitmaps, two rows of e_stride words per task
     uint32_t e_stride;
+    const uint32_t *L;       // class member lists, [task][2][PE_LIST_CAP]
     uint8_t *ff8;                 // [cap] first failing filter (0 pass, 0xFF not in set)
     unsigned long long *pref64;   // [cap]
     CandKey *cand_g;              // [st_cap]
@@ -91,6 +114,7 @@ struct SeqParams {
     uint32_t touched_words;
     uint32_t touched_in_smem;
     DevCounters *ctr;
+    uint32_t dbg_flags;   // debugging switches (PE_SEQ_FLAGS)
 };
 
 // Per-group evaluation context resolved once into shared memory so that a node
@@ -108,6 +132,7 @@ struct FastTask {      // staged descriptor of one k=1 task
     long long cpu_res, mem_res;
     uint32_t *svccol;
     uint32_t w0, tie_start, task_off, simple, counts, ws, row0;
+    uint32_t n_list, n_class;   // list mode (tie_start == 0): listed / total members of the best class; n_list == 0: bitmap mode
 };
 
 struct SeqShared {
@@ -115,7 +140,8 @@ struct SeqShared {
     GroupCtx C;
     FastTask ft[PE_SEQ_RING];
     unsigned long long full_bar[PE_SEQ_RING], empty_bar[PE_SEQ_RING];
-    uint32_t stop, resume, stop_reason, bars_live;
+    uint32_t stop, resume, stop_reason, bars_live, consumed;
+    uint32_t armed[PE_SEQ_RING];
     uint32_t red32[40];
     unsigned long long red64[40];
     uint32_t bins[256];
@@ -242,6 +268,188 @@ __device__ __forceinline__ uint32_t eval_ctx(const DevTable &T, const TickDev &K
     return 0;
 }
 
+
+// ---- fast mode, consumer warp: tasks strictly in order, shared memory only on the common path
+struct SeqDebug { unsigned long long n_fast, n_placed, iters, stops[5]; long long cyc_wait, cyc_work; };
+
+// Everything the ordered loop reads from the kernel parameters, copied into registers once:
+// going through a reference to the __grid_constant__ parameter block costs hundreds of cycles per access.
+struct FastEnv {
+    uint32_t *out_node, *out_fail, *total;
+    int64_t *cpu, *mem;
+    const uint32_t *E;
+    const pe_group *groups;
+    DevCounters *ctr;
+    uint32_t g_begin, g_end, e_stride, N;
+};
+
+__device__ __forceinline__ void fast_commit(const SeqParams &P, const FastEnv &V, const FastTask &f, uint32_t gq, uint32_t n, uint32_t *touched) {
+    V.out_node[f.task_off] = n;
+    if (f.simple) {   // NodeInfo.addTask, nodeinfo.go:125-153, as fire-and-forget reductions
+        if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&V.cpu[n]), (unsigned long long)(-f.cpu_res));
+        if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&V.mem[n]), (unsigned long long)(-f.mem_res));
+        if (f.counts) { atomicAdd(&V.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
+    } else {
+        add_task_global(P.T, P.K, V.groups[gq], n, f.counts != 0, V.ctr);
+    }
+    touched[n >> 5] |= 1u << (n & 31u);
+}
+
+__device__ __noinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uint32_t *touched, const uint32_t *ring, uint32_t start,
+                                           SeqDebug &dbg_out) {
+    SeqDebug dbg = dbg_out;   // registers inside the loop
+    const uint32_t lane = threadIdx.x & 31u;
+    FastEnv V;
+    V.out_node = P.K.out_node; V.out_fail = P.K.out_fail; V.total = P.T.total; V.cpu = P.T.cpu; V.mem = P.T.mem;
+    V.E = P.E; V.groups = P.K.groups; V.ctr = P.ctr; V.g_begin = P.g_begin; V.g_end = P.g_end; V.e_stride = P.e_stride; V.N = P.T.n_nodes;
+    const uint32_t N = V.N, nwords = (N + 31u) >> 5;
+    uint32_t i = 0, reason = 0;
+    for (; start + i < V.g_end; i++) {
+        const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
+        const long long tw0 = clock64();
+        if (!sq_mbar_wait_wd(&S.full_bar[slot], round & 1u, V.ctr, PE_DEV_ERR_WD_CONSUMER)) { reason = 1; break; }
+        const long long tw1 = clock64();
+        dbg.cyc_wait += tw1 - tw0;
+        const FastTask &f = S.ft[slot];
+        if (f.c0 == PE_PREF_NONE) { reason = 1; break; }      // nothing feasible when the batch began, or k != 1
+        uint32_t n = PE_NONE;
+        if (f.n_list) {
+            // ---- list mode (canonical tie order): the first members of the class in node order
+            const uint4 *lst4 = reinterpret_cast<const uint4 *>(ring + slot * PE_SEQ_WIN);
+            for (uint32_t j = 0; j < f.n_list && n == PE_NONE; j += 128u) {
+                const uint32_t il = j + lane * 4u;
+                uint32_t first = PE_NONE;
+                if (il < f.n_list) {
+                    const uint4 e = lst4[il >> 2];
+                    const uint32_t left = f.n_list - il;
+                    if (left > 3u && !((touched[e.w >> 5] >> (e.w & 31u)) & 1u)) first = e.w;
+                    if (left > 2u && !((touched[e.z >> 5] >> (e.z & 31u)) & 1u)) first = e.z;
+                    if (left > 1u && !((touched[e.y >> 5] >> (e.y & 31u)) & 1u)) first = e.y;
+                    if (!((touched[e.x >> 5] >> (e.x & 31u)) & 1u)) first = e.x;
+                }
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, first != PE_NONE);
+                if (b) n = __shfl_sync(0xFFFFFFFFu, first, __ffs((int)b) - 1);
+                dbg.iters++;
+            }
+            if (n == PE_NONE && f.n_class > f.n_list) {
+                // the class goes on past the listed members: continue on its bitmap (L2), 32 words a round
+                const uint32_t last = ring[slot * PE_SEQ_WIN + f.n_list - 1u];
+                const uint32_t *Erow = V.E + ((size_t)(start + i - V.g_begin) * 2u + f.row0) * V.e_stride;
+                for (uint32_t wb = last >> 5; wb < nwords && n == PE_NONE; wb += 32u) {
+                    const uint32_t w = wb + lane;
+                    uint32_t v = 0;
+                    if (w < nwords) {
+                        v = Erow[w] & ~touched[w];
+                        if (w == (last >> 5)) v &= (last & 31u) == 31u ? 0u : (0xFFFFFFFFu << ((last & 31u) + 1u));
+                        if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
+                    }
+                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0u);
+                    if (b) {
+                        const int src = __ffs((int)b) - 1;
+                        const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
+                        n = (wb + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
+                    }
+                    dbg.iters++;
+                }
+            }
+            if (n == PE_NONE) { reason = 4; break; }           // the whole class is consumed
+        } else {
+            // ---- bitmap mode (rotated tie order): the staged window of the class bitmap
+            const uint32_t lo_bit = max(f.tie_start, f.w0 * 32u);
+            const uint32_t lo_word = lo_bit >> 5;
+            const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - f.ws);    // f.ws: window start, multiple of 4 words
+            const uint32_t *buf = ring + slot * PE_SEQ_WIN;
+            for (uint32_t j = 0; j < nwin && n == PE_NONE; j += 32u) {
+                const uint32_t w = f.ws + j + lane;
+                uint32_t v = 0;
+                if (j + lane < nwin && w >= lo_word) {
+                    v = buf[j + lane] & ~touched[w];
+                    if (w == lo_word) v &= 0xFFFFFFFFu << (lo_bit & 31u);
+                    if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
+                }
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0u);
+                if (b) {
+                    const int src = __ffs((int)b) - 1;
+                    const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
+                    n = (f.ws + j + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
+                }
+            }
+            if (n == PE_NONE) { reason = 2; break; }           // not inside the staged window (may wrap): block-wide walk
+        }
+        const bool counts = f.counts != 0u;
+        if (lane == 0) { fast_commit(P, V, f, start + i, n, touched); dbg.n_fast++; dbg.n_placed++; }
+        if (lane < 8) V.out_fail[(size_t)(start + i) * PE_NUM_FILTERS + lane] = 0;
+        __syncwarp();
+        if (lane == 0) sq_mbar_arrive_relaxed(&S.empty_bar[slot]);   // slot reads are done (their values were used above)
+        dbg.cyc_work += clock64() - tw1;
+        if (!counts) { reason = 3; i++; break; }               // rank did not move: later class bitmaps may hide this node
+    }
+    dbg.stops[reason]++;
+    if (lane == 0) {
+        S.resume = start + i;
+        S.consumed = i;
+        S.stop_reason = reason;
+        if (reason == 3) S.neutral = 1;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t *>(&S.stop) = 1;
+    }
+    dbg_out = dbg;
+}
+
+// ---- fast mode, producer warps (warps 1..PE_SEQ_NPW): warp p prefetches the tasks i == p-1 (mod NPW);
+// one converged lane per warp issues the TMA copy (the CUTLASS elect-one idiom).
+__device__ __noinline__ void fast_producer(const SeqParams &P, SeqShared &S, uint32_t *ring, uint32_t start) {
+    const uint32_t lane = threadIdx.x & 31u, pw = (threadIdx.x >> 5) - 1u;
+    const uint32_t nwords = (P.T.n_nodes + 31u) >> 5;
+    const ScanResult *scan = P.scan; const uint32_t *E = P.E, *L = P.L;
+    const uint32_t g_begin = P.g_begin, g_end = P.g_end, e_stride = P.e_stride;
+    volatile uint32_t *vstop = &S.stop;
+    for (uint32_t i = pw; start + i < g_end; i += PE_SEQ_NPW) {
+        const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
+        const uint32_t gq = start + i;
+        uint32_t go = 1;
+        if (lane == 0) {
+            const ScanResult sr = scan[gq - g_begin];          // issued before the wait: overlaps it
+            while (!sq_mbar_try_wait(&S.empty_bar[slot], (round & 1u) ^ 1u)) {
+                if (*vstop) { go = 0; break; }
+                __nanosleep(32);
+            }
+            if (*vstop) go = 0;
+            if (go) {
+                FastTask f;
+                f.c0 = (sr.flags & PE_SR_K1) ? sr.c0 : PE_PREF_NONE;
+                f.w0 = sr.w0; f.row0 = sr.row0;
+                f.tie_start = sr.tie_start;
+                f.task_off = sr.task_off;
+                f.cpu_res = sr.cpu_res; f.mem_res = sr.mem_res;
+                f.simple = (sr.flags & PE_SR_SIMPLE) ? 1u : 0u;
+                f.counts = (sr.flags & PE_SR_COUNTS) ? 1u : 0u;
+                f.svccol = sr.svccol;
+                f.ws = (max(sr.tie_start, sr.w0 * 32u) >> 5) & ~3u;     // 16-byte aligned window start
+                f.n_class = sr.n0;
+                f.n_list = (sr.tie_start == 0u && f.c0 != PE_PREF_NONE) ? min(sr.n0, (uint32_t)PE_LIST_CAP) : 0u;
+                S.ft[slot] = f;
+                S.armed[slot] = i + 1u;
+                if (f.n_list) {
+                    const uint32_t bytes = ((f.n_list + 3u) & ~3u) * 4u;
+                    sq_mbar_expect_tx(&S.full_bar[slot], bytes);
+                    sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, L + ((size_t)(gq - g_begin) * 2u + f.row0) * PE_LIST_CAP, bytes, &S.full_bar[slot]);
+                } else if (f.c0 != PE_PREF_NONE && f.ws < nwords) {
+                    // rows are padded to e_stride (a multiple of 32 words), so the copy may run past nwords
+                    const uint32_t nw = min((uint32_t)PE_SEQ_WIN, e_stride - f.ws);
+                    const uint32_t *src = E + ((size_t)(gq - g_begin) * 2u + f.row0) * e_stride + f.ws;
+                    sq_mbar_expect_tx(&S.full_bar[slot], nw * 4u);
+                    sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, src, nw * 4u, &S.full_bar[slot]);
+                } else {
+                    sq_mbar_arrive(&S.full_bar[slot]);
+                }
+            }
+        }
+        go = __shfl_sync(0xFFFFFFFFu, go, 0);    // the whole warp leaves together (and reaches the block barrier converged)
+        if (!go) break;
+    }
+}
+
 __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_constant__ SeqParams P) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ SeqShared S;
@@ -267,25 +475,31 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     for (uint32_t w = tid; w < P.touched_words; w += nth) touched[w] = 0;
     if (tid == 0) { S.neutral = 0; S.bars_live = 0; S.bestv[0] = S.bestv[1] = S.bestv[2] = PE_NONE; }
     uint32_t slot = 0;   // uniform across the block
-    unsigned long long n_fast = 0, n_medium = 0, n_slow = 0, n_placed = 0, n_evalg = 0;   // thread 0's private tallies
+    unsigned long long n_fast = 0, n_medium = 0, n_slow = 0, n_placed = 0, n_evalg = 0;
+    long long cyc_fast = 0, cyc_medium = 0, cyc_generic = 0, t_mark = clock64();
+    SeqDebug dbg{};   // thread 0's private tallies
     __syncthreads();
 
     uint32_t gi = P.g_begin;
     while (gi < P.g_end) {
         // ================= fast mode: warp-specialised pipeline over k == 1 tasks ====
-        // Warps 1..NPW prefetch (descriptor + first PE_SEQ_WIN words of the best-class
-        // bitmap) into a ring of shared-memory slots; warp 0 consumes the slots IN
-        // ORDER, so the ordered part touches shared memory only.  Hand-off uses
-        // mbarriers (full/empty per slot).  The mode ends at the first task the
-        // bitmaps cannot resolve; that task takes the block-wide path below.
+        // Producer warps prefetch, per task, the scan record and the first PE_SEQ_WIN
+        // words of its best-class bitmap (one TMA bulk copy, completion on the slot's
+        // mbarrier) into a ring of shared-memory slots; warp 0 consumes the slots IN
+        // ORDER, so the ordered part touches shared memory only.  The mode ends at the
+        // first task the bitmaps cannot resolve; that task takes the block-wide path.
         if (P.scan != nullptr && !S.neutral) {
             __syncthreads();
+            { const long long t1 = clock64(); cyc_generic += t1 - t_mark; t_mark = t1; }
             if (tid == 0) {
                 for (int r = 0; r < PE_SEQ_RING; r++) {
-                    if (S.bars_live) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.empty_bar[r]); }
+                    if (S.bars_live && !(P.dbg_flags & 2u)) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.empty_bar[r]); }
                     sq_mbar_init(&S.full_bar[r], 1);
                     sq_mbar_init(&S.empty_bar[r], 1);
+                    S.armed[r] = 0;
                 }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                if (P.dbg_flags & 4u) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 S.bars_live = 1;
                 S.stop = 0;
                 S.resume = P.g_end;
@@ -295,106 +509,18 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             const uint32_t start = gi;
             const uint32_t nwords = (N + 31u) >> 5;
             volatile uint32_t *vstop = &S.stop;
+            if (warp == 0) fast_consumer(P, S, touched, ring, start, dbg);
+            else if (warp <= PE_SEQ_NPW) fast_producer(P, S, ring, start);
+            __syncthreads();
+            // bulk copies armed for slots the consumer never took must land before the ring is reused
             if (warp == 0) {
-                // ---------------- consumer: strictly in task order
-                uint32_t i = 0, reason = 0;
-                for (; start + i < P.g_end; i++) {
-                    const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
-                    sq_mbar_wait(&S.full_bar[slot], round & 1u);
-                    const FastTask f = S.ft[slot];
-                    if (f.c0 == PE_PREF_NONE) { reason = 1; break; }      // nothing feasible when the batch began, or k != 1
-                    const uint32_t lo_bit = max(f.tie_start, f.w0 * 32u);
-                    const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - f.ws);
-                    const uint32_t *buf = ring + slot * PE_SEQ_WIN;
-                    uint32_t n = PE_NONE;
-                    for (uint32_t j = 0; j < nwin; j += 32u) {
-                        const uint32_t w = f.ws + j + lane;
-                        uint32_t v = 0;
-                        if (j + lane < nwin) {
-                            v = buf[j + lane] & ~touched[w];
-                            if (j + lane == 0) v &= 0xFFFFFFFFu << (lo_bit & 31u);
-                            if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
-                        }
-                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0u);
-                        if (b) {
-                            const int src = __ffs((int)b) - 1;
-                            const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
-                            n = (f.ws + j + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
-                            break;
-                        }
-                    }
-                    if (n == PE_NONE) { reason = 2; break; }               // not inside the staged window
-                    if (lane == 0) {
-                        K.out_node[f.task_off] = n;
-                        if (f.simple) {                // NodeInfo.addTask, nodeinfo.go:125-153, as fire-and-forget reductions
-                            if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-f.cpu_res));
-                            if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-f.mem_res));
-                            if (f.counts) { atomicAdd(&T.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
-                        } else {
-                            add_task_global(T, K, K.groups[start + i], n, f.counts != 0, P.ctr);
-                        }
-                        touched[n >> 5] |= 1u << (n & 31u);
-                        n_fast++; n_placed++;
-                    }
-                    if (lane < 8) K.out_fail[(size_t)(start + i) * PE_NUM_FILTERS + lane] = 0;
-                    __syncwarp();
-                    if (lane == 0) sq_mbar_arrive(&S.empty_bar[slot]);
-                    if (!f.counts) { reason = 3; i++; break; }             // rank did not move: later class bitmaps may hide this node
-                }
-                if (lane == 0) {
-                    S.resume = start + i;
-                    S.stop_reason = reason;
-                    if (reason == 3) S.neutral = 1;
-                    __threadfence_block();
-                    *vstop = 1;
-                }
-            } else if (warp <= PE_SEQ_NPW) {
-                // ---------------- producers
-                for (uint32_t i = warp - 1; start + i < P.g_end; i += PE_SEQ_NPW) {
-                    const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
-                    bool stopped = false;
-                    while (!sq_mbar_try_wait(&S.empty_bar[slot], (round & 1u) ^ 1u)) {
-                        if (*vstop) { stopped = true; break; }
-                    }
-                    if (stopped || *vstop) break;
-                    const uint32_t gq = start + i;
-                    uint32_t ws = 0, valid = 0, row0 = 0;
-                    if (lane == 0) {
-                        const pe_group g = K.groups[gq];
-                        const ScanResult sr = P.scan[gq - P.g_begin];
-                        FastTask f;
-                        f.c0 = g.n_tasks == 1 ? sr.c0 : PE_PREF_NONE;
-                        f.w0 = sr.w0; f.row0 = sr.row0;
-                        f.tie_start = g.tie_start;
-                        f.task_off = g.task_off;
-                        f.cpu_res = g.cpu_res; f.mem_res = g.mem_res;
-                        f.simple = (g.gen_cnt == 0 && g.port_cnt == 0) ? 1u : 0u;
-                        f.counts = g.n_tasks == 1 ? (K.task_flags[g.task_off] & PE_T_COUNTS) : 0u;
-                        f.svccol = T.svc[g.svc_id];
-                        f.ws = max(g.tie_start, sr.w0 * 32u) >> 5;
-                        S.ft[slot] = f;
-                        ws = f.ws; valid = f.c0 != PE_PREF_NONE; row0 = f.row0;
-                    }
-                    ws = __shfl_sync(0xFFFFFFFFu, ws, 0);
-                    valid = __shfl_sync(0xFFFFFFFFu, valid, 0);
-                    row0 = __shfl_sync(0xFFFFFFFFu, row0, 0);
-                    if (valid) {
-                        const uint32_t *src = P.E + ((size_t)(gq - P.g_begin) * 2u + row0) * P.e_stride + ws;
-                        uint32_t *dst = ring + slot * PE_SEQ_WIN;
-                        const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - ws);
-                        for (uint32_t j = 0; j < nwin; j += 256u) {
-                            uint32_t v[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) { const uint32_t x = j + u * 32u + lane; v[u] = x < nwin ? src[x] : 0u; }
-#pragma unroll
-                            for (int u = 0; u < 8; u++) { const uint32_t x = j + u * 32u + lane; if (x < PE_SEQ_WIN) dst[x] = v[u]; }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) sq_mbar_arrive(&S.full_bar[slot]);
+                for (uint32_t r = 0; r < PE_SEQ_RING; r++) {     // converged: every lane waits on the same slot
+                    const uint32_t a = S.armed[r];
+                    if (a != 0u && a - 1u >= S.consumed) sq_mbar_wait_wd(&S.full_bar[r], ((a - 1u) / PE_SEQ_RING) & 1u, P.ctr, PE_DEV_ERR_WD_DRAIN);
                 }
             }
             __syncthreads();
+            { const long long t1 = clock64(); cyc_fast += t1 - t_mark; t_mark = t1; }
             gi = S.resume;
             if (gi >= P.g_end) break;
             // group gi takes the block-wide path
@@ -429,8 +555,9 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             // so the arg-min is either the first untouched member of the second class or
             // a touched member of the best class re-evaluated against the live state.
             const ScanResult sr = P.scan[this_gi - P.g_begin];
-            if (sr.c0 != PE_PREF_NONE) {
-                // (i) the best class may continue beyond the window the pipeline staged
+            const bool exhausted = S.stop_reason == 4u && S.resume == this_gi;   // the pipeline walked the complete member list
+            if (sr.c0 != PE_PREF_NONE && !exhausted) {
+                // (i) the best class may continue beyond the window / list the pipeline staged
                 const uint32_t *E1w = P.E + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * P.e_stride;
                 const uint32_t n1 = find_first(E1w, sr.w0, N, G.tie_start, touched, S, slot);
                 if (n1 != PE_NONE) {
@@ -444,6 +571,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                     }
                     if (tid < 8) ofail[tid] = 0;
                     __syncthreads();
+                    { const long long t1 = clock64(); cyc_medium += t1 - t_mark; t_mark = t1; }
                     continue;
                 }
             }
@@ -451,24 +579,48 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             if (sr.c0 != PE_PREF_NONE && sr.c1 != PE_PREF_NONE) {
                 const uint32_t *E1 = P.E + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * P.e_stride;
                 const uint32_t *E2 = P.E + ((size_t)(this_gi - P.g_begin) * 2u + (sr.row0 ^ 1u)) * P.e_stride;
-                const uint32_t n2 = find_first(E2, sr.w1, N, G.tie_start, touched, S, slot);
+                uint32_t n2 = PE_NONE;
+                const bool use_lists = G.tie_start == 0u;
+                const uint32_t *L1 = P.L + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * PE_LIST_CAP;
+                const uint32_t *L2 = P.L + ((size_t)(this_gi - P.g_begin) * 2u + (sr.row0 ^ 1u)) * PE_LIST_CAP;
+                if (use_lists && sr.n1 > 0u) {
+                    const uint32_t nl = min(sr.n1, (uint32_t)PE_LIST_CAP);
+                    uint32_t c = PE_NONE;
+                    if (tid < nl) { const uint32_t p2 = L2[tid]; if (!((touched[p2 >> 5] >> (p2 & 31u)) & 1u)) c = tid; }
+                    const uint32_t at = block_min_pos(c, S, slot);
+                    if (at != PE_NONE) n2 = L2[at];
+                    else if (sr.n1 > nl) n2 = find_first(E2, sr.w1, N, G.tie_start, touched, S, slot);
+                } else {
+                    n2 = find_first(E2, sr.w1, N, G.tie_start, touched, S, slot);
+                }
                 if (n2 != PE_NONE) {
                     unsigned long long bp = sr.c1;
                     uint32_t bt = tie_pos(n2, G.tie_start, N), bn = n2;
-                    const uint32_t nw = (N + 31u) >> 5;
-                    for (uint32_t w = sr.w0 + tid; w < nw; w += nth) {
-                        uint32_t v = E1[w] & touched[w];
-                        if (w == nw - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
-                        while (v) {
-                            const uint32_t n = w * 32u + (uint32_t)__ffs((int)v) - 1u;
-                            v &= v - 1u;
-                            const uint32_t meta = T.meta[n];
-                            const uint32_t sv = svccol[n];
-                            if (eval_ctx(T, K, G, S.C, n, meta, sv) != 0) continue;
-                            const uint32_t fails = G.fail_cnt ? fail_count(K, G, n) : 0u;
-                            const unsigned long long pref = make_pref(fails, sv, T.total[n]);
-                            const uint32_t tp = tie_pos(n, G.tie_start, N);
-                            if (pref < bp || (pref == bp && tp < bt)) { bp = pref; bt = tp; bn = n; }
+                    auto consider = [&](uint32_t n) {
+                        const uint32_t meta = T.meta[n];
+                        const uint32_t sv = svccol[n];
+                        if (eval_ctx(T, K, G, S.C, n, meta, sv) != 0) return;
+                        const uint32_t fails = G.fail_cnt ? fail_count(K, G, n) : 0u;
+                        const unsigned long long pref = make_pref(fails, sv, T.total[n]);
+                        const uint32_t tp = tie_pos(n, G.tie_start, N);
+                        if (pref < bp || (pref == bp && tp < bt)) { bp = pref; bt = tp; bn = n; }
+                    };
+                    if (use_lists && sr.n0 <= (uint32_t)PE_LIST_CAP) {
+                        // the complete best class is listed: one member per thread
+                        for (uint32_t t = tid; t < sr.n0; t += nth) {
+                            const uint32_t n = L1[t];
+                            if ((touched[n >> 5] >> (n & 31u)) & 1u) consider(n);
+                        }
+                    } else {
+                        const uint32_t nw = (N + 31u) >> 5;
+                        for (uint32_t w = sr.w0 + tid; w < nw; w += nth) {
+                            uint32_t v = E1[w] & touched[w];
+                            if (w == nw - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
+                            while (v) {
+                                const uint32_t n = w * 32u + (uint32_t)__ffs((int)v) - 1u;
+                                v &= v - 1u;
+                                consider(n);
+                            }
                         }
                     }
                     const uint32_t hi = (uint32_t)(bp >> 32), lo = (uint32_t)bp;
@@ -499,6 +651,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                     if (tid == 0) { n_medium++; n_placed++; }
                     if (tid < 8) ofail[tid] = 0;
                     __syncthreads();
+                    { const long long t1 = clock64(); cyc_medium += t1 - t_mark; t_mark = t1; }
                     continue;
                 }
             }
@@ -838,8 +991,15 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
         }
     }
     if (tid == 0) {
+        n_fast += dbg.n_fast; n_placed += dbg.n_placed;
         P.ctr->fast_path += n_fast;
         P.ctr->medium_path += n_medium;
+        cyc_generic += clock64() - t_mark;   // whatever is left is the generic path (and loop overhead)
+        P.ctr->cyc_fast += (unsigned long long)cyc_fast;
+        P.ctr->cyc_medium += (unsigned long long)cyc_medium;
+        P.ctr->cyc_generic += (unsigned long long)cyc_generic;
+        P.ctr->cyc_cons_wait += (unsigned long long)dbg.cyc_wait; P.ctr->cyc_cons_work += (unsigned long long)dbg.cyc_work; P.ctr->iters += dbg.iters;
+        for (int r = 0; r < 5; r++) P.ctr->stops[r] += dbg.stops[r];
         P.ctr->slow_path += n_slow;
         P.ctr->placements += n_placed;
         P.ctr->evals_generic += n_evalg;

@@ -1,0 +1,37 @@
+"""Rank plumbing for the N>1 benchmark arm (one process per GPU, launched by torchrun).
+
+The placement path itself has no data-path collective in round 1 (DESIGN.md section 7:
+"replicas only"); what crosses ranks is the timing reduction the bench contract asks for:
+MAX over ranks of the device time, SUM over ranks of the work done."""
+from __future__ import annotations
+
+import os
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def reduce_step(times, counts, device=None):
+    """times -> elementwise MAX over ranks, counts -> elementwise SUM over ranks (lists of floats)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return list(times), list(counts)
+    if device is None:
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(times), dtype=torch.float64, device=device)
+    c = torch.tensor(list(counts), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return t.tolist(), c.tolist()
+
+
+def shard_range(n_items: int, rank: int, world: int, align: int = 1):
+    """Contiguous [lo, hi) range of `n_items` owned by `rank` (node-index sharding),
+    boundaries aligned to `align` items (scan tiles)."""
+    per = -(-n_items // world)
+    per = -(-per // align) * align
+    lo = min(n_items, rank * per)
+    hi = min(n_items, lo + per)
+    return lo, hi

@@ -1,0 +1,55 @@
+"""world_size-2 checks of the N>1 plumbing on CPU (gloo, 127.0.0.1)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from swarmkit_b200.dist import reduce_step, shard_range
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t, c = reduce_step([10.0 + rank, 5.0 - rank], [100.0 * (rank + 1)])
+    out.put((rank, t, c))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reduce_step_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, t, c in res:
+        assert t == [11.0, 5.0] and c == [300.0]      # MAX of times, SUM of work
+
+
+def test_shard_range_covers_everything_once():
+    for n, world, align in ((100_000, 8, 1024), (1_000_000, 8, 2048), (5, 2, 1), (4096, 3, 1024)):
+        seen = 0
+        prev_hi = 0
+        for r in range(world):
+            lo, hi = shard_range(n, r, world, align)
+            assert lo == prev_hi or lo == hi == n
+            assert lo % align == 0 or lo == n
+            seen += hi - lo
+            prev_hi = hi
+        assert seen == n and prev_hi == n
