@@ -499,7 +499,6 @@ struct pe_engine {
         P.touched_words = with_scan ? (n_nodes + 31) / 32 : 0;
         P.touched_in_smem = P.touched_words <= 12288 ? 1 : 0;   // <= 48 KB of shared memory
         P.ctr = d_ctr;
-        P.dbg_flags = getenv("PE_SEQ_FLAGS") ? (uint32_t)atoi(getenv("PE_SEQ_FLAGS")) : 0u;
         size_t dyn = seq_dyn_smem_bytes(P.touched_in_smem ? P.touched_words : 0);
         EvPair *ev = ev_begin(1);
         k_sequencer<<<1, PE_SEQ_THREADS, dyn, stream>>>(P);
@@ -640,6 +639,8 @@ struct pe_engine {
                 scan_out = reinterpret_cast<ScanResult *>(p); scan_out_cap = Bmax;
             }
         }
+        // failure counters default to zero; only groups with unplaced tasks write theirs
+        if (n_groups) CU(cudaMemsetAsync(d_out_fail, 0, (size_t)n_groups * PE_NUM_FILTERS * 4, stream));
         EvPair *ev_run = ev_begin(4);
         uint32_t g = 0;
         while (g < n_groups) {
@@ -687,10 +688,9 @@ struct pe_engine {
         stats.fast_path += c.fast_path; stats.medium_path += c.medium_path; stats.slow_path += c.slow_path;
         stats.placements += c.placements; stats.evals_generic += c.evals_generic;
         stats.seq_cycles_fast += c.cyc_fast; stats.seq_cycles_medium += c.cyc_medium; stats.seq_cycles_generic += c.cyc_generic;
-        if (getenv("PE_DEBUG_SEQ")) fprintf(stderr, "[seq] wait %llu work %llu iters %llu stops end=%llu none=%llu window=%llu neutral=%llu exhausted=%llu\n", c.cyc_cons_wait, c.cyc_cons_work, c.iters, c.stops[0], c.stops[1], c.stops[2], c.stops[3], c.stops[4]);
         ev_collect();
         if (c.error & (PE_DEV_ERR_WD_CONSUMER | PE_DEV_ERR_WD_DRAIN | PE_DEV_ERR_WD_SCAN)) {
-            char b[400]; snprintf(b, sizeof b, "device watchdog fired (code 0x%x): a kernel pipeline stalled; marks start=%u end=%u pstage=%u stopped=%u vstop=%u nlist=%u nclass=%u c0hi=%u | cons task=%u slot=%u round=%u", c.error, c.marks[0], c.marks[1], c.marks[2], c.marks[3], c.marks[4], c.marks[5], c.marks[6], c.marks[7], c.marks[8], c.marks[9], c.marks[10]);
+            char b[160]; snprintf(b, sizeof b, "device watchdog fired (code 0x%x): a kernel pipeline stalled for more than a second", c.error);
             err = b; return PE_ERR_CUDA;
         }
         if (c.error & PE_DEV_ERR_SVC_OVERFLOW) { err = "a per-service task count reached 2^24 - 1 on one node"; return PE_ERR_OVERFLOW; }

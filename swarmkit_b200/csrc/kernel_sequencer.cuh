@@ -37,7 +37,7 @@ __device__ __forceinline__ bool key_less(const CandKey &a, const CandKey &b) {
     return a.pref < b.pref || (a.pref == b.pref && a.tie < b.tie);
 }
 
-#define PE_SEQ_THREADS 1024
+#define PE_SEQ_THREADS 512     // 128 registers per thread: the ordered fast path must not spill
 #define PE_SEQ_KS 2048          // candidates staged in shared memory
 #define PE_SEQ_RING 16          // fast-mode ring slots
 #define PE_SEQ_NPW 8            // producer warps (warps 1..NPW)
@@ -114,7 +114,6 @@ struct SeqParams {
     uint32_t touched_words;
     uint32_t touched_in_smem;
     DevCounters *ctr;
-    uint32_t dbg_flags;   // debugging switches (PE_SEQ_FLAGS)
 };
 
 // Per-group evaluation context resolved once into shared memory so that a node
@@ -269,72 +268,59 @@ __device__ __forceinline__ uint32_t eval_ctx(const DevTable &T, const TickDev &K
 }
 
 
-// ---- fast mode, consumer warp: tasks strictly in order, shared memory only on the common path
+// ---- fast mode, consumer warp: tasks strictly in order, shared memory only on the common path.
+// One warp executes a dependent chain (~7 cycles per instruction), so this loop is kept as short
+// as possible: no per-task global loads, no block barriers, reservations as fire-and-forget reductions.
 struct SeqDebug { unsigned long long n_fast, n_placed, iters, stops[5]; long long cyc_wait, cyc_work; };
 
-// Everything the ordered loop reads from the kernel parameters, copied into registers once:
-// going through a reference to the __grid_constant__ parameter block costs hundreds of cycles per access.
-struct FastEnv {
-    uint32_t *out_node, *out_fail, *total;
-    int64_t *cpu, *mem;
-    const uint32_t *E;
-    const pe_group *groups;
-    DevCounters *ctr;
-    uint32_t g_begin, g_end, e_stride, N;
-};
-
-__device__ __forceinline__ void fast_commit(const SeqParams &P, const FastEnv &V, const FastTask &f, uint32_t gq, uint32_t n, uint32_t *touched) {
-    V.out_node[f.task_off] = n;
+__device__ __forceinline__ void fast_commit(const SeqParams &P, const FastTask &f, uint32_t gq, uint32_t n, uint32_t *touched) {
+    const DevTable &T = P.T;
+    P.K.out_node[f.task_off] = n;
     if (f.simple) {   // NodeInfo.addTask, nodeinfo.go:125-153, as fire-and-forget reductions
-        if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&V.cpu[n]), (unsigned long long)(-f.cpu_res));
-        if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&V.mem[n]), (unsigned long long)(-f.mem_res));
-        if (f.counts) { atomicAdd(&V.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
+        if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-f.cpu_res));
+        if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-f.mem_res));
+        if (f.counts) { atomicAdd(&T.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
     } else {
-        add_task_global(P.T, P.K, V.groups[gq], n, f.counts != 0, V.ctr);
+        add_task_global(T, P.K, P.K.groups[gq], n, f.counts != 0, P.ctr);
     }
     touched[n >> 5] |= 1u << (n & 31u);
 }
 
-__device__ __noinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uint32_t *touched, const uint32_t *ring, uint32_t start,
-                                           SeqDebug &dbg_out) {
-    SeqDebug dbg = dbg_out;   // registers inside the loop
+__device__ __forceinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uint32_t *touched, const uint32_t *ring, uint32_t start,
+                                              SeqDebug &dbg) {
     const uint32_t lane = threadIdx.x & 31u;
-    FastEnv V;
-    V.out_node = P.K.out_node; V.out_fail = P.K.out_fail; V.total = P.T.total; V.cpu = P.T.cpu; V.mem = P.T.mem;
-    V.E = P.E; V.groups = P.K.groups; V.ctr = P.ctr; V.g_begin = P.g_begin; V.g_end = P.g_end; V.e_stride = P.e_stride; V.N = P.T.n_nodes;
-    const uint32_t N = V.N, nwords = (N + 31u) >> 5;
+    const uint32_t N = P.T.n_nodes, nwords = (N + 31u) >> 5;
     uint32_t i = 0, reason = 0;
-    for (; start + i < V.g_end; i++) {
+    for (; start + i < P.g_end; i++) {
         const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
-        const long long tw0 = clock64();
-        if (!sq_mbar_wait_wd(&S.full_bar[slot], round & 1u, V.ctr, PE_DEV_ERR_WD_CONSUMER)) { reason = 1; break; }
-        const long long tw1 = clock64();
-        dbg.cyc_wait += tw1 - tw0;
+        if (!sq_mbar_wait_wd(&S.full_bar[slot], round & 1u, P.ctr, PE_DEV_ERR_WD_CONSUMER)) { reason = 1; break; }
         const FastTask &f = S.ft[slot];
         if (f.c0 == PE_PREF_NONE) { reason = 1; break; }      // nothing feasible when the batch began, or k != 1
         uint32_t n = PE_NONE;
-        if (f.n_list) {
+        const uint32_t n_list = f.n_list;
+        if (n_list) {
             // ---- list mode (canonical tie order): the first members of the class in node order
             const uint4 *lst4 = reinterpret_cast<const uint4 *>(ring + slot * PE_SEQ_WIN);
-            for (uint32_t j = 0; j < f.n_list && n == PE_NONE; j += 128u) {
+            for (uint32_t j = 0; j < n_list && n == PE_NONE; j += 128u) {
                 const uint32_t il = j + lane * 4u;
                 uint32_t first = PE_NONE;
-                if (il < f.n_list) {
+                if (il < n_list) {
                     const uint4 e = lst4[il >> 2];
-                    const uint32_t left = f.n_list - il;
-                    if (left > 3u && !((touched[e.w >> 5] >> (e.w & 31u)) & 1u)) first = e.w;
-                    if (left > 2u && !((touched[e.z >> 5] >> (e.z & 31u)) & 1u)) first = e.z;
-                    if (left > 1u && !((touched[e.y >> 5] >> (e.y & 31u)) & 1u)) first = e.y;
-                    if (!((touched[e.x >> 5] >> (e.x & 31u)) & 1u)) first = e.x;
+                    const uint32_t left = n_list - il;
+                    const uint32_t tx = touched[e.x >> 5], ty = left > 1u ? touched[e.y >> 5] : ~0u;
+                    const uint32_t tz = left > 2u ? touched[e.z >> 5] : ~0u, tw = left > 3u ? touched[e.w >> 5] : ~0u;
+                    if (!((tw >> (e.w & 31u)) & 1u)) first = e.w;
+                    if (!((tz >> (e.z & 31u)) & 1u)) first = e.z;
+                    if (!((ty >> (e.y & 31u)) & 1u)) first = e.y;
+                    if (!((tx >> (e.x & 31u)) & 1u)) first = e.x;
                 }
                 const uint32_t b = __ballot_sync(0xFFFFFFFFu, first != PE_NONE);
                 if (b) n = __shfl_sync(0xFFFFFFFFu, first, __ffs((int)b) - 1);
-                dbg.iters++;
             }
-            if (n == PE_NONE && f.n_class > f.n_list) {
+            if (n == PE_NONE && f.n_class > n_list) {
                 // the class goes on past the listed members: continue on its bitmap (L2), 32 words a round
-                const uint32_t last = ring[slot * PE_SEQ_WIN + f.n_list - 1u];
-                const uint32_t *Erow = V.E + ((size_t)(start + i - V.g_begin) * 2u + f.row0) * V.e_stride;
+                const uint32_t last = ring[slot * PE_SEQ_WIN + n_list - 1u];
+                const uint32_t *Erow = P.E + ((size_t)(start + i - P.g_begin) * 2u + f.row0) * P.e_stride;
                 for (uint32_t wb = last >> 5; wb < nwords && n == PE_NONE; wb += 32u) {
                     const uint32_t w = wb + lane;
                     uint32_t v = 0;
@@ -349,7 +335,6 @@ __device__ __noinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uin
                         const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
                         n = (wb + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
                     }
-                    dbg.iters++;
                 }
             }
             if (n == PE_NONE) { reason = 4; break; }           // the whole class is consumed
@@ -377,14 +362,21 @@ __device__ __noinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uin
             if (n == PE_NONE) { reason = 2; break; }           // not inside the staged window (may wrap): block-wide walk
         }
         const bool counts = f.counts != 0u;
-        if (lane == 0) { fast_commit(P, V, f, start + i, n, touched); dbg.n_fast++; dbg.n_placed++; }
-        if (lane < 8) V.out_fail[(size_t)(start + i) * PE_NUM_FILTERS + lane] = 0;
+        if (lane == 0) {
+            // out_fail rows were zeroed when the tick started.  For the common reservation (no generic
+            // resources / host ports) only the choice is recorded here; the column updates (four
+            // reductions per task) are applied by the whole block when fast mode ends -- nothing reads
+            // those columns in between, and global atomics in this loop would serialise on their latency.
+            if (f.simple) { P.K.out_node[f.task_off] = n; touched[n >> 5] |= 1u << (n & 31u); }
+            else fast_commit(P, f, start + i, n, touched);
+        }
         __syncwarp();
         if (lane == 0) sq_mbar_arrive_relaxed(&S.empty_bar[slot]);   // slot reads are done (their values were used above)
-        dbg.cyc_work += clock64() - tw1;
         if (!counts) { reason = 3; i++; break; }               // rank did not move: later class bitmaps may hide this node
     }
-    dbg.stops[reason]++;
+    const uint32_t committed = (reason == 3) ? i : i;          // tasks [start, start+i) were placed here
+    dbg.n_fast += committed; dbg.n_placed += committed;
+    dbg.stops[reason < 5 ? reason : 0]++;
     if (lane == 0) {
         S.resume = start + i;
         S.consumed = i;
@@ -393,12 +385,11 @@ __device__ __noinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uin
         __threadfence_block();
         *reinterpret_cast<volatile uint32_t *>(&S.stop) = 1;
     }
-    dbg_out = dbg;
 }
 
 // ---- fast mode, producer warps (warps 1..PE_SEQ_NPW): warp p prefetches the tasks i == p-1 (mod NPW);
 // one converged lane per warp issues the TMA copy (the CUTLASS elect-one idiom).
-__device__ __noinline__ void fast_producer(const SeqParams &P, SeqShared &S, uint32_t *ring, uint32_t start) {
+__device__ __forceinline__ void fast_producer(const SeqParams &P, SeqShared &S, uint32_t *ring, uint32_t start) {
     const uint32_t lane = threadIdx.x & 31u, pw = (threadIdx.x >> 5) - 1u;
     const uint32_t nwords = (P.T.n_nodes + 31u) >> 5;
     const ScanResult *scan = P.scan; const uint32_t *E = P.E, *L = P.L;
@@ -493,13 +484,12 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             { const long long t1 = clock64(); cyc_generic += t1 - t_mark; t_mark = t1; }
             if (tid == 0) {
                 for (int r = 0; r < PE_SEQ_RING; r++) {
-                    if (S.bars_live && !(P.dbg_flags & 2u)) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.empty_bar[r]); }
+                    if (S.bars_live) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.empty_bar[r]); }
                     sq_mbar_init(&S.full_bar[r], 1);
                     sq_mbar_init(&S.empty_bar[r], 1);
                     S.armed[r] = 0;
                 }
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                if (P.dbg_flags & 4u) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 S.bars_live = 1;
                 S.stop = 0;
                 S.resume = P.g_end;
@@ -518,6 +508,16 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                     const uint32_t a = S.armed[r];
                     if (a != 0u && a - 1u >= S.consumed) sq_mbar_wait_wd(&S.full_bar[r], ((a - 1u) / PE_SEQ_RING) & 1u, P.ctr, PE_DEV_ERR_WD_DRAIN);
                 }
+            }
+            __syncthreads();
+            // apply the deferred reservations of the tasks fast mode placed: [start, start + consumed)
+            for (uint32_t q = start + tid; q < start + S.consumed; q += nth) {
+                const ScanResult sr = P.scan[q - P.g_begin];
+                if (!(sr.flags & PE_SR_SIMPLE)) continue;              // already applied in place
+                const uint32_t n = K.out_node[sr.task_off];
+                if (sr.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-sr.cpu_res));
+                if (sr.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-sr.mem_res));
+                if (sr.flags & PE_SR_COUNTS) { atomicAdd(&T.total[n], 1u); atomicAdd(&sr.svccol[n], 1u); }
             }
             __syncthreads();
             { const long long t1 = clock64(); cyc_fast += t1 - t_mark; t_mark = t1; }
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                 if (use_lists && sr.n1 > 0u) {
                     const uint32_t nl = min(sr.n1, (uint32_t)PE_LIST_CAP);
                     uint32_t c = PE_NONE;
-                    if (tid < nl) { const uint32_t p2 = L2[tid]; if (!((touched[p2 >> 5] >> (p2 & 31u)) & 1u)) c = tid; }
+                    for (uint32_t t = tid; t < nl && c == PE_NONE; t += nth) { const uint32_t p2 = L2[t]; if (!((touched[p2 >> 5] >> (p2 & 31u)) & 1u)) c = t; }
                     const uint32_t at = block_min_pos(c, S, slot);
                     if (at != PE_NONE) n2 = L2[at];
                     else if (sr.n1 > nl) n2 = find_first(E2, sr.w1, N, G.tie_start, touched, S, slot);
