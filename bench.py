@@ -38,6 +38,16 @@ METRIC = "task placements/sec at 1M tasks x 100k nodes"
 UNIT = "placements/s"
 
 
+def scan_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_scan launch, from the committed ncu capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["traffic_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -260,7 +270,10 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
             "placed_per_step": placed_all / args.steps / world,
             "evals_per_s_per_gpu": st["evals"] / scan_s if scan_s > 0 else None,
-            "split_ms_per_step": {"scan": st["scan_ms"] / args.steps, "sequencer": st["sequencer_ms"] / args.steps},
+            "pairs_per_s_per_gpu": st["pairs"] / world / (dev_ms / 1e3),
+            "scan_rows_per_task": st["scan_rows"] / max(placed_total, 1),
+            "split_ms_per_step": {"scan": st["scan_ms"] / args.steps, "sequencer": st["sequencer_ms"] / args.steps,
+                                  "classify_static_rows": st["prep_ms"] / args.steps},
             "paths": {"fast": st["fast_path"], "medium": st["medium_path"], "slow": st["slow_path"]},
             "sequencer_cycles": {"fast": st["seq_cycles_fast"], "medium": st["seq_cycles_medium"], "generic": st["seq_cycles_generic"]},
             "e2e": {"value": e2e_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -268,7 +281,7 @@ def main():
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": scan_traffic(), "peak_source": peak_src,
                          "note": "kernel k_scan; algorithmic bytes = sum over (task,node) evals of the columns that eval reads "
                                  "(meta 4 + total 4 + service count 4 + 4 per distinct constraint column [+16 cpu/mem, ...]); "
                                  "streaming-equivalent: node tiles are re-used by 16 tasks per CTA from shared memory and are "

@@ -206,6 +206,11 @@ typedef struct pe_stats {
     double run_ms;             /* CUDA-event time from the first to the last kernel of pe_tick_run */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t seq_cycles_fast, seq_cycles_medium, seq_cycles_generic; /* SM cycles of the sequencer per mode */
+    uint64_t pairs;            /* (task,node) pairs the batched scan covered (tasks x nodes); `evals` counts the
+                                  evaluations it executed: tasks with identical descriptors share one scan row */
+    uint64_t scan_rows;        /* distinct descriptors scanned (rows), summed over batches                       */
+    uint64_t static_evals;     /* (signature,node) evaluations of the attribute filters (k_static)               */
+    double prep_ms;            /* CUDA-event time in classify / static / rows kernels                            */
 } pe_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */

@@ -89,7 +89,8 @@ class pe_stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("sequencer_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("run_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("seq_cycles_fast", C.c_uint64),
-                ("seq_cycles_medium", C.c_uint64), ("seq_cycles_generic", C.c_uint64)]
+                ("seq_cycles_medium", C.c_uint64), ("seq_cycles_generic", C.c_uint64),
+                ("pairs", C.c_uint64), ("scan_rows", C.c_uint64), ("static_evals", C.c_uint64), ("prep_ms", C.c_double)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

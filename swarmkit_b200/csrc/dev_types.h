@@ -48,23 +48,20 @@ struct TickDev {
     uint32_t *out_fail;  // [n_groups * 8]
 };
 
-// Per-task result of the batched k=1 scan.
-// The scan keeps the two smallest rank classes of every task: bitmap rows
-// 2*task + row0 (best class) and 2*task + (row0 ^ 1) (second class).
+// Result of the batched k=1 scan for one ROW (= one distinct task descriptor of
+// the batch; tasks with identical descriptors share a row, kernel_classify.cuh).
+// The scan keeps the two smallest rank classes of every row: bitmap rows
+// 2*row (best class) and 2*row + 1 (second class), member lists likewise.
 struct ScanResult {
     unsigned long long c0;  // smallest (f5, svc, total) prefix among feasible nodes; PE_PREF_NONE if none
     unsigned long long c1;  // second smallest prefix; PE_PREF_NONE if there is no second class
-    uint32_t w0;            // first valid word of the best-class bitmap (earlier words are stale)
-    uint32_t w1;            // first valid word of the second-class bitmap
-    uint32_t row0;          // physical row (0/1) holding the best class
     uint32_t n0, n1;        // members of the best / second class (the first PE_LIST_CAP of each are listed)
-    uint32_t pad;
-    // what the sequencer's fast path needs to commit, so that it reads ONE record per task
+    // what the sequencer's fast path needs to commit, so that it reads ONE record per row
     uint32_t tie_start;
-    uint32_t task_off;
     uint32_t flags;         // PE_SR_*
     long long cpu_res, mem_res;
-    uint32_t *svccol;       // the task's per-service counter column
+    uint32_t *svccol;       // the row's per-service counter column
+    unsigned long long pad;
 };
 #define PE_SR_SIMPLE 1u     // no generic resources / host ports: the reservation is four reductions
 #define PE_SR_COUNTS 2u     // DesiredState <= COMPLETED: bumps the spread counters
@@ -74,7 +71,8 @@ struct DevCounters {
     unsigned long long fast_path, medium_path, slow_path, placements, evals_generic;
     unsigned long long cyc_fast, cyc_medium, cyc_generic;   // SM cycles the sequencer spent in each mode
     unsigned long long cyc_cons_wait, cyc_cons_work, stops[5], iters;   // consumer warp: waiting on producers / working; fast-mode exits by reason
+    unsigned long long scan_evals, scan_bytes;     // (row,node) evaluations the scan kernel executed / their algorithmic bytes
+    unsigned long long static_evals, scan_rows;    // (signature,node) evaluations of k_static; rows scanned
     uint32_t error;
     uint32_t pad;
-    uint32_t marks[16];   // debug breadcrumbs of the sequencer pipeline
 };

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kernel_misc.cuh"
+#include "kernel_classify.cuh"
 #include "kernel_scan.cuh"
 #include "kernel_sequencer.cuh"
 
@@ -65,10 +66,11 @@ struct pe_engine {
     // ---- staged tick
     void *tick_buf = nullptr; size_t tick_cap = 0;
     TickDev K{};
-    std::vector<pe_group> groups;
-    std::vector<pe_constraint> h_cons;
-    std::vector<pe_generic_want> h_gens;
-    std::vector<uint32_t> h_ports, h_plugs;
+    struct Run { uint32_t begin, end; bool one; };   // maximal runs of k == 1 / k != 1 groups
+    std::vector<Run> runs;
+    // what the k == 1 groups of the staged tick use (decides the scan's tile columns and variant)
+    bool use_res = false, use_dyn = false, scan_ok = true;
+    std::vector<uint8_t> use_gen, use_pw;
     uint32_t n_groups = 0, n_tasks = 0;
     uint32_t *d_out_node = nullptr, *d_out_fail = nullptr; size_t out_node_cap = 0, out_fail_cap = 0;
 
@@ -83,6 +85,11 @@ struct pe_engine {
     uint32_t *E = nullptr; size_t E_words = 0;
     uint32_t *Lbuf = nullptr; size_t L_words = 0;   // class member lists
     ScanResult *scan_out = nullptr; uint32_t scan_out_cap = 0;
+    // descriptor classes / signature bitmaps / rows (kernel_classify.cuh)
+    void *cls_buf = nullptr; size_t cls_cap = 0;     // per-run arrays
+    void *rows_buf = nullptr; size_t rows_cap = 0;   // per-batch arrays
+    uint32_t *Sbuf = nullptr; size_t S_words = 0;    // signature bitmaps
+    uint32_t *d_cls_counters = nullptr;              // [0] signatures [1] classes [2] rows of the current batch
     DevCounters *d_ctr = nullptr;
     void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
 
@@ -108,30 +115,16 @@ struct pe_engine {
         cfg_flags = cfg->flags;
         max_batch = cfg->max_batch;
         CU(cudaMalloc(&d_ctr, sizeof(DevCounters)));
+        CU(cudaMalloc(&d_cls_counters, 16));
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
         CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(12288)));
-        for (auto fn : scan_variants()) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         int32_t rc = ensure_cap(cfg->node_capacity ? cfg->node_capacity : 1);
         if (rc) return rc;
         // the five fixed attribute columns always exist
         for (uint32_t c = 0; c < PE_ATTR_FIRST_LABEL; c++) { rc = ensure_col(attr, c, 4); if (rc) return rc; }
         return PE_OK;
-    }
-
-    typedef void (*ScanFn)(const ScanParams);
-    // [NE index 0/4/8/16][has_res][has_extra]
-    static ScanFn scan_fn(int ne_idx, bool res, bool extra) {
-        static ScanFn tab[4][2][2] = {
-            {{k_scan<0, false, false>, k_scan<0, false, true>}, {k_scan<0, true, false>, k_scan<0, true, true>}},
-            {{k_scan<4, false, false>, k_scan<4, false, true>}, {k_scan<4, true, false>, k_scan<4, true, true>}},
-            {{k_scan<8, false, false>, k_scan<8, false, true>}, {k_scan<8, true, false>, k_scan<8, true, true>}},
-            {{k_scan<16, false, false>, k_scan<16, false, true>}, {k_scan<16, true, false>, k_scan<16, true, true>}}};
-        return tab[ne_idx][res ? 1 : 0][extra ? 1 : 0];
-    }
-    static std::vector<ScanFn> scan_variants() {
-        std::vector<ScanFn> v;
-        for (int a = 0; a < 4; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 2; c++) v.push_back(scan_fn(a, b, c));
-        return v;
     }
 
     void destroy() {
@@ -145,7 +138,7 @@ struct pe_engine {
         for (auto p : gen) fr(p);
         for (auto p : d_tab) fr(p);
         fr(tick_buf); fr(d_out_node); fr(d_out_fail); fr(ff8); fr(pref64); fr(cand_g); fr(st_cpu_g); fr(st_mem_g); fr(st_gen_g);
-        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf);
+        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters);
         for (auto &p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         if (stream) cudaStreamDestroy(stream);
     }
@@ -264,6 +257,7 @@ struct pe_engine {
                 else if (ev_pool[i].kind == 1) stats.sequencer_ms += ms;
                 else if (ev_pool[i].kind == 2) stats.h2d_ms += ms;
                 else if (ev_pool[i].kind == 3) stats.d2h_ms += ms;
+                else if (ev_pool[i].kind == 5) stats.prep_ms += ms;
                 else stats.run_ms += ms;
             }
         }
@@ -379,6 +373,9 @@ struct pe_engine {
     int32_t validate_and_prepare(const pe_tick *tk) {
         if (!tk) { err = "null tick"; return PE_ERR_INVALID; }
         int32_t rc;
+        runs.clear();
+        use_res = use_dyn = false; scan_ok = true;
+        use_gen.assign(PE_SCAN_MAXGENK, 0); use_pw.assign(PE_SCAN_MAXW, 0);
         for (uint32_t i = 0; i < tk->n_groups; i++) {
             const pe_group &g = tk->groups[i];
             if ((uint64_t)g.task_off + g.n_tasks > tk->n_tasks) { err = "group task range out of bounds"; return PE_ERR_INVALID; }
@@ -388,7 +385,27 @@ struct pe_engine {
                 (uint64_t)g.fail_off + g.fail_cnt > tk->n_fails) { err = "group side-array range out of bounds"; return PE_ERR_INVALID; }
             if (n_nodes && g.tie_start >= n_nodes) { err = "tie_start >= node count"; return PE_ERR_INVALID; }
             if (g.gen_cnt > PE_MAX_GEN_WANTS) { err = "more than 8 generic reservations in one task"; return PE_ERR_UNSUPPORTED; }
-            if ((rc = ensure_col(svc, g.svc_id, 4))) return rc;
+            if ((g.svc_id >= svc.size() || !svc[g.svc_id]) && (rc = ensure_col(svc, g.svc_id, 4))) return rc;
+            const bool one = g.n_tasks == 1;
+            if (runs.empty() || runs.back().one != one) runs.push_back({i, i + 1, one});
+            else runs.back().end = i + 1;
+            if (one) {   // the scan path: which state-dependent columns ride in the node tiles
+                if ((g.filter_mask >> PE_F_RESOURCE) & 1u) {
+                    use_res = use_dyn = true;
+                    for (uint32_t e = 0; e < g.gen_cnt; e++) {
+                        const uint32_t kd = tk->gens[g.gen_off + e].kind;
+                        if (kd >= PE_SCAN_MAXGENK) scan_ok = false; else use_gen[kd] = 1;
+                    }
+                }
+                if ((g.filter_mask >> PE_F_HOSTPORT) & 1u) {
+                    use_dyn = true;
+                    for (uint32_t e = 0; e < g.port_cnt; e++) {
+                        const uint32_t w = tk->ports[g.port_off + e] >> 5;
+                        if (w >= PE_SCAN_MAXW) scan_ok = false; else use_pw[w] = 1;
+                    }
+                }
+                if (((g.filter_mask >> PE_F_MAXREPLICAS) & 1u) || g.fail_cnt) use_dyn = true;
+            }
             if ((g.flags & PE_G_LOG_DRIVER) && (rc = ensure_col(plug, g.log_plugin >> 5, 4))) return rc;
         }
         for (uint32_t i = 0; i < tk->n_cons; i++) if ((rc = ensure_col(attr, tk->cons[i].col, 4))) return rc;
@@ -405,11 +422,6 @@ struct pe_engine {
         int32_t rc = validate_and_prepare(tk);
         if (rc) return rc;
         n_groups = tk->n_groups; n_tasks = tk->n_tasks;
-        groups.assign(tk->groups, tk->groups + tk->n_groups);
-        h_cons.assign(tk->cons, tk->cons + tk->n_cons);
-        h_gens.assign(tk->gens, tk->gens + tk->n_gens);
-        h_ports.assign(tk->ports, tk->ports + tk->n_ports);
-        h_plugs.assign(tk->plugs, tk->plugs + tk->n_plugs);
         size_t off[10]; size_t o = 0;
         auto place = [&](int i, size_t bytes) { off[i] = o; o += (bytes + 15) / 16 * 16; };
         place(0, (size_t)tk->n_groups * sizeof(pe_group));
@@ -486,11 +498,17 @@ struct pe_engine {
 
     uint32_t e_stride() const { return round_up(cap / 32, 32); }
 
+    // device arrays of the current k == 1 run / batch (carved from cls_buf / rows_buf)
+    uint32_t *ht_full = nullptr, *ht_static = nullptr, *dcls = nullptr, *scls = nullptr, *srow = nullptr, *static_reps = nullptr,
+             *mark = nullptr, *rowof = nullptr;
+    uint32_t *row_group = nullptr, *row_srow = nullptr, *task_row = nullptr;
+
     int32_t launch_sequencer(uint32_t g0, uint32_t g1, bool with_scan) {
         SeqParams P;
         P.T = table(); P.K = K;
         P.g_begin = g0; P.g_end = g1;
         P.scan = with_scan ? scan_out : nullptr;
+        P.task_row = task_row;
         P.E = E; P.e_stride = e_stride(); P.L = Lbuf;
         P.ff8 = ff8; P.pref64 = pref64; P.cand_g = cand_g;
         P.st_cpu_g = st_cpu_g; P.st_mem_g = st_mem_g; P.st_svc_g = st_svc_g; P.st_tot_g = st_tot_g;
@@ -508,94 +526,30 @@ struct pe_engine {
         return PE_OK;
     }
 
-    // Plan one scan batch over groups [g0, g0+B): which columns ride in the
-    // tile, the tile size, the kernel variant.  Returns false if the batch
-    // needs something the scan path does not stage (sequencer handles it).
-    bool plan_scan(uint32_t g0, uint32_t B, ScanParams &P, bool &has_res, bool &has_extra, uint64_t &alg_bytes, uint32_t &max_con) {
-        std::vector<uint8_t> use_attr(attr.size(), 0), use_gen(gen.size(), 0), use_pw(ports.size(), 0), use_qw(plug.size(), 0);
-        has_res = false; has_extra = false;
-        bool use_ip = false;
-        alg_bytes = 0;
-        max_con = 0;
-        uint32_t seen_cols[PE_SCAN_MAXCON];
-        for (uint32_t i = 0; i < B; i++) {
-            const pe_group &g = groups[g0 + i];
-            if (g.con_cnt > PE_SCAN_MAXCON) return false;
-            if ((g.filter_mask >> PE_F_CONSTRAINT) & 1u) max_con = std::max(max_con, g.con_cnt);
-            uint64_t per_eval = 12;  // meta + total + per-service count
-            uint32_t nseen = 0;
-            for (uint32_t e = 0; e < g.con_cnt; e++) {
-                uint32_t c = h_cons[g.con_off + e].col;
-                if (c >= PE_SCAN_MAXATTR) return false;
-                use_attr[c] = 1;
-                bool dup = false;
-                for (uint32_t s = 0; s < nseen; s++) dup |= seen_cols[s] == c;
-                if (!dup) { seen_cols[nseen++] = c; per_eval += 4; }
-            }
-            if ((g.filter_mask >> PE_F_RESOURCE) & 1u) {
-                has_res = true;
-                per_eval += 16;
-                for (uint32_t e = 0; e < g.gen_cnt; e++) {
-                    uint32_t kd = h_gens[g.gen_off + e].kind;
-                    if (kd >= PE_SCAN_MAXGENK) return false;
-                    use_gen[kd] = 1;
-                    per_eval += 8;
-                }
-            }
-            if ((g.filter_mask >> PE_F_PLUGIN) & 1u) {
-                has_extra = true;
-                for (uint32_t e = 0; e < g.plug_cnt; e++) {
-                    uint32_t w = h_plugs[g.plug_off + e] >> 5;
-                    if (w >= PE_SCAN_MAXW) return false;
-                    use_qw[w] = 1;
-                }
-                if (g.flags & PE_G_LOG_DRIVER) {
-                    uint32_t w = g.log_plugin >> 5;
-                    if (w >= PE_SCAN_MAXW) return false;
-                    use_qw[w] = 1;
-                }
-                per_eval += 4;
-            }
-            if ((g.filter_mask >> PE_F_HOSTPORT) & 1u) {
-                has_extra = true;
-                for (uint32_t e = 0; e < g.port_cnt; e++) {
-                    uint32_t w = h_ports[g.port_off + e] >> 5;
-                    if (w >= PE_SCAN_MAXW) return false;
-                    use_pw[w] = 1;
-                }
-                per_eval += 4;
-            }
-            if (g.ip_cnt) { has_extra = true; use_ip = true; per_eval += 16; }
-            if ((g.filter_mask >> PE_F_MAXREPLICAS) & 1u) has_extra = true;
-            if (g.fail_cnt) has_extra = true;
-            alg_bytes += per_eval * n_nodes;
-        }
-        // column list
-        P.n_cols = 0;
-        uint32_t bpn = 0;
+    // Which columns ride in the scan's node tiles and the tile size, from what the
+    // k == 1 groups of the staged tick use.  Returns false if the scan cannot stage it.
+    bool plan_scan(ScanParams &P) {
+        if (!scan_ok) return false;
         struct Tmp { const void *base; uint32_t elem; uint32_t *off32; uint16_t *off16; };
         std::vector<Tmp> cols;
-        cols.push_back({meta, 4, &P.off_meta, nullptr});
+        P.off_total = P.off_cpu = P.off_mem = 0;
         cols.push_back({total, 4, &P.off_total, nullptr});
-        P.off_cpu = P.off_mem = P.off_ip = 0;
-        if (has_res) { cols.push_back({cpu, 8, &P.off_cpu, nullptr}); cols.push_back({mem, 8, &P.off_mem, nullptr}); }
-        if (use_ip) cols.push_back({ip, 16, &P.off_ip, nullptr});
-        memset(P.off_attr, 0xFF, sizeof P.off_attr); memset(P.off_gen, 0xFF, sizeof P.off_gen);
-        memset(P.off_portw, 0xFF, sizeof P.off_portw); memset(P.off_plugw, 0xFF, sizeof P.off_plugw);
-        for (uint32_t c = 0; c < use_attr.size() && c < PE_SCAN_MAXATTR; c++) if (use_attr[c]) cols.push_back({attr[c], 4, nullptr, &P.off_attr[c]});
-        for (uint32_t c = 0; c < use_gen.size() && c < PE_SCAN_MAXGENK; c++) if (use_gen[c]) cols.push_back({gen[c], 8, nullptr, &P.off_gen[c]});
-        for (uint32_t c = 0; c < use_pw.size() && c < PE_SCAN_MAXW; c++) if (use_pw[c]) cols.push_back({ports[c], 4, nullptr, &P.off_portw[c]});
-        for (uint32_t c = 0; c < use_qw.size() && c < PE_SCAN_MAXW; c++) if (use_qw[c]) cols.push_back({plug[c], 4, nullptr, &P.off_plugw[c]});
+        if (use_res) { cols.push_back({cpu, 8, &P.off_cpu, nullptr}); cols.push_back({mem, 8, &P.off_mem, nullptr}); }
+        memset(P.off_gen, 0xFF, sizeof P.off_gen); memset(P.off_portw, 0xFF, sizeof P.off_portw);
+        for (uint32_t c = 0; c < PE_SCAN_MAXGENK && c < gen.size(); c++) if (use_gen[c] && gen[c]) cols.push_back({gen[c], 8, nullptr, &P.off_gen[c]});
+        for (uint32_t c = 0; c < PE_SCAN_MAXW && c < ports.size(); c++) if (use_pw[c] && ports[c]) cols.push_back({ports[c], 4, nullptr, &P.off_portw[c]});
         if (cols.size() > PE_SCAN_MAXCOLS) return false;
+        uint32_t bpn = 0;
         for (auto &c : cols) bpn += c.elem;
         // largest tile whose two stages fit the per-CTA budget (2 CTAs / SM)
         const uint32_t budget = 100 * 1024;
         uint32_t TN = 2048;
         while (TN > 256 && 2u * TN * bpn > budget) TN >>= 1;
         if (2u * TN * bpn > budget) return false;
-        uint32_t o = 0;
-        // 8- and 16-byte columns first so every column start stays aligned to its element size
+        // 8-byte columns first so every column start stays aligned to its element size
         std::stable_sort(cols.begin(), cols.end(), [](const Tmp &a, const Tmp &b) { return a.elem > b.elem; });
+        uint32_t o = 0;
+        P.n_cols = 0;
         for (auto &c : cols) {
             ScanCol &sc = P.cols[P.n_cols++];
             sc.base = c.base; sc.elem = c.elem; sc.smem_off = o;
@@ -608,10 +562,91 @@ struct pe_engine {
         P.n_tiles = (n_nodes + TN - 1) / TN;
         P.K = K;
         P.n_nodes = n_nodes;
-        P.g_begin = g0; P.n_tasks = B;
         P.svc = reinterpret_cast<uint32_t *const *>(d_tab[2]);
         P.out = scan_out; P.E = E; P.e_stride = e_stride(); P.L = Lbuf;
+        P.S = Sbuf; P.s_stride = e_stride();
+        P.ctr = d_ctr;
         return true;
+    }
+
+    // One maximal run [g, e) of k == 1 groups through classify -> (static) -> per batch rows / scan / sequencer.
+    int32_t run_k1(uint32_t g, uint32_t e, uint32_t Bmax) {
+        int32_t rc;
+        const uint32_t n = e - g;
+        ScanParams SP;
+        if (!plan_scan(SP)) {
+            for (uint32_t b0 = g; b0 < e; b0 += Bmax) if ((rc = launch_sequencer(b0, std::min(e, b0 + Bmax), false))) return rc;
+            return PE_OK;
+        }
+        uint32_t ht = 1024;
+        while (ht < 2u * n) ht <<= 1;
+        if ((rc = ensure_buf(cls_buf, cls_cap, ((size_t)2 * ht + (size_t)6 * n) * 4 + 64))) return rc;
+        ht_full = reinterpret_cast<uint32_t *>(cls_buf); ht_static = ht_full + ht;
+        dcls = ht_static + ht; scls = dcls + n; srow = scls + n; static_reps = srow + n; mark = static_reps + n; rowof = mark + n;
+        if ((rc = ensure_buf(rows_buf, rows_cap, (size_t)3 * Bmax * 4 + 64))) return rc;
+        row_group = reinterpret_cast<uint32_t *>(rows_buf); row_srow = row_group + Bmax; task_row = row_srow + Bmax;
+
+        EvPair *evp = ev_begin(5);
+        CU(cudaMemsetAsync(ht_full, 0xFF, (size_t)2 * ht * 4, stream));
+        CU(cudaMemsetAsync(mark, 0, (size_t)n * 4, stream));
+        CU(cudaMemsetAsync(d_cls_counters, 0, 16, stream));
+        ClassifyParams CP;
+        CP.K = K; CP.g0 = g; CP.n = n; CP.ht_full = ht_full; CP.ht_static = ht_static; CP.ht_mask = ht - 1;
+        CP.dcls = dcls; CP.scls = scls; CP.srow = srow; CP.static_reps = static_reps; CP.counters = d_cls_counters;
+        k_classify<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)num_sms * 8u), 256, 0, stream>>>(CP);
+        stats.kernel_launches++;
+        uint32_t h_cnt[4] = {0, 0, 0, 0};
+        CU(cudaMemcpyAsync(h_cnt, d_cls_counters, 16, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        const uint32_t n_sig = h_cnt[0];
+        const size_t stride = e_stride();
+        // signature bitmaps for the whole run when they fit in 1 GB, else one bitmap per row of each batch
+        const bool cached = (size_t)n_sig * stride * 4 <= ((size_t)1 << 30);
+        const size_t s_rows = cached ? n_sig : Bmax;
+        if (s_rows * stride > S_words) {
+            void *p = Sbuf; size_t c = S_words * 4;
+            if ((rc = ensure_buf(p, c, s_rows * stride * 4))) return rc;
+            Sbuf = reinterpret_cast<uint32_t *>(p); S_words = c / 4;
+        }
+        SP.S = Sbuf;
+        StaticParams XP;
+        XP.T = table(); XP.K = K; XP.S = Sbuf; XP.s_stride = (uint32_t)stride; XP.lo = 0; XP.hi = n_nodes; XP.ctr = d_ctr;
+        const uint32_t chunks = (uint32_t)stride / 32u;
+        auto launch_static = [&](const uint32_t *reps, const uint32_t *cnt, uint32_t max_rows) {
+            XP.reps = reps; XP.n_reps = cnt;
+            const unsigned long long units = (unsigned long long)max_rows * chunks;
+            const uint32_t grid = (uint32_t)std::min<unsigned long long>((units + 7) / 8, (unsigned long long)num_sms * 16ull);
+            k_static<<<std::max(grid, 1u), 256, 0, stream>>>(XP);
+            stats.kernel_launches++;
+        };
+        if (cached && n_sig) launch_static(static_reps, d_cls_counters, n_sig);
+        ev_end(evp);
+
+        uint32_t stamp = 0;
+        for (uint32_t b0 = g; b0 < e; b0 += Bmax) {
+            const uint32_t B = std::min(Bmax, e - b0);
+            EvPair *evr = ev_begin(5);
+            RowsParams RP;
+            RP.dcls = dcls; RP.scls = scls; RP.srow = srow; RP.g0 = g; RP.b0 = b0; RP.B = B; RP.mark = mark; RP.rowof = rowof;
+            RP.stamp = ++stamp; RP.static_cached = cached ? 1u : 0u;
+            RP.row_group = row_group; RP.row_srow = row_srow; RP.task_row = task_row; RP.n_rows = d_cls_counters + 2;
+            k_rows<<<1, 1024, 0, stream>>>(RP);
+            stats.kernel_launches++;
+            if (!cached) launch_static(row_group, d_cls_counters + 2, B);
+            ev_end(evr);
+            SP.row_group = row_group; SP.row_srow = row_srow; SP.n_rows = d_cls_counters + 2;
+            const uint32_t grid = std::max((B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS, std::min(B, (uint32_t)num_sms * 2u));
+            const size_t dyn = 2 * (size_t)SP.stage_bytes;
+            EvPair *ev = ev_begin(0);
+            if (use_dyn) k_scan<true><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            else k_scan<false><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            ev_end(ev);
+            CU(cudaGetLastError());
+            stats.kernel_launches++; stats.scan_launches++;
+            stats.pairs += (uint64_t)B * n_nodes;
+            if ((rc = launch_sequencer(b0, b0 + B, true))) return rc;
+        }
+        return PE_OK;
     }
 
     int32_t tick_run() {
@@ -622,7 +657,7 @@ struct pe_engine {
         const uint32_t Bmax = max_batch ? max_batch : wave;
         const bool spec = !(cfg_flags & PE_CFG_NO_SPECULATION) && n_nodes > 0;
         if (spec) {
-            size_t need = (size_t)Bmax * 2u * e_stride();   // two class rows per task
+            size_t need = (size_t)Bmax * 2u * e_stride();   // two class rows per scan row
             if (need > E_words) {
                 void *p = E; size_t c = E_words * 4;
                 if ((rc = ensure_buf(p, c, need * 4))) return rc;
@@ -642,39 +677,13 @@ struct pe_engine {
         // failure counters default to zero; only groups with unplaced tasks write theirs
         if (n_groups) CU(cudaMemsetAsync(d_out_fail, 0, (size_t)n_groups * PE_NUM_FILTERS * 4, stream));
         EvPair *ev_run = ev_begin(4);
-        uint32_t g = 0;
-        while (g < n_groups) {
+        for (const Run &r : runs) {
             // maximal run of k == 1 groups -> batched scan path; anything else -> sequencer alone
-            uint32_t e = g;
-            const bool one = groups[g].n_tasks == 1;
-            while (e < n_groups && (groups[e].n_tasks == 1) == one) e++;
-            if (one && spec && e - g >= 4) {
-                for (uint32_t b0 = g; b0 < e; b0 += Bmax) {
-                    const uint32_t B = std::min(Bmax, e - b0);
-                    ScanParams SP;
-                    bool has_res, has_extra;
-                    uint64_t alg = 0;
-                    uint32_t max_con = 0;
-                    if (plan_scan(b0, B, SP, has_res, has_extra, alg, max_con)) {
-                        const uint32_t grid = (B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS;
-                        const size_t dyn = 2 * (size_t)SP.stage_bytes;
-                        EvPair *ev = ev_begin(0);
-                        const int ne_idx = max_con == 0 ? 0 : max_con <= 4 ? 1 : max_con <= 8 ? 2 : 3;
-                        scan_fn(ne_idx, has_res, has_extra)<<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
-                        ev_end(ev);
-                        CU(cudaGetLastError());
-                        stats.kernel_launches++; stats.scan_launches++;
-                        stats.evals += (uint64_t)B * n_nodes;
-                        stats.scan_bytes += alg;
-                        if ((rc = launch_sequencer(b0, b0 + B, true))) return rc;
-                    } else {
-                        if ((rc = launch_sequencer(b0, b0 + B, false))) return rc;
-                    }
-                }
+            if (r.one && spec && r.end - r.begin >= 4) {
+                if ((rc = run_k1(r.begin, r.end, Bmax))) return rc;
             } else {
-                if ((rc = launch_sequencer(g, e, false))) return rc;
+                if ((rc = launch_sequencer(r.begin, r.end, false))) return rc;
             }
-            g = e;
         }
         ev_end(ev_run);
         CU(cudaStreamSynchronize(stream));
@@ -688,6 +697,7 @@ struct pe_engine {
         stats.fast_path += c.fast_path; stats.medium_path += c.medium_path; stats.slow_path += c.slow_path;
         stats.placements += c.placements; stats.evals_generic += c.evals_generic;
         stats.seq_cycles_fast += c.cyc_fast; stats.seq_cycles_medium += c.cyc_medium; stats.seq_cycles_generic += c.cyc_generic;
+        stats.evals += c.scan_evals; stats.scan_bytes += c.scan_bytes; stats.static_evals += c.static_evals; stats.scan_rows += c.scan_rows;
         ev_collect();
         if (c.error & (PE_DEV_ERR_WD_CONSUMER | PE_DEV_ERR_WD_DRAIN | PE_DEV_ERR_WD_SCAN)) {
             char b[160]; snprintf(b, sizeof b, "device watchdog fired (code 0x%x): a kernel pipeline stalled for more than a second", c.error);

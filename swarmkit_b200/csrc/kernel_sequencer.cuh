@@ -98,10 +98,11 @@ struct SeqParams {
     DevTable T;
     TickDev K;
     uint32_t g_begin, g_end;
-    const ScanResult *scan;  // [g_end - g_begin] or nullptr
-    const uint32_t *E;       // class bitmaps, two rows of e_stride words per task
+    const ScanResult *scan;  // [row] or nullptr
+    const uint32_t *task_row; // [g_end - g_begin] task -> scan row (tasks with identical descriptors share one)
+    const uint32_t *E;       // class bitmaps, two rows of e_stride words per scan row (best class, second class)
     uint32_t e_stride;
-    const uint32_t *L;       // class member lists, [task][2][PE_LIST_CAP]
+    const uint32_t *L;       // class member lists, [row][2][PE_LIST_CAP]
     uint8_t *ff8;                 // [cap] first failing filter (0 pass, 0xFF not in set)
     unsigned long long *pref64;   // [cap]
     CandKey *cand_g;              // [st_cap]
@@ -130,7 +131,7 @@ struct FastTask {      // staged descriptor of one k=1 task
     unsigned long long c0;
     long long cpu_res, mem_res;
     uint32_t *svccol;
-    uint32_t w0, tie_start, task_off, simple, counts, ws, row0;
+    uint32_t tie_start, task_off, simple, counts, ws, row;
     uint32_t n_list, n_class;   // list mode (tie_start == 0): listed / total members of the best class; n_list == 0: bitmap mode
 };
 
@@ -320,7 +321,7 @@ __device__ __forceinline__ void fast_consumer(const SeqParams &P, SeqShared &S, 
             if (n == PE_NONE && f.n_class > n_list) {
                 // the class goes on past the listed members: continue on its bitmap (L2), 32 words a round
                 const uint32_t last = ring[slot * PE_SEQ_WIN + n_list - 1u];
-                const uint32_t *Erow = P.E + ((size_t)(start + i - P.g_begin) * 2u + f.row0) * P.e_stride;
+                const uint32_t *Erow = P.E + (size_t)f.row * 2u * P.e_stride;
                 for (uint32_t wb = last >> 5; wb < nwords && n == PE_NONE; wb += 32u) {
                     const uint32_t w = wb + lane;
                     uint32_t v = 0;
@@ -340,7 +341,7 @@ __device__ __forceinline__ void fast_consumer(const SeqParams &P, SeqShared &S, 
             if (n == PE_NONE) { reason = 4; break; }           // the whole class is consumed
         } else {
             // ---- bitmap mode (rotated tie order): the staged window of the class bitmap
-            const uint32_t lo_bit = max(f.tie_start, f.w0 * 32u);
+            const uint32_t lo_bit = f.tie_start;
             const uint32_t lo_word = lo_bit >> 5;
             const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - f.ws);    // f.ws: window start, multiple of 4 words
             const uint32_t *buf = ring + slot * PE_SEQ_WIN;
@@ -400,7 +401,9 @@ __device__ __forceinline__ void fast_producer(const SeqParams &P, SeqShared &S, 
         const uint32_t gq = start + i;
         uint32_t go = 1;
         if (lane == 0) {
-            const ScanResult sr = scan[gq - g_begin];          // issued before the wait: overlaps it
+            const uint32_t row = P.task_row[gq - g_begin];
+            const ScanResult sr = scan[row];                   // issued before the wait: overlaps it
+            const uint32_t task_off = P.K.groups[gq].task_off;
             while (!sq_mbar_try_wait(&S.empty_bar[slot], (round & 1u) ^ 1u)) {
                 if (*vstop) { go = 0; break; }
                 __nanosleep(32);
@@ -409,14 +412,14 @@ __device__ __forceinline__ void fast_producer(const SeqParams &P, SeqShared &S, 
             if (go) {
                 FastTask f;
                 f.c0 = (sr.flags & PE_SR_K1) ? sr.c0 : PE_PREF_NONE;
-                f.w0 = sr.w0; f.row0 = sr.row0;
+                f.row = row;
                 f.tie_start = sr.tie_start;
-                f.task_off = sr.task_off;
+                f.task_off = task_off;
                 f.cpu_res = sr.cpu_res; f.mem_res = sr.mem_res;
                 f.simple = (sr.flags & PE_SR_SIMPLE) ? 1u : 0u;
                 f.counts = (sr.flags & PE_SR_COUNTS) ? 1u : 0u;
                 f.svccol = sr.svccol;
-                f.ws = (max(sr.tie_start, sr.w0 * 32u) >> 5) & ~3u;     // 16-byte aligned window start
+                f.ws = (sr.tie_start >> 5) & ~3u;                       // 16-byte aligned window start
                 f.n_class = sr.n0;
                 f.n_list = (sr.tie_start == 0u && f.c0 != PE_PREF_NONE) ? min(sr.n0, (uint32_t)PE_LIST_CAP) : 0u;
                 S.ft[slot] = f;
@@ -424,11 +427,11 @@ __device__ __forceinline__ void fast_producer(const SeqParams &P, SeqShared &S, 
                 if (f.n_list) {
                     const uint32_t bytes = ((f.n_list + 3u) & ~3u) * 4u;
                     sq_mbar_expect_tx(&S.full_bar[slot], bytes);
-                    sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, L + ((size_t)(gq - g_begin) * 2u + f.row0) * PE_LIST_CAP, bytes, &S.full_bar[slot]);
+                    sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, L + (size_t)row * 2u * PE_LIST_CAP, bytes, &S.full_bar[slot]);
                 } else if (f.c0 != PE_PREF_NONE && f.ws < nwords) {
                     // rows are padded to e_stride (a multiple of 32 words), so the copy may run past nwords
                     const uint32_t nw = min((uint32_t)PE_SEQ_WIN, e_stride - f.ws);
-                    const uint32_t *src = E + ((size_t)(gq - g_begin) * 2u + f.row0) * e_stride + f.ws;
+                    const uint32_t *src = E + (size_t)row * 2u * e_stride + f.ws;
                     sq_mbar_expect_tx(&S.full_bar[slot], nw * 4u);
                     sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, src, nw * 4u, &S.full_bar[slot]);
                 } else {
@@ -512,9 +515,9 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             __syncthreads();
             // apply the deferred reservations of the tasks fast mode placed: [start, start + consumed)
             for (uint32_t q = start + tid; q < start + S.consumed; q += nth) {
-                const ScanResult sr = P.scan[q - P.g_begin];
+                const ScanResult sr = P.scan[P.task_row[q - P.g_begin]];
                 if (!(sr.flags & PE_SR_SIMPLE)) continue;              // already applied in place
-                const uint32_t n = K.out_node[sr.task_off];
+                const uint32_t n = K.out_node[K.groups[q].task_off];
                 if (sr.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-sr.cpu_res));
                 if (sr.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-sr.mem_res));
                 if (sr.flags & PE_SR_COUNTS) { atomicAdd(&T.total[n], 1u); atomicAdd(&sr.svccol[n], 1u); }
@@ -554,12 +557,13 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             // than the second class when the batch began and ranks can only have grown,
             // so the arg-min is either the first untouched member of the second class or
             // a touched member of the best class re-evaluated against the live state.
-            const ScanResult sr = P.scan[this_gi - P.g_begin];
+            const uint32_t srow = P.task_row[this_gi - P.g_begin];
+            const ScanResult sr = P.scan[srow];
             const bool exhausted = S.stop_reason == 4u && S.resume == this_gi;   // the pipeline walked the complete member list
             if (sr.c0 != PE_PREF_NONE && !exhausted) {
                 // (i) the best class may continue beyond the window / list the pipeline staged
-                const uint32_t *E1w = P.E + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * P.e_stride;
-                const uint32_t n1 = find_first(E1w, sr.w0, N, G.tie_start, touched, S, slot);
+                const uint32_t *E1w = P.E + (size_t)srow * 2u * P.e_stride;
+                const uint32_t n1 = find_first(E1w, 0u, N, G.tie_start, touched, S, slot);
                 if (n1 != PE_NONE) {
                     if (tid == 0) {
                         const bool counts = (K.task_flags[G.task_off] & PE_T_COUNTS) != 0;
@@ -577,21 +581,21 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             }
             // (ii) best class consumed: second class + touched members of the best class
             if (sr.c0 != PE_PREF_NONE && sr.c1 != PE_PREF_NONE) {
-                const uint32_t *E1 = P.E + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * P.e_stride;
-                const uint32_t *E2 = P.E + ((size_t)(this_gi - P.g_begin) * 2u + (sr.row0 ^ 1u)) * P.e_stride;
+                const uint32_t *E1 = P.E + (size_t)srow * 2u * P.e_stride;
+                const uint32_t *E2 = E1 + P.e_stride;
                 uint32_t n2 = PE_NONE;
                 const bool use_lists = G.tie_start == 0u;
-                const uint32_t *L1 = P.L + ((size_t)(this_gi - P.g_begin) * 2u + sr.row0) * PE_LIST_CAP;
-                const uint32_t *L2 = P.L + ((size_t)(this_gi - P.g_begin) * 2u + (sr.row0 ^ 1u)) * PE_LIST_CAP;
+                const uint32_t *L1 = P.L + (size_t)srow * 2u * PE_LIST_CAP;
+                const uint32_t *L2 = L1 + PE_LIST_CAP;
                 if (use_lists && sr.n1 > 0u) {
                     const uint32_t nl = min(sr.n1, (uint32_t)PE_LIST_CAP);
                     uint32_t c = PE_NONE;
                     for (uint32_t t = tid; t < nl && c == PE_NONE; t += nth) { const uint32_t p2 = L2[t]; if (!((touched[p2 >> 5] >> (p2 & 31u)) & 1u)) c = t; }
                     const uint32_t at = block_min_pos(c, S, slot);
                     if (at != PE_NONE) n2 = L2[at];
-                    else if (sr.n1 > nl) n2 = find_first(E2, sr.w1, N, G.tie_start, touched, S, slot);
+                    else if (sr.n1 > nl) n2 = find_first(E2, 0u, N, G.tie_start, touched, S, slot);
                 } else {
-                    n2 = find_first(E2, sr.w1, N, G.tie_start, touched, S, slot);
+                    n2 = find_first(E2, 0u, N, G.tie_start, touched, S, slot);
                 }
                 if (n2 != PE_NONE) {
                     unsigned long long bp = sr.c1;
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                         }
                     } else {
                         const uint32_t nw = (N + 31u) >> 5;
-                        for (uint32_t w = sr.w0 + tid; w < nw; w += nth) {
+                        for (uint32_t w = tid; w < nw; w += nth) {
                             uint32_t v = E1[w] & touched[w];
                             if (w == nw - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
                             while (v) {
