@@ -275,7 +275,9 @@ def main():
             "split_ms_per_step": {"scan": st["scan_ms"] / args.steps, "sequencer": st["sequencer_ms"] / args.steps,
                                   "classify_static_rows": st["prep_ms"] / args.steps},
             "paths": {"fast": st["fast_path"], "medium": st["medium_path"], "slow": st["slow_path"]},
-            "sequencer_cycles": {"fast": st["seq_cycles_fast"], "medium": st["seq_cycles_medium"], "generic": st["seq_cycles_generic"]},
+            "sequencer_cycles": {"fast": st["seq_cycles_fast"], "medium": st["seq_cycles_medium"], "generic": st["seq_cycles_generic"],
+                                 "fast_exits": st["seq_stops"], "ordered_warp_wait": st["seq_cons_wait"],
+                                 "ordered_warp_work": st["seq_cons_work"], "candidate_taken": st["seq_rewalks"], "prof": st["seq_prof"]},
             "e2e": {"value": e2e_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(st["kernel_launches"]),

@@ -211,6 +211,12 @@ typedef struct pe_stats {
     uint64_t scan_rows;        /* distinct descriptors scanned (rows), summed over batches                       */
     uint64_t static_evals;     /* (signature,node) evaluations of the attribute filters (k_static)               */
     double prep_ms;            /* CUDA-event time in classify / static / rows kernels                            */
+    /* sequencer fast-mode diagnostics: exits by reason (end, none, window, neutral, class consumed); the rest is
+     * filled only by builds with -DPE_SEQ_PROFILE=1: cycles the ordered warp waited for / worked on staged tasks,
+     * tasks whose staged candidate had been taken                                                                */
+    uint64_t seq_stops[5];
+    uint64_t seq_cons_wait, seq_cons_work, seq_rewalks;
+    uint64_t seq_prof[16];      /* see SeqDebug in kernel_sequencer.cuh */
 } pe_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */

@@ -51,6 +51,8 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
     if not force and _newer(LIB_ENGINE, deps):
         return LIB_ENGINE
     cmd = [nvcc_path(), *NVCC_FLAGS, os.path.join(CSRC, "engine.cu"), "-o", LIB_ENGINE]
+    if os.environ.get("PE_SEQ_PROFILE") == "1":   # diagnostic build: the sequencer's ordered warp tallies wait / work cycles
+        cmd.insert(1, "-DPE_SEQ_PROFILE=1")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -90,10 +90,12 @@ class pe_stats(C.Structure):
                 ("sequencer_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("run_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("seq_cycles_fast", C.c_uint64),
                 ("seq_cycles_medium", C.c_uint64), ("seq_cycles_generic", C.c_uint64),
-                ("pairs", C.c_uint64), ("scan_rows", C.c_uint64), ("static_evals", C.c_uint64), ("prep_ms", C.c_double)]
+                ("pairs", C.c_uint64), ("scan_rows", C.c_uint64), ("static_evals", C.c_uint64), ("prep_ms", C.c_double),
+                ("seq_stops", C.c_uint64 * 5), ("seq_cons_wait", C.c_uint64), ("seq_cons_work", C.c_uint64),
+                ("seq_rewalks", C.c_uint64), ("seq_prof", C.c_uint64 * 16)]
 
     def as_dict(self) -> dict:
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if hasattr(getattr(self, n), "__len__") else getattr(self, n)) for n, _ in self._fields_}
 
 
 class EngineError(RuntimeError):

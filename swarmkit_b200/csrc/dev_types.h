@@ -66,12 +66,14 @@ struct ScanResult {
 #define PE_SR_SIMPLE 1u     // no generic resources / host ports: the reservation is four reductions
 #define PE_SR_COUNTS 2u     // DesiredState <= COMPLETED: bumps the spread counters
 #define PE_SR_K1 4u         // the group really has exactly one task
+#define PE_SR_STATIC_ONLY 8u // no resource / host-port / max-replicas filter and no recent-failure counts: feasibility cannot change inside a tick
 
 struct DevCounters {
     unsigned long long fast_path, medium_path, slow_path, placements, evals_generic;
     unsigned long long cyc_fast, cyc_medium, cyc_generic;   // SM cycles the sequencer spent in each mode
     unsigned long long cyc_cons_wait, cyc_cons_work, stops[5], iters;   // consumer warp: waiting on producers / working; fast-mode exits by reason
     unsigned long long scan_evals, scan_bytes;     // (row,node) evaluations the scan kernel executed / their algorithmic bytes
+    unsigned long long prof[16];                    // sequencer diagnostics (PE_SEQ_PROFILE builds)
     unsigned long long static_evals, scan_rows;    // (signature,node) evaluations of k_static; rows scanned
     uint32_t error;
     uint32_t pad;

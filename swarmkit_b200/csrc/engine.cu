@@ -697,6 +697,9 @@ struct pe_engine {
         stats.fast_path += c.fast_path; stats.medium_path += c.medium_path; stats.slow_path += c.slow_path;
         stats.placements += c.placements; stats.evals_generic += c.evals_generic;
         stats.seq_cycles_fast += c.cyc_fast; stats.seq_cycles_medium += c.cyc_medium; stats.seq_cycles_generic += c.cyc_generic;
+        for (int r = 0; r < 5; r++) stats.seq_stops[r] += c.stops[r];
+        for (int r = 0; r < 16; r++) stats.seq_prof[r] += c.prof[r];
+        stats.seq_cons_wait += c.cyc_cons_wait; stats.seq_cons_work += c.cyc_cons_work; stats.seq_rewalks += c.iters;
         stats.evals += c.scan_evals; stats.scan_bytes += c.scan_bytes; stats.static_evals += c.static_evals; stats.scan_rows += c.scan_rows;
         ev_collect();
         if (c.error & (PE_DEV_ERR_WD_CONSUMER | PE_DEV_ERR_WD_DRAIN | PE_DEV_ERR_WD_SCAN)) {

@@ -37,11 +37,15 @@ __device__ __forceinline__ bool key_less(const CandKey &a, const CandKey &b) {
     return a.pref < b.pref || (a.pref == b.pref && a.tie < b.tie);
 }
 
+#ifndef PE_SEQ_PROFILE
+#define PE_SEQ_PROFILE 0        // 1: the consumer warp also tallies wait / work cycles (diagnostic builds)
+#endif
 #define PE_SEQ_THREADS 512     // 128 registers per thread: the ordered fast path must not spill
 #define PE_SEQ_KS 2048          // candidates staged in shared memory
-#define PE_SEQ_RING 16          // fast-mode ring slots
-#define PE_SEQ_NPW 8            // producer warps (warps 1..NPW)
-#define PE_SEQ_WIN 1024         // bitmap words staged per task (32k nodes)
+#define PE_SEQ_RING 32          // fast-mode ring slots
+#define PE_SEQ_NPW 11           // producer warps: 1-3, 5-7, 9-11, 13-14.  Warp 15 commits; warps 4, 8, 12 sit fast mode out so
+                                // that the ordered warp (warp 0) has its SM sub-partition's issue slots to itself
+#define PE_SEQ_WIN 512          // words staged per task: list entries, or bitmap words (16k nodes)
 #define PE_MAX_GEN_WANTS 8
 #define PE_CTX_MAXC 16
 #define PE_ST_FAILED 1u
@@ -82,13 +86,23 @@ __device__ __forceinline__ void sq_tma_bulk_g2s(void *dst, const void *src, uint
                  "l"(src), "r"(bytes), "r"(seq_smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void st_release_smem(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(seq_smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_smem(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(seq_smem_u32(p)) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sq_mbar_wait(unsigned long long *bar, uint32_t parity) {
     while (!sq_mbar_try_wait(bar, parity)) {}
 }
 // Same, but gives up after ~1 s and raises a device error instead of hanging the GPU.
 __device__ __forceinline__ bool sq_mbar_wait_wd(unsigned long long *bar, uint32_t parity, DevCounters *ctr, uint32_t code) {
+    if (sq_mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!sq_mbar_try_wait(bar, parity)) {
+        __nanosleep(20);     // a spinning warp would take issue slots from the warps that do the work
         if (clock64() - t0 > 2000000000LL) { atomicOr(&ctr->error, code); return false; }
     }
     return true;
@@ -127,21 +141,43 @@ struct GroupCtx {
     uint32_t usable;   // 1: every constraint is staged here (con_cnt <= PE_CTX_MAXC)
 };
 
-struct FastTask {      // staged descriptor of one k=1 task
-    unsigned long long c0;
-    long long cpu_res, mem_res;
-    uint32_t *svccol;
-    uint32_t tie_start, task_off, simple, counts, ws, row;
-    uint32_t n_list, n_class;   // list mode (tie_start == 0): listed / total members of the best class; n_list == 0: bitmap mode
+// Staged descriptor of one k=1 task: two 16-byte records the consumer reads with two loads.
+struct FastTask {
+    // a
+    uint32_t n_cand;     // candidates the producer left in S.cands[slot] (list mode)
+    uint32_t last;       // last staged member (where the class bitmap takes over)
+    uint32_t n_list;     // staged members (list mode); 0 in bitmap mode
+    uint32_t task_off;
+    // b
+    uint32_t n_class;    // members of the best class
+    uint32_t row;        // scan row
+    uint32_t flags;      // PE_FT_*
+    uint32_t tie_start;
 };
+#define PE_FT_VALID 1u    // the scan found a feasible node and the group has exactly one task
+#define PE_FT_SIMPLE 2u   // reservation = counters (+ cpu / mem): deferred, applied when fast mode ends
+#define PE_FT_COUNTS 4u   // DesiredState <= COMPLETED
+#define PE_FT_PLAIN (PE_FT_VALID | PE_FT_SIMPLE | PE_FT_COUNTS)
+#define PE_FT_INLINE 8u   // no state-dependent filter: a consumed best class is resolved by the ordered warp itself
+#define PE_SEQ_NCAND 32   // candidates per task: must be >= PE_SEQ_RING (see fast_consumer)
+#define PE_SEQ_GROUP 8    // tasks the ordered warp resolves per iteration
+#define PE_SEQ_LOGN 512   // placements the ordered warp may run ahead of the committer warp
+#define PE_SEQ_ROWCUR 6656 // scan rows that get list cursors (the ring and the cursors alias the k > 1 staging area)
+#define PE_SEQ_STAGING_BYTES (PE_SEQ_KS * 45)   // CandKey 16 + cpu 8 + mem 8 + svc 4 + tot 4 + placed 4 + flags 1 per staged candidate
+#define PE_SEQ_FAST_BYTES (PE_SEQ_RING * PE_SEQ_WIN * 4 + PE_SEQ_ROWCUR * 8)
+#define PE_SEQ_REGION0 (((PE_SEQ_STAGING_BYTES > PE_SEQ_FAST_BYTES ? PE_SEQ_STAGING_BYTES : PE_SEQ_FAST_BYTES) + 15) & ~15)
 
 struct SeqShared {
     pe_group G;
     GroupCtx C;
-    FastTask ft[PE_SEQ_RING];
-    unsigned long long full_bar[PE_SEQ_RING], empty_bar[PE_SEQ_RING];
+    __align__(16) FastTask ft[PE_SEQ_RING];
+    uint32_t cands[PE_SEQ_RING][PE_SEQ_NCAND];
+    uint32_t quick[PE_SEQ_RING];  // candidates of a task the ordered warp may resolve in a group (plain reservation, list mode), else PE_NONE
+    uint32_t log[PE_SEQ_LOGN];   // node chosen for fast task q of the session, at q % PE_SEQ_LOGN
+    uint32_t pub, applied;       // tasks placed by the ordered warp / reservations applied by the committer warp
+    uint32_t tma_ph[PE_SEQ_RING];   // phase of each slot's copy barrier (one producer owns a slot at a time)
+    unsigned long long full_bar[PE_SEQ_RING], tma_bar[PE_SEQ_RING];
     uint32_t stop, resume, stop_reason, bars_live, consumed;
-    uint32_t armed[PE_SEQ_RING];
     uint32_t red32[40];
     unsigned long long red64[40];
     uint32_t bins[256];
@@ -269,178 +305,564 @@ __device__ __forceinline__ uint32_t eval_ctx(const DevTable &T, const TickDev &K
 }
 
 
-// ---- fast mode, consumer warp: tasks strictly in order, shared memory only on the common path.
-// One warp executes a dependent chain (~7 cycles per instruction), so this loop is kept as short
-// as possible: no per-task global loads, no block barriers, reservations as fire-and-forget reductions.
-struct SeqDebug { unsigned long long n_fast, n_placed, iters, stops[5]; long long cyc_wait, cyc_work; };
+struct SeqDebug { unsigned long long n_fast, n_placed, n_medium, iters, stops[5]; long long cyc_wait, cyc_work; unsigned long long prof[16]; };
+// prof (PE_SEQ_PROFILE builds): 0 single-task calls, 1 their cycles, 2 bitmap continuations, 3 their cycles,
+// 4 inline-medium calls, 5 their cycles, 6 cycles waiting for the committer inside them, 7 best-class members re-ranked
 
-__device__ __forceinline__ void fast_commit(const SeqParams &P, const FastTask &f, uint32_t gq, uint32_t n, uint32_t *touched) {
-    const DevTable &T = P.T;
-    P.K.out_node[f.task_off] = n;
-    if (f.simple) {   // NodeInfo.addTask, nodeinfo.go:125-153, as fire-and-forget reductions
-        if (f.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-f.cpu_res));
-        if (f.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-f.mem_res));
-        if (f.counts) { atomicAdd(&T.total[n], 1u); atomicAdd(&f.svccol[n], 1u); }
-    } else {
-        add_task_global(T, P.K, P.K.groups[gq], n, f.counts != 0, P.ctr);
-    }
+// ---- fast mode -------------------------------------------------------------------------------
+// Warp 0 consumes tasks strictly in order; warps 1..PE_SEQ_NPW stay ahead of it.  Producer warp p
+// stages the tasks i == p-1 (mod NPW): the scan row's member list comes into the task's ring slot
+// by TMA bulk copy, the producer walks it against the `touched` bitmap and leaves the first
+// PE_SEQ_NCAND untouched members as the task's candidates.  Touched bits never clear, and a slot is
+// refilled only after its previous task was consumed, so at most PE_SEQ_RING - 1 placements happen
+// between the producer's look and the consumer's turn: of PE_SEQ_NCAND >= PE_SEQ_RING candidates
+// one always survives, and it is exactly the first untouched member.  The ordered warp's dependent
+// chain per task is: one candidate per lane, its touched bit, a ballot.  Four consecutive tasks are
+// resolved per iteration: their loads are issued together and the choices of the earlier ones are
+// applied to the later ones in registers.
+
+__device__ __forceinline__ void fast_commit(const SeqParams &P, uint32_t gq, uint32_t task_off, bool counts, uint32_t n, uint32_t *touched) {
+    P.K.out_node[task_off] = n;
+    add_task_global(P.T, P.K, P.K.groups[gq], n, counts, P.ctr);   // generic resources / host ports: in place
     touched[n >> 5] |= 1u << (n & 31u);
 }
 
-__device__ __forceinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uint32_t *touched, const uint32_t *ring, uint32_t start,
-                                              SeqDebug &dbg) {
-    const uint32_t lane = threadIdx.x & 31u;
+// One task, every case.  Returns 0 to go on, else the stop reason (+ 16 if the task itself was placed).
+// All reservations of the session's tasks [0, upto) are in the global columns (the caller published `pub` >= upto).
+__device__ __forceinline__ bool wait_applied(const SeqParams &P, SeqShared &S, uint32_t upto) {
+    const long long t0 = clock64();
+    while (ld_acquire_smem(&S.applied) < upto) {
+        __nanosleep(20);
+        if (clock64() - t0 > 2000000000LL) { atomicOr(&P.ctr->error, PE_DEV_ERR_WD_CONSUMER); return false; }
+    }
+    return true;
+}
+
+// The best class of a task is consumed (every member was taken earlier in the batch) and the task has
+// no state-dependent filter.  Every node outside the two recorded classes ranked strictly worse than
+// the second class when the batch began and ranks only grow, so the arg-min is the first untouched
+// member of the second class or a member of the best class at its LIVE rank.  PE_NONE: not resolvable
+// here (no second class / no untouched member of it / best class not fully listed).
+__device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared &S, const uint32_t *touched, uint32_t *rowcur2, uint32_t row,
+                                                  uint32_t i, uint32_t lane, SeqDebug &dbg) {
     const uint32_t N = P.T.n_nodes, nwords = (N + 31u) >> 5;
-    uint32_t i = 0, reason = 0;
-    for (; start + i < P.g_end; i++) {
-        const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
-        if (!sq_mbar_wait_wd(&S.full_bar[slot], round & 1u, P.ctr, PE_DEV_ERR_WD_CONSUMER)) { reason = 1; break; }
-        const FastTask &f = S.ft[slot];
-        if (f.c0 == PE_PREF_NONE) { reason = 1; break; }      // nothing feasible when the batch began, or k != 1
-        uint32_t n = PE_NONE;
-        const uint32_t n_list = f.n_list;
-        if (n_list) {
-            // ---- list mode (canonical tie order): the first members of the class in node order
-            const uint4 *lst4 = reinterpret_cast<const uint4 *>(ring + slot * PE_SEQ_WIN);
-            for (uint32_t j = 0; j < n_list && n == PE_NONE; j += 128u) {
-                const uint32_t il = j + lane * 4u;
-                uint32_t first = PE_NONE;
-                if (il < n_list) {
-                    const uint4 e = lst4[il >> 2];
-                    const uint32_t left = n_list - il;
-                    const uint32_t tx = touched[e.x >> 5], ty = left > 1u ? touched[e.y >> 5] : ~0u;
-                    const uint32_t tz = left > 2u ? touched[e.z >> 5] : ~0u, tw = left > 3u ? touched[e.w >> 5] : ~0u;
-                    if (!((tw >> (e.w & 31u)) & 1u)) first = e.w;
-                    if (!((tz >> (e.z & 31u)) & 1u)) first = e.z;
-                    if (!((ty >> (e.y & 31u)) & 1u)) first = e.y;
-                    if (!((tx >> (e.x & 31u)) & 1u)) first = e.x;
-                }
-                const uint32_t b = __ballot_sync(0xFFFFFFFFu, first != PE_NONE);
-                if (b) n = __shfl_sync(0xFFFFFFFFu, first, __ffs((int)b) - 1);
+    const ScanResult *sr = &P.scan[row];
+    const uint32_t *L1 = P.L + (size_t)row * 2u * PE_LIST_CAP, *L2 = L1 + PE_LIST_CAP;
+    // one round of independent global loads: the row record, the head of the best class's list and 128
+    // members of the second class starting at the row's cursor (members before it are touched for good)
+    const uint32_t cur2 = row < (uint32_t)PE_SEQ_ROWCUR ? (rowcur2[row] & ~31u) : 0u;
+    uint32_t v2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const uint32_t idx = cur2 + (uint32_t)k * 32u + lane; v2[k] = idx < (uint32_t)PE_LIST_CAP ? L2[idx] : 0u; }
+    const unsigned long long c1 = sr->c1;
+    const uint4 meta = *reinterpret_cast<const uint4 *>(&sr->n0);   // n0, n1, tie_start, flags
+    const uint32_t *svccol = sr->svccol;
+    const uint32_t head1 = L1[lane];                                 // (rows are PE_LIST_CAP long: in bounds)
+    const uint32_t n0 = meta.x, n1 = meta.y;
+    if (c1 == PE_PREF_NONE || n0 > (uint32_t)PE_LIST_CAP) return PE_NONE;
+    const uint32_t nl = min(n1, (uint32_t)PE_LIST_CAP);
+    uint32_t n2 = PE_NONE;
+    for (uint32_t j = cur2; j < nl && n2 == PE_NONE; j += 128u) {
+        if (j != cur2) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint32_t idx = j + (uint32_t)k * 32u + lane; v2[k] = idx < nl ? L2[idx] : 0u; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t idx = j + (uint32_t)k * 32u + lane;
+            const bool u = idx < nl && !((touched[v2[k] >> 5] >> (v2[k] & 31u)) & 1u);
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, u);
+            if (b && n2 == PE_NONE) {
+                const int src = __ffs((int)b) - 1;
+                n2 = __shfl_sync(0xFFFFFFFFu, v2[k], src);
+                if (lane == 0 && row < (uint32_t)PE_SEQ_ROWCUR) rowcur2[row] = j + (uint32_t)k * 32u + (uint32_t)src;
             }
-            if (n == PE_NONE && f.n_class > n_list) {
-                // the class goes on past the listed members: continue on its bitmap (L2), 32 words a round
-                const uint32_t last = ring[slot * PE_SEQ_WIN + n_list - 1u];
-                const uint32_t *Erow = P.E + (size_t)f.row * 2u * P.e_stride;
-                for (uint32_t wb = last >> 5; wb < nwords && n == PE_NONE; wb += 32u) {
-                    const uint32_t w = wb + lane;
-                    uint32_t v = 0;
-                    if (w < nwords) {
-                        v = Erow[w] & ~touched[w];
-                        if (w == (last >> 5)) v &= (last & 31u) == 31u ? 0u : (0xFFFFFFFFu << ((last & 31u) + 1u));
-                        if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
-                    }
-                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0u);
-                    if (b) {
-                        const int src = __ffs((int)b) - 1;
-                        const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
-                        n = (wb + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
-                    }
-                }
+        }
+    }
+    if (n2 == PE_NONE && n1 > nl) {
+        const uint32_t last = L2[nl - 1u];
+        const uint32_t *Erow = P.E + ((size_t)row * 2u + 1u) * P.e_stride;
+        for (uint32_t wb = last >> 5; wb < nwords && n2 == PE_NONE; wb += 32u) {
+            const uint32_t w = wb + lane;
+            uint32_t v = 0;
+            if (w < nwords) {
+                v = Erow[w] & ~touched[w];
+                if (w == (last >> 5)) v &= (last & 31u) == 31u ? 0u : (0xFFFFFFFFu << ((last & 31u) + 1u));
+                if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
             }
-            if (n == PE_NONE) { reason = 4; break; }           // the whole class is consumed
-        } else {
-            // ---- bitmap mode (rotated tie order): the staged window of the class bitmap
-            const uint32_t lo_bit = f.tie_start;
-            const uint32_t lo_word = lo_bit >> 5;
-            const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - f.ws);    // f.ws: window start, multiple of 4 words
-            const uint32_t *buf = ring + slot * PE_SEQ_WIN;
-            for (uint32_t j = 0; j < nwin && n == PE_NONE; j += 32u) {
-                const uint32_t w = f.ws + j + lane;
+            const uint32_t bb = __ballot_sync(0xFFFFFFFFu, v != 0u);
+            if (bb) {
+                const int src = __ffs((int)bb) - 1;
+                const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
+                n2 = (wb + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
+            }
+        }
+    }
+    if (n2 == PE_NONE) return PE_NONE;
+#if PE_SEQ_PROFILE
+    const long long tw0 = clock64();
+#endif
+    if (!wait_applied(P, S, i)) return PE_NONE;
+#if PE_SEQ_PROFILE
+    dbg.prof[6] += (unsigned long long)(clock64() - tw0);
+    dbg.prof[7] += n0;
+#endif
+    unsigned long long bp = c1;
+    uint32_t bn = n2;
+    for (uint32_t j = lane; j < n0; j += 32u) {
+        const uint32_t n = j < 32u ? head1 : L1[j];   // (j < 32 only in the first round, where j == lane)
+        const uint32_t sv = __ldcg(svccol + n), tot = __ldcg(P.T.total + n);    // live: the committer's reductions land in L2
+        const unsigned long long pref = make_pref(0u, sv, tot);
+        if (pref < bp || (pref == bp && n < bn)) { bp = pref; bn = n; }
+    }
+    const uint32_t hi = (uint32_t)(bp >> 32), lo = (uint32_t)bp;
+    const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+    const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
+    return __reduce_min_sync(0xFFFFFFFFu, (hi == mh && lo == ml) ? bn : 0xFFFFFFFFu);
+}
+
+__device__ __forceinline__ uint32_t consume_one(const SeqParams &P, SeqShared &S, uint32_t *touched, const uint32_t *ring, uint32_t *rowcur2,
+                                                uint32_t gq, uint32_t slot, uint32_t lane, uint32_t i, SeqDebug &dbg) {
+    const uint32_t N = P.T.n_nodes, nwords = (N + 31u) >> 5;
+#if PE_SEQ_PROFILE
+    const long long tq0 = clock64();
+    dbg.prof[0]++;
+#endif
+    const uint4 fa = *reinterpret_cast<const uint4 *>(&S.ft[slot].n_cand);
+    const uint4 fb = *reinterpret_cast<const uint4 *>(&S.ft[slot].n_class);
+    const uint32_t n_cand = fa.x, last = fa.y, n_list = fa.z, task_off = fa.w;
+    const uint32_t n_class = fb.x, row = fb.y, flags = fb.z, tie_start = fb.w;
+    if (!(flags & PE_FT_VALID)) return 1;                  // nothing feasible when the batch began, or k != 1
+    uint32_t n = PE_NONE;
+    if (n_list) {
+        // ---- list mode (canonical tie order)
+        const uint32_t c = lane < n_cand ? S.cands[slot][lane] : 0u;
+        const bool u = lane < n_cand && !((touched[c >> 5] >> (c & 31u)) & 1u);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, u);
+        if (b) n = __shfl_sync(0xFFFFFFFFu, c, __ffs((int)b) - 1);
+        else if (n_cand >= PE_SEQ_NCAND) return 2;         // cannot happen (see above); the block-wide walk is always right
+        else if (n_class > n_list) {
+            // every staged member is taken and the class goes on: continue on its bitmap (L2), 32 words a round
+#if PE_SEQ_PROFILE
+            const long long tb0 = clock64();
+            dbg.prof[2]++;
+#endif
+            const uint32_t *Erow = P.E + (size_t)row * 2u * P.e_stride;
+            for (uint32_t wb = last >> 5; wb < nwords && n == PE_NONE; wb += 32u) {
+                const uint32_t w = wb + lane;
                 uint32_t v = 0;
-                if (j + lane < nwin && w >= lo_word) {
-                    v = buf[j + lane] & ~touched[w];
-                    if (w == lo_word) v &= 0xFFFFFFFFu << (lo_bit & 31u);
+                if (w < nwords) {
+                    v = Erow[w] & ~touched[w];
+                    if (w == (last >> 5)) v &= (last & 31u) == 31u ? 0u : (0xFFFFFFFFu << ((last & 31u) + 1u));
                     if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
                 }
-                const uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0u);
-                if (b) {
-                    const int src = __ffs((int)b) - 1;
+                const uint32_t bb = __ballot_sync(0xFFFFFFFFu, v != 0u);
+                if (bb) {
+                    const int src = __ffs((int)bb) - 1;
                     const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
-                    n = (f.ws + j + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
+                    n = (wb + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
                 }
             }
-            if (n == PE_NONE) { reason = 2; break; }           // not inside the staged window (may wrap): block-wide walk
+#if PE_SEQ_PROFILE
+            dbg.prof[3] += (unsigned long long)(clock64() - tb0);
+#endif
         }
-        const bool counts = f.counts != 0u;
-        if (lane == 0) {
-            // out_fail rows were zeroed when the tick started.  For the common reservation (no generic
-            // resources / host ports) only the choice is recorded here; the column updates (four
-            // reductions per task) are applied by the whole block when fast mode ends -- nothing reads
-            // those columns in between, and global atomics in this loop would serialise on their latency.
-            if (f.simple) { P.K.out_node[f.task_off] = n; touched[n >> 5] |= 1u << (n & 31u); }
-            else fast_commit(P, f, start + i, n, touched);
+        if (n == PE_NONE && (flags & PE_FT_INLINE) && (flags & PE_FT_PLAIN) == PE_FT_PLAIN) {
+#if PE_SEQ_PROFILE
+            const long long tm0 = clock64();
+            dbg.prof[4]++;
+#endif
+            n = inline_medium(P, S, touched, rowcur2, row, i, lane, dbg);
+            if (n != PE_NONE) dbg.n_medium++;
+#if PE_SEQ_PROFILE
+            dbg.prof[5] += (unsigned long long)(clock64() - tm0);
+#endif
         }
-        __syncwarp();
-        if (lane == 0) sq_mbar_arrive_relaxed(&S.empty_bar[slot]);   // slot reads are done (their values were used above)
-        if (!counts) { reason = 3; i++; break; }               // rank did not move: later class bitmaps may hide this node
+        if (n == PE_NONE) return 4;                        // the whole class is consumed
+    } else {
+        // ---- bitmap mode (rotated tie order): the staged window of the class bitmap
+        const uint32_t lo_bit = tie_start;
+        const uint32_t lo_word = lo_bit >> 5;
+        const uint32_t ws = lo_word & ~3u;                 // window start, multiple of 4 words
+        const uint32_t nwin = min((uint32_t)PE_SEQ_WIN, nwords - ws);
+        const uint32_t *buf = ring + slot * PE_SEQ_WIN;
+        for (uint32_t j = 0; j < nwin && n == PE_NONE; j += 32u) {
+            const uint32_t w = ws + j + lane;
+            uint32_t v = 0;
+            if (j + lane < nwin && w >= lo_word) {
+                v = buf[j + lane] & ~touched[w];
+                if (w == lo_word) v &= 0xFFFFFFFFu << (lo_bit & 31u);
+                if (w == nwords - 1 && (N & 31u)) v &= (1u << (N & 31u)) - 1u;
+            }
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, v != 0u);
+            if (b) {
+                const int src = __ffs((int)b) - 1;
+                const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, src);
+                n = (ws + j + (uint32_t)src) * 32u + (uint32_t)__ffs((int)vv) - 1u;
+            }
+        }
+        if (n == PE_NONE) return 2;                        // not inside the staged window (may wrap): block-wide walk
     }
-    const uint32_t committed = (reason == 3) ? i : i;          // tasks [start, start+i) were placed here
-    dbg.n_fast += committed; dbg.n_placed += committed;
+    const bool counts = (flags & PE_FT_COUNTS) != 0u;
+    if (lane == 0) {
+        // out_fail rows were zeroed when the tick started.  For the common reservation (no generic
+        // resources / host ports) only the choice is logged here; the committer warp writes out_node
+        // and applies the column updates (four reductions per task) -- global traffic in this loop
+        // would serialise on its latency.
+        if (flags & PE_FT_SIMPLE) { atomicOr(&touched[n >> 5], 1u << (n & 31u)); S.log[i % PE_SEQ_LOGN] = n; }
+    }
+    if (!(flags & PE_FT_SIMPLE)) {
+        // generic resources / host ports are read-modify-write in place: the earlier reservations must have landed
+        if (!wait_applied(P, S, i)) return 1;
+        if (lane == 0) fast_commit(P, gq, task_off, counts, n, touched);
+    }
+    __syncwarp();   // (the slot is handed back when the caller publishes `pub`)
+#if PE_SEQ_PROFILE
+    dbg.prof[1] += (unsigned long long)(clock64() - tq0);
+#endif
+    return counts ? 0u : 16u + 3u;                         // rank did not move: later class bitmaps may hide this node
+}
+
+// The ordered warp's accesses to the touched bitmap, spelled out: an unconditional load (the compiler would
+// otherwise wrap each one in a divergent branch and serialise the eight loads of a group) and a single
+// reduction without the warp-aggregation code nvcc puts around atomicOr.
+template <bool TS>
+__device__ __forceinline__ uint32_t ld_touched(const uint32_t *touched, uint32_t word) {
+    uint32_t v;
+    if (TS) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(seq_smem_u32(touched + word)));
+    else asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(touched + word));
+    return v;
+}
+template <bool TS>
+__device__ __forceinline__ void mark_touched(uint32_t *touched, uint32_t n) {
+    if (TS) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(seq_smem_u32(touched + (n >> 5))), "r"(1u << (n & 31u)) : "memory");
+    else asm volatile("red.global.or.b32 [%0], %1;" ::"l"(touched + (n >> 5)), "r"(1u << (n & 31u)) : "memory");
+}
+
+// TS: the touched bitmap lives in shared memory.
+template <bool TS>
+__device__ __forceinline__ void fast_consumer(const SeqParams &P, SeqShared &S, uint32_t *touched_s, const uint32_t *ring, uint32_t *rowcur2,
+                                              uint32_t start, SeqDebug &dbg) {
+    uint32_t *touched = TS ? touched_s : P.touched_g;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t total = P.g_end - start;
+    uint32_t i = 0, reason = 0, applied_seen = 0;
+    while (i < total) {
+        if (i + (uint32_t)PE_SEQ_GROUP - applied_seen > (uint32_t)PE_SEQ_LOGN) {     // the placement log is a ring: never lap the committer
+            applied_seen = ld_acquire_smem(&S.applied);
+            if (i + (uint32_t)PE_SEQ_GROUP - applied_seen > (uint32_t)PE_SEQ_LOGN) {
+                if (!wait_applied(P, S, i + (uint32_t)PE_SEQ_GROUP - (uint32_t)PE_SEQ_LOGN)) { reason = 1; break; }
+                applied_seen = ld_acquire_smem(&S.applied);
+            }
+        }
+        // ---- PE_SEQ_GROUP plain list-mode tasks at once.  Groups are aligned, so the eight slots are
+        // consecutive, share the barrier phase, and every shared-memory address is base + constant.
+        if ((i & (uint32_t)(PE_SEQ_GROUP - 1)) == 0u && i + (uint32_t)PE_SEQ_GROUP <= total) {
+#if PE_SEQ_PROFILE
+            const long long tp0 = clock64();
+#endif
+            const uint32_t slot0 = i % PE_SEQ_RING, par = (i / PE_SEQ_RING) & 1u;
+            unsigned long long *fb = &S.full_bar[slot0];
+            bool ready = true;
+#pragma unroll
+            for (int q = 0; q < PE_SEQ_GROUP; q++) ready = sq_mbar_try_wait(fb + q, par) && ready;
+            if (!ready) {
+#pragma unroll 1
+                for (int q = 0; q < PE_SEQ_GROUP; q++) ready = sq_mbar_wait_wd(fb + q, par, P.ctr, PE_DEV_ERR_WD_CONSUMER) && (q == 0 || ready);
+                if (!ready) { reason = 1; break; }
+            }
+#if PE_SEQ_PROFILE
+            const long long tp1 = clock64();
+            dbg.cyc_wait += tp1 - tp0;
+#endif
+            uint32_t nc[PE_SEQ_GROUP], c[PE_SEQ_GROUP], u[PE_SEQ_GROUP];
+            const uint32_t *qk = &S.quick[slot0];
+            const uint32_t *cd = &S.cands[slot0][lane];
+#pragma unroll
+            for (int q = 0; q < PE_SEQ_GROUP; q++) { nc[q] = qk[q]; c[q] = cd[q * PE_SEQ_NCAND]; }
+#pragma unroll
+            for (int q = 0; q < PE_SEQ_GROUP; q++) {
+                const bool in = nc[q] != PE_NONE && lane < nc[q];      // (slots hold stale words past the candidate count)
+                c[q] = in ? c[q] : 0u;
+                const uint32_t tw = ld_touched<TS>(touched, c[q] >> 5);
+                u[q] = (in ? 1u : 0u) & ~(tw >> (c[q] & 31u));
+            }
+#if PE_SEQ_PROFILE
+            { uint32_t any = 0;
+#pragma unroll
+              for (int q = 0; q < PE_SEQ_GROUP; q++) any |= u[q];
+              if (__any_sync(0xFFFFFFFFu, any == 77u)) dbg.prof[15]++; }
+            const long long tp2 = clock64();
+            dbg.prof[8] += (unsigned long long)(tp2 - tp1);       // loads + touched bits
+#endif
+            uint32_t *lg = &S.log[i % PE_SEQ_LOGN];
+            uint32_t done = 0;
+#pragma unroll
+            for (int q = 0; q < PE_SEQ_GROUP; q++) {
+                if (done != (uint32_t)q) continue;
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, u[q] != 0u);
+                if (b == 0u) continue;                                           // the general routine takes it
+                const uint32_t n = __shfl_sync(0xFFFFFFFFu, c[q], __ffs((int)b) - 1);
+#pragma unroll
+                for (int r = q + 1; r < PE_SEQ_GROUP; r++) u[r] &= (c[r] != n) ? 1u : 0u;   // what this choice takes from the later ones
+                if (lane == 0) {
+                    mark_touched<TS>(touched, n);
+                    lg[q] = n;                                                   // out_node + reservation: committer warp
+                }
+                done = (uint32_t)q + 1u;
+            }
+#if PE_SEQ_PROFILE
+            const long long tp3 = clock64();
+            dbg.prof[9] += (unsigned long long)(tp3 - tp2);       // resolving the eight tasks
+#endif
+            __syncwarp();
+            i += done;
+            if (lane == 0 && done) st_release_smem(&S.pub, i);                   // committer may apply them, producers may refill the slots
+#if PE_SEQ_PROFILE
+            dbg.prof[10] += (unsigned long long)(clock64() - tp3);  // publish
+            dbg.prof[11]++;
+            dbg.cyc_work += clock64() - tp1;
+            if (done != (uint32_t)PE_SEQ_GROUP) dbg.iters++;
+#endif
+            if (done == (uint32_t)PE_SEQ_GROUP) continue;
+            if (i >= total) break;
+        }
+        // ---- one task, every case
+        const uint32_t slot = i % PE_SEQ_RING;
+        if (!sq_mbar_wait_wd(&S.full_bar[slot], (i / PE_SEQ_RING) & 1u, P.ctr, PE_DEV_ERR_WD_CONSUMER)) { reason = 1; break; }
+        const uint32_t r = consume_one(P, S, touched, ring, rowcur2, start + i, slot, lane, i, dbg);
+        if (r == 0u || r >= 16u) {
+            i++;
+            if (lane == 0) st_release_smem(&S.pub, i);
+        }
+        if (r == 0u) continue;
+        reason = r >= 16u ? r - 16u : r;
+        break;
+    }
+    dbg.n_fast += i; dbg.n_placed += i;                        // tasks [start, start+i) were placed here (n_medium of them by inline_medium)
     dbg.stops[reason < 5 ? reason : 0]++;
     if (lane == 0) {
         S.resume = start + i;
         S.consumed = i;
         S.stop_reason = reason;
         if (reason == 3) S.neutral = 1;
-        __threadfence_block();
-        *reinterpret_cast<volatile uint32_t *>(&S.stop) = 1;
+        st_release_smem(&S.pub, i);
+        st_release_smem(&S.stop, 1u);
     }
 }
 
-// ---- fast mode, producer warps (warps 1..PE_SEQ_NPW): warp p prefetches the tasks i == p-1 (mod NPW);
-// one converged lane per warp issues the TMA copy (the CUTLASS elect-one idiom).
-__device__ __forceinline__ void fast_producer(const SeqParams &P, SeqShared &S, uint32_t *ring, uint32_t start) {
-    const uint32_t lane = threadIdx.x & 31u, pw = (threadIdx.x >> 5) - 1u;
-    const uint32_t nwords = (P.T.n_nodes + 31u) >> 5;
-    const ScanResult *scan = P.scan; const uint32_t *E = P.E, *L = P.L;
-    const uint32_t g_begin = P.g_begin, g_end = P.g_end, e_stride = P.e_stride;
-    volatile uint32_t *vstop = &S.stop;
-    for (uint32_t i = pw; start + i < g_end; i += PE_SEQ_NPW) {
-        const uint32_t slot = i % PE_SEQ_RING, round = i / PE_SEQ_RING;
-        const uint32_t gq = start + i;
-        uint32_t go = 1;
-        if (lane == 0) {
-            const uint32_t row = P.task_row[gq - g_begin];
-            const ScanResult sr = scan[row];                   // issued before the wait: overlaps it
-            const uint32_t task_off = P.K.groups[gq].task_off;
-            while (!sq_mbar_try_wait(&S.empty_bar[slot], (round & 1u) ^ 1u)) {
-                if (*vstop) { go = 0; break; }
-                __nanosleep(32);
-            }
-            if (*vstop) go = 0;
-            if (go) {
-                FastTask f;
-                f.c0 = (sr.flags & PE_SR_K1) ? sr.c0 : PE_PREF_NONE;
-                f.row = row;
-                f.tie_start = sr.tie_start;
-                f.task_off = task_off;
-                f.cpu_res = sr.cpu_res; f.mem_res = sr.mem_res;
-                f.simple = (sr.flags & PE_SR_SIMPLE) ? 1u : 0u;
-                f.counts = (sr.flags & PE_SR_COUNTS) ? 1u : 0u;
-                f.svccol = sr.svccol;
-                f.ws = (sr.tie_start >> 5) & ~3u;                       // 16-byte aligned window start
-                f.n_class = sr.n0;
-                f.n_list = (sr.tie_start == 0u && f.c0 != PE_PREF_NONE) ? min(sr.n0, (uint32_t)PE_LIST_CAP) : 0u;
-                S.ft[slot] = f;
-                S.armed[slot] = i + 1u;
-                if (f.n_list) {
-                    const uint32_t bytes = ((f.n_list + 3u) & ~3u) * 4u;
-                    sq_mbar_expect_tx(&S.full_bar[slot], bytes);
-                    sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, L + (size_t)row * 2u * PE_LIST_CAP, bytes, &S.full_bar[slot]);
-                } else if (f.c0 != PE_PREF_NONE && f.ws < nwords) {
-                    // rows are padded to e_stride (a multiple of 32 words), so the copy may run past nwords
-                    const uint32_t nw = min((uint32_t)PE_SEQ_WIN, e_stride - f.ws);
-                    const uint32_t *src = E + (size_t)row * 2u * e_stride + f.ws;
-                    sq_mbar_expect_tx(&S.full_bar[slot], nw * 4u);
-                    sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, src, nw * 4u, &S.full_bar[slot]);
-                } else {
-                    sq_mbar_arrive(&S.full_bar[slot]);
+// Committer warp: applies the reservations of the tasks the ordered warp placed (NodeInfo.addTask,
+// nodeinfo.go:125-153, as reductions), 32 tasks at a time, and publishes how far it got.
+__device__ __forceinline__ void fast_committer(const SeqParams &P, SeqShared &S, uint32_t start) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t done = 0;
+    for (;;) {
+        const uint32_t stop = ld_acquire_smem(&S.stop);
+        const uint32_t pub = ld_acquire_smem(&S.pub);
+        if (pub == done) {
+            if (stop) break;
+            __nanosleep(20);
+            continue;
+        }
+        const uint32_t q = done + lane;
+        if (q < pub) {
+            const uint32_t gq = start + q;
+            const ScanResult *sr = &P.scan[P.task_row[gq - P.g_begin]];
+            const uint32_t fl = sr->flags;
+            if (fl & PE_SR_SIMPLE) {               // others were applied in place by the ordered warp
+                const uint32_t n = S.log[q % PE_SEQ_LOGN];
+                P.K.out_node[P.K.groups[gq].task_off] = n;
+                const long long cpu_res = sr->cpu_res, mem_res = sr->mem_res;
+                if (cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&P.T.cpu[n]), (unsigned long long)(-cpu_res));
+                if (mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&P.T.mem[n]), (unsigned long long)(-mem_res));
+                if (fl & PE_SR_COUNTS) {
+                    atomicAdd(&P.T.total[n], 1u);
+                    if (atomicAdd(&sr->svccol[n], 1u) + 1u >= 0xFFFFFFu) atomicOr(&P.ctr->error, PE_DEV_ERR_SVC_OVERFLOW);
                 }
             }
         }
-        go = __shfl_sync(0xFFFFFFFFu, go, 0);    // the whole warp leaves together (and reaches the block barrier converged)
-        if (!go) break;
+        __threadfence();
+        __syncwarp();
+        done = min(pub, done + 32u);
+        if (lane == 0) st_release_smem(&S.applied, done);
+    }
+}
+
+// Producer side of one task, split in two so that a warp keeps two tasks in flight: `stage_issue`
+// (lane 0) waits for the slot, writes the descriptor and starts the copy; `stage_finish` (whole
+// warp) waits for the copy, picks the candidates and hands the slot to the consumer.
+struct ProdDesc { uint32_t row, off; unsigned long long c0; uint4 meta; };   // lane 0's prefetched view of a task (meta = n0, n1, tie_start, flags)
+struct ProdTask { uint32_t go, n_list, base, n_listed, row, copy; };   // n_list members staged from list offset base; n_listed in the row's list
+
+__device__ __forceinline__ ProdTask stage_issue(const SeqParams &P, SeqShared &S, uint32_t *ring, uint32_t *rowcur, uint32_t start, uint32_t i,
+                                                uint32_t lane, const ProdDesc &d) {
+    const uint32_t row = d.row, task_off = d.off;
+    ProdTask t; t.go = 1; t.n_list = 0; t.base = 0; t.n_listed = 0; t.row = row; t.copy = 0;
+    const uint32_t slot = i % PE_SEQ_RING;
+    if (lane == 0) {
+        const uint32_t nwords = (P.T.n_nodes + 31u) >> 5;
+        volatile uint32_t *vstop = &S.stop;
+        const unsigned long long c0 = d.c0;
+        const uint4 meta = d.meta;
+        while (ld_acquire_smem(&S.pub) + (uint32_t)PE_SEQ_RING <= i) {      // the slot's previous task (i - RING) is not consumed yet
+            if (*vstop) { t.go = 0; break; }
+            __nanosleep(32);
+        }
+        if (*vstop) t.go = 0;
+        if (t.go) {
+            const bool valid = (meta.w & PE_SR_K1) && c0 != PE_PREF_NONE;
+            FastTask &f = S.ft[slot];
+            // list mode: stage the window of the member list that starts at the row's cursor (every member
+            // before the cursor is known to be touched: tasks that share the row, and windows already walked)
+            if (meta.z == 0u && valid) {
+                t.n_listed = min(meta.x, (uint32_t)PE_LIST_CAP);
+                t.base = row < (uint32_t)PE_SEQ_ROWCUR ? (min(rowcur[row], t.n_listed - 1u) & ~3u) : 0u;
+                t.n_list = min(t.n_listed - t.base, (uint32_t)PE_SEQ_WIN);
+            }
+            f.n_cand = 0; f.last = 0;
+            S.quick[slot] = PE_NONE;
+            f.n_list = t.n_list;
+            f.task_off = task_off;
+            f.n_class = meta.x;
+            f.row = row;
+            f.flags = (valid ? PE_FT_VALID : 0u) | ((meta.w & PE_SR_SIMPLE) ? PE_FT_SIMPLE : 0u) | ((meta.w & PE_SR_COUNTS) ? PE_FT_COUNTS : 0u) |
+                      ((meta.w & PE_SR_STATIC_ONLY) ? PE_FT_INLINE : 0u);
+            f.tie_start = meta.z;
+            bool has_copy = false;
+            if (t.n_list) {
+                const uint32_t bytes = ((t.n_list + 3u) & ~3u) * 4u;
+                sq_mbar_expect_tx(&S.tma_bar[slot], bytes);
+                sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, P.L + (size_t)row * 2u * PE_LIST_CAP + t.base, bytes, &S.tma_bar[slot]);
+                has_copy = true;
+            } else if (valid) {
+                const uint32_t ws = (meta.z >> 5) & ~3u;                       // 16-byte aligned window start
+                if (ws < nwords) {
+                    // rows are padded to e_stride (a multiple of 32 words), so the copy may run past nwords
+                    const uint32_t nw = min((uint32_t)PE_SEQ_WIN, P.e_stride - ws);
+                    sq_mbar_expect_tx(&S.tma_bar[slot], nw * 4u);
+                    sq_tma_bulk_g2s(ring + slot * PE_SEQ_WIN, P.E + (size_t)row * 2u * P.e_stride + ws, nw * 4u, &S.tma_bar[slot]);
+                    has_copy = true;
+                }
+            }
+            t.copy = has_copy ? 1u : 0u;
+        }
+    }
+    t.go = __shfl_sync(0xFFFFFFFFu, t.go, 0);
+    t.n_list = __shfl_sync(0xFFFFFFFFu, t.n_list, 0);
+    t.base = __shfl_sync(0xFFFFFFFFu, t.base, 0);
+    t.n_listed = __shfl_sync(0xFFFFFFFFu, t.n_listed, 0);
+    t.row = __shfl_sync(0xFFFFFFFFu, t.row, 0);
+    t.copy = __shfl_sync(0xFFFFFFFFu, t.copy, 0);
+    return t;
+}
+
+__device__ __forceinline__ bool stage_finish(const SeqParams &P, SeqShared &S, uint32_t *ring, uint32_t *rowcur, const uint32_t *touched,
+                                             uint32_t i, uint32_t lane, ProdTask t) {
+    const uint32_t slot = i % PE_SEQ_RING;
+    uint32_t *buf = ring + slot * PE_SEQ_WIN;
+    auto wait_copy = [&]() -> bool {
+        const uint32_t ph = S.tma_ph[slot];
+        if (!sq_mbar_wait_wd(&S.tma_bar[slot], ph, P.ctr, PE_DEV_ERR_WD_DRAIN)) return false;
+        __syncwarp();
+        if (lane == 0) S.tma_ph[slot] = ph ^ 1u;
+        __syncwarp();
+        return true;
+    };
+    if (t.copy && !wait_copy()) return false;
+    if (t.n_list) {
+        const uint32_t lane_lt = (1u << lane) - 1u;
+        uint32_t found = 0, first_at = 0;
+        for (;;) {
+            // the first PE_SEQ_NCAND untouched members of the window, in list order (lane-major: 4 consecutive entries per lane)
+            const uint4 *lst4 = reinterpret_cast<const uint4 *>(buf);
+            for (uint32_t j = 0; j < t.n_list && found < PE_SEQ_NCAND; j += 128u) {
+                const uint32_t il = j + lane * 4u;
+                uint32_t m = 0;
+                uint4 e = make_uint4(0, 0, 0, 0);
+                if (il < t.n_list) {
+                    e = lst4[il >> 2];
+                    const uint32_t left = t.n_list - il;
+                    const uint32_t tx = touched[e.x >> 5], ty = left > 1u ? touched[e.y >> 5] : ~0u;
+                    const uint32_t tz = left > 2u ? touched[e.z >> 5] : ~0u, tw = left > 3u ? touched[e.w >> 5] : ~0u;
+                    m = (((tx >> (e.x & 31u)) & 1u) ^ 1u) | ((((ty >> (e.y & 31u)) & 1u) ^ 1u) << 1) | ((((tz >> (e.z & 31u)) & 1u) ^ 1u) << 2) |
+                        ((((tw >> (e.w & 31u)) & 1u) ^ 1u) << 3);
+                }
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, m & 1u), b1 = __ballot_sync(0xFFFFFFFFu, m & 2u);
+                const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, m & 4u), b3 = __ballot_sync(0xFFFFFFFFu, m & 8u);
+                const uint32_t any = b0 | b1 | b2 | b3;
+                if (found == 0u && any) first_at = j + (uint32_t)(__ffs((int)any) - 1) * 4u;   // (rounded down to the lane's 4 entries)
+                uint32_t pos = found + __popc(b0 & lane_lt) + __popc(b1 & lane_lt) + __popc(b2 & lane_lt) + __popc(b3 & lane_lt);
+                if ((m & 1u) && pos < PE_SEQ_NCAND) S.cands[slot][pos] = e.x;
+                pos += m & 1u;
+                if ((m & 2u) && pos < PE_SEQ_NCAND) S.cands[slot][pos] = e.y;
+                pos += (m >> 1) & 1u;
+                if ((m & 4u) && pos < PE_SEQ_NCAND) S.cands[slot][pos] = e.z;
+                pos += (m >> 2) & 1u;
+                if ((m & 8u) && pos < PE_SEQ_NCAND) S.cands[slot][pos] = e.w;
+                found += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+            }
+            // every member before this one is touched for good: later tasks of the row start here
+            const uint32_t cur = t.base + (found ? first_at : t.n_list);
+            if (lane == 0 && t.row < (uint32_t)PE_SEQ_ROWCUR) atomicMax(&rowcur[t.row], cur);
+            if (found || t.base + t.n_list >= t.n_listed) break;
+            // the whole window is taken and the list goes on: bring the next window into the same slot
+            t.base += t.n_list;
+            t.n_list = min(t.n_listed - t.base, (uint32_t)PE_SEQ_WIN);
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const uint32_t bytes = ((t.n_list + 3u) & ~3u) * 4u;
+                sq_mbar_expect_tx(&S.tma_bar[slot], bytes);
+                sq_tma_bulk_g2s(buf, P.L + (size_t)t.row * 2u * PE_LIST_CAP + t.base, bytes, &S.tma_bar[slot]);
+            }
+            if (!wait_copy()) return false;
+        }
+        if (lane == 0) {
+            const uint32_t fl = S.ft[slot].flags;
+            S.quick[slot] = (fl & PE_FT_PLAIN) == PE_FT_PLAIN ? min(found, (uint32_t)PE_SEQ_NCAND) : PE_NONE;
+            S.ft[slot].n_cand = min(found, (uint32_t)PE_SEQ_NCAND);
+            S.ft[slot].n_list = t.base + t.n_list;     // list members known to the pipeline (all touched, or candidates)
+            S.ft[slot].last = buf[t.n_list - 1u];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) sq_mbar_arrive(&S.full_bar[slot]);   // release: descriptor, candidates and the copied words are visible
+    return true;
+}
+
+// One converged lane per warp issues the TMA copies (the CUTLASS elect-one idiom).  A producer
+// never leaves with a copy in flight: whatever it issued it also waits for.
+__device__ __forceinline__ void fast_producer(const SeqParams &P, SeqShared &S, uint32_t *ring, uint32_t *rowcur, const uint32_t *touched,
+                                              uint32_t start) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t pw = warp - 1u - (warp >> 2);     // 1,2,3,5,6,7,9,10,11,13,14 -> 0..10
+    const uint32_t total = P.g_end - start;
+    if (pw >= total) return;
+    // lane 0's global loads run ahead of their use: the task -> row map two tasks ahead, the row record one ahead
+    auto load_row = [&](uint32_t i, ProdDesc &d) {
+        if (lane == 0 && i < total) { d.row = P.task_row[start + i - P.g_begin]; d.off = P.K.groups[start + i].task_off; }
+    };
+    auto load_scan = [&](uint32_t i, ProdDesc &d) {
+        if (lane == 0 && i < total) { d.c0 = P.scan[d.row].c0; d.meta = *reinterpret_cast<const uint4 *>(&P.scan[d.row].n0); }
+    };
+    ProdDesc dA{}, dB{}, dC{};
+    load_row(pw, dA); load_row(pw + PE_SEQ_NPW, dB); load_row(pw + 2u * PE_SEQ_NPW, dC);
+    load_scan(pw, dA); load_scan(pw + PE_SEQ_NPW, dB);
+    ProdTask cur = stage_issue(P, S, ring, rowcur, start, pw, lane, dA);
+    if (!cur.go) return;
+    for (uint32_t i = pw;; i += PE_SEQ_NPW) {
+        const uint32_t nxt = i + PE_SEQ_NPW;
+        ProdTask nx; nx.go = 0; nx.n_list = 0; nx.base = 0; nx.n_listed = 0; nx.row = 0; nx.copy = 0;
+        if (nxt < total) {
+            load_scan(nxt + PE_SEQ_NPW, dC);
+            ProdDesc dN{};
+            load_row(nxt + 2u * PE_SEQ_NPW, dN);
+            nx = stage_issue(P, S, ring, rowcur, start, nxt, lane, dB);   // the next copy flies while this task's list is walked
+            dB = dC; dC = dN;
+        }
+        if (!stage_finish(P, S, ring, rowcur, touched, i, lane, cur)) return;
+        if (nxt >= total || !nx.go) return;     // (stage_issue starts no copy when it returns go == 0)
+        cur = nx;
     }
 }
 
@@ -462,9 +884,13 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     uint32_t *st_tot_s = st_svc_s + PE_SEQ_KS;
     uint32_t *st_placed_s = st_tot_s + PE_SEQ_KS;
     uint8_t *st_flags_s = reinterpret_cast<uint8_t *>(st_placed_s + PE_SEQ_KS);
-    uint32_t *touched_s = reinterpret_cast<uint32_t *>(st_flags_s + PE_SEQ_KS);
+    uint32_t *touched_s = reinterpret_cast<uint32_t *>(dyn_smem + PE_SEQ_REGION0);   // after the staging area / the ring + cursors aliasing it
     uint32_t *touched = P.touched_in_smem ? touched_s : P.touched_g;
-    uint32_t *ring = touched_s + (P.touched_in_smem ? ((P.touched_words + 3u) & ~3u) : 0u);   // [PE_SEQ_RING][PE_SEQ_WIN]
+    // fast mode (scan batches hold k == 1 groups only) re-uses the k > 1 staging area: ring slots + per-row list cursors
+    uint32_t *ring = reinterpret_cast<uint32_t *>(dyn_smem);   // [PE_SEQ_RING][PE_SEQ_WIN]
+    uint32_t *rowcur = ring + PE_SEQ_RING * PE_SEQ_WIN;        // [PE_SEQ_ROWCUR]
+    uint32_t *rowcur2 = rowcur + PE_SEQ_ROWCUR;                // second-class cursors (inline_medium)
+    if (P.scan != nullptr) for (uint32_t r = tid; r < 2u * PE_SEQ_ROWCUR; r += nth) rowcur[r] = 0;
 
     for (uint32_t w = tid; w < P.touched_words; w += nth) touched[w] = 0;
     if (tid == 0) { S.neutral = 0; S.bars_live = 0; S.bestv[0] = S.bestv[1] = S.bestv[2] = PE_NONE; }
@@ -487,42 +913,26 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             { const long long t1 = clock64(); cyc_generic += t1 - t_mark; t_mark = t1; }
             if (tid == 0) {
                 for (int r = 0; r < PE_SEQ_RING; r++) {
-                    if (S.bars_live) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.empty_bar[r]); }
+                    if (S.bars_live) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.tma_bar[r]); }
                     sq_mbar_init(&S.full_bar[r], 1);
-                    sq_mbar_init(&S.empty_bar[r], 1);
-                    S.armed[r] = 0;
+                    sq_mbar_init(&S.tma_bar[r], 1);
+                    S.tma_ph[r] = 0;
                 }
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 S.bars_live = 1;
-                S.stop = 0;
+                S.stop = 0; S.pub = 0; S.applied = 0;
                 S.resume = P.g_end;
                 S.stop_reason = 0;
             }
             __syncthreads();
             const uint32_t start = gi;
-            const uint32_t nwords = (N + 31u) >> 5;
-            volatile uint32_t *vstop = &S.stop;
-            if (warp == 0) fast_consumer(P, S, touched, ring, start, dbg);
-            else if (warp <= PE_SEQ_NPW) fast_producer(P, S, ring, start);
-            __syncthreads();
-            // bulk copies armed for slots the consumer never took must land before the ring is reused
             if (warp == 0) {
-                for (uint32_t r = 0; r < PE_SEQ_RING; r++) {     // converged: every lane waits on the same slot
-                    const uint32_t a = S.armed[r];
-                    if (a != 0u && a - 1u >= S.consumed) sq_mbar_wait_wd(&S.full_bar[r], ((a - 1u) / PE_SEQ_RING) & 1u, P.ctr, PE_DEV_ERR_WD_DRAIN);
-                }
+                if (P.touched_in_smem) fast_consumer<true>(P, S, touched_s, ring, rowcur2, start, dbg);
+                else fast_consumer<false>(P, S, touched_s, ring, rowcur2, start, dbg);
             }
-            __syncthreads();
-            // apply the deferred reservations of the tasks fast mode placed: [start, start + consumed)
-            for (uint32_t q = start + tid; q < start + S.consumed; q += nth) {
-                const ScanResult sr = P.scan[P.task_row[q - P.g_begin]];
-                if (!(sr.flags & PE_SR_SIMPLE)) continue;              // already applied in place
-                const uint32_t n = K.out_node[K.groups[q].task_off];
-                if (sr.cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.cpu[n]), (unsigned long long)(-sr.cpu_res));
-                if (sr.mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&T.mem[n]), (unsigned long long)(-sr.mem_res));
-                if (sr.flags & PE_SR_COUNTS) { atomicAdd(&T.total[n], 1u); atomicAdd(&sr.svccol[n], 1u); }
-            }
-            __syncthreads();
+            else if (warp == 15) fast_committer(P, S, start);
+            else if ((warp & 3u) != 0u) fast_producer(P, S, ring, rowcur, touched, start);
+            __syncthreads();   // no copy is in flight (every producer waits for the one it issued); every reservation is applied
             { const long long t1 = clock64(); cyc_fast += t1 - t_mark; t_mark = t1; }
             gi = S.resume;
             if (gi >= P.g_end) break;
@@ -995,7 +1405,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
         }
     }
     if (tid == 0) {
-        n_fast += dbg.n_fast; n_placed += dbg.n_placed;
+        n_fast += dbg.n_fast - dbg.n_medium; n_medium += dbg.n_medium; n_placed += dbg.n_placed;
         P.ctr->fast_path += n_fast;
         P.ctr->medium_path += n_medium;
         cyc_generic += clock64() - t_mark;   // whatever is left is the generic path (and loop overhead)
@@ -1004,6 +1414,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
         P.ctr->cyc_generic += (unsigned long long)cyc_generic;
         P.ctr->cyc_cons_wait += (unsigned long long)dbg.cyc_wait; P.ctr->cyc_cons_work += (unsigned long long)dbg.cyc_work; P.ctr->iters += dbg.iters;
         for (int r = 0; r < 5; r++) P.ctr->stops[r] += dbg.stops[r];
+        for (int r = 0; r < 16; r++) P.ctr->prof[r] += dbg.prof[r];
         P.ctr->slow_path += n_slow;
         P.ctr->placements += n_placed;
         P.ctr->evals_generic += n_evalg;
@@ -1011,9 +1422,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
 }
 
 static inline size_t seq_dyn_smem_bytes(uint32_t touched_words_in_smem) {
-    size_t a = (size_t)PE_SEQ_KS * (sizeof(CandKey) + 8 + 8 + 4 + 4 + 4 + 1);
-    size_t b = (size_t)PE_SEQ_RING * PE_SEQ_WIN * 4;    // fast-mode ring
-    return a + (((size_t)touched_words_in_smem + 3) & ~(size_t)3) * 4 + b + 16;
+    return (size_t)PE_SEQ_REGION0 + (((size_t)touched_words_in_smem + 3) & ~(size_t)3) * 4 + 16;
 }
 
 }  // namespace pe
