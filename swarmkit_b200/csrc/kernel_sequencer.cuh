@@ -42,10 +42,11 @@ __device__ __forceinline__ bool key_less(const CandKey &a, const CandKey &b) {
 #endif
 #define PE_SEQ_THREADS 512     // 128 registers per thread: the ordered fast path must not spill
 #define PE_SEQ_KS 2048          // candidates staged in shared memory
-#define PE_SEQ_RING 32          // fast-mode ring slots
+#define PE_SEQ_RING 64          // fast-mode ring slots (copies are started this far ahead of the ordered warp)
 #define PE_SEQ_NPW 11           // producer warps: 1-3, 5-7, 9-11, 13-14.  Warp 15 commits; warps 4, 8, 12 sit fast mode out so
                                 // that the ordered warp (warp 0) has its SM sub-partition's issue slots to itself
-#define PE_SEQ_WIN 512          // words staged per task: list entries, or bitmap words (16k nodes)
+#define PE_SEQ_WIN 256          // words staged per task: list entries, or bitmap words (8k nodes)
+#define PE_SEQ_DEPTH 3          // copies a producer warp keeps in flight
 #define PE_MAX_GEN_WANTS 8
 #define PE_CTX_MAXC 16
 #define PE_ST_FAILED 1u
@@ -159,7 +160,7 @@ struct FastTask {
 #define PE_FT_COUNTS 4u   // DesiredState <= COMPLETED
 #define PE_FT_PLAIN (PE_FT_VALID | PE_FT_SIMPLE | PE_FT_COUNTS)
 #define PE_FT_INLINE 8u   // no state-dependent filter: a consumed best class is resolved by the ordered warp itself
-#define PE_SEQ_NCAND 32   // candidates per task: must be >= PE_SEQ_RING (see fast_consumer)
+#define PE_SEQ_NCAND 32   // candidates per task = how far ahead of the ordered warp a list is walked (see fast_consumer)
 #define PE_SEQ_GROUP 8    // tasks the ordered warp resolves per iteration
 #define PE_SEQ_LOGN 512   // placements the ordered warp may run ahead of the committer warp
 #define PE_SEQ_ROWCUR 6656 // scan rows that get list cursors (the ring and the cursors alias the k > 1 staging area)
@@ -176,7 +177,8 @@ struct SeqShared {
     uint32_t log[PE_SEQ_LOGN];   // node chosen for fast task q of the session, at q % PE_SEQ_LOGN
     uint32_t pub, applied;       // tasks placed by the ordered warp / reservations applied by the committer warp
     uint32_t tma_ph[PE_SEQ_RING];   // phase of each slot's copy barrier (one producer owns a slot at a time)
-    unsigned long long full_bar[PE_SEQ_RING], tma_bar[PE_SEQ_RING];
+    unsigned long long tma_bar[PE_SEQ_RING];
+    uint32_t ready[PE_SEQ_RING];  // session index + 1 of the task staged in the slot (release-stored by its producer)
     uint32_t stop, resume, stop_reason, bars_live, consumed;
     uint32_t red32[40];
     unsigned long long red64[40];
@@ -313,13 +315,13 @@ struct SeqDebug { unsigned long long n_fast, n_placed, n_medium, iters, stops[5]
 // Warp 0 consumes tasks strictly in order; warps 1..PE_SEQ_NPW stay ahead of it.  Producer warp p
 // stages the tasks i == p-1 (mod NPW): the scan row's member list comes into the task's ring slot
 // by TMA bulk copy, the producer walks it against the `touched` bitmap and leaves the first
-// PE_SEQ_NCAND untouched members as the task's candidates.  Touched bits never clear, and a slot is
-// refilled only after its previous task was consumed, so at most PE_SEQ_RING - 1 placements happen
-// between the producer's look and the consumer's turn: of PE_SEQ_NCAND >= PE_SEQ_RING candidates
-// one always survives, and it is exactly the first untouched member.  The ordered warp's dependent
-// chain per task is: one candidate per lane, its touched bit, a ballot.  Four consecutive tasks are
-// resolved per iteration: their loads are issued together and the choices of the earlier ones are
-// applied to the later ones in registers.
+// PE_SEQ_NCAND untouched members as the task's candidates.  Touched bits never clear, so every
+// member before a candidate stays touched and the first candidate that is still untouched at the
+// task's turn is exactly the first untouched member; at most PE_SEQ_RING - 1 placements happen in
+// between, which almost never takes all the candidates (then the ordered warp walks the window
+// itself).  The ordered warp's dependent chain per task is: one candidate per lane, its touched
+// bit, a warp min-reduction.  PE_SEQ_GROUP consecutive tasks are resolved per iteration: their loads
+// are issued together and the choices of the earlier ones are applied to the later ones in registers.
 
 __device__ __forceinline__ void fast_commit(const SeqParams &P, uint32_t gq, uint32_t task_off, bool counts, uint32_t n, uint32_t *touched) {
     P.K.out_node[task_off] = n;
@@ -440,8 +442,19 @@ __device__ __forceinline__ uint32_t consume_one(const SeqParams &P, SeqShared &S
         const bool u = lane < n_cand && !((touched[c >> 5] >> (c & 31u)) & 1u);
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, u);
         if (b) n = __shfl_sync(0xFFFFFFFFu, c, __ffs((int)b) - 1);
-        else if (n_cand >= PE_SEQ_NCAND) return 2;         // cannot happen (see above); the block-wide walk is always right
-        else if (n_class > n_list) {
+        if (n == PE_NONE && n_cand >= PE_SEQ_NCAND) {
+            // every candidate went to the tasks in between (the list was walked up to PE_SEQ_RING tasks ago): walk the
+            // staged window again; members before it are touched, so what it finds is the first untouched member
+            const uint32_t *lst = ring + slot * PE_SEQ_WIN;
+            for (uint32_t j = 0; j < tie_start && n == PE_NONE; j += 32u) {           // (list mode keeps the staged count in this field)
+                const uint32_t idx = j + lane;
+                const uint32_t v = idx < tie_start ? lst[idx] : 0u;
+                const bool uu = idx < tie_start && !((touched[v >> 5] >> (v & 31u)) & 1u);
+                const uint32_t bb = __ballot_sync(0xFFFFFFFFu, uu);
+                if (bb) n = __shfl_sync(0xFFFFFFFFu, v, __ffs((int)bb) - 1);
+            }
+        }
+        if (n == PE_NONE && n_class > n_list) {
             // every staged member is taken and the class goes on: continue on its bitmap (L2), 32 words a round
 #if PE_SEQ_PROFILE
             const long long tb0 = clock64();
@@ -562,54 +575,70 @@ __device__ __forceinline__ void fast_consumer(const SeqParams &P, SeqShared &S, 
             const long long tp0 = clock64();
 #endif
             const uint32_t slot0 = i % PE_SEQ_RING, par = (i / PE_SEQ_RING) & 1u;
-            unsigned long long *fb = &S.full_bar[slot0];
+            // eight plain loads of the slots' ready words (an mbarrier wait costs ~150 cycles each), then one acquire fence
+            const volatile uint32_t *rd = &S.ready[slot0];
             bool ready = true;
+            {
+                uint32_t rv[PE_SEQ_GROUP];
 #pragma unroll
-            for (int q = 0; q < PE_SEQ_GROUP; q++) ready = sq_mbar_try_wait(fb + q, par) && ready;
-            if (!ready) {
-#pragma unroll 1
-                for (int q = 0; q < PE_SEQ_GROUP; q++) ready = sq_mbar_wait_wd(fb + q, par, P.ctr, PE_DEV_ERR_WD_CONSUMER) && (q == 0 || ready);
-                if (!ready) { reason = 1; break; }
+                for (int q = 0; q < PE_SEQ_GROUP; q++) rv[q] = rd[q];
+#pragma unroll
+                for (int q = 0; q < PE_SEQ_GROUP; q++) ready = ready && rv[q] == i + (uint32_t)q + 1u;
             }
+            if (!ready) {
+                const long long t0 = clock64();
+#pragma unroll 1
+                for (int q = 0; q < PE_SEQ_GROUP; q++) {
+                    while (rd[q] != i + (uint32_t)q + 1u) {
+                        __nanosleep(20);
+                        if (clock64() - t0 > 2000000000LL) { atomicOr(&P.ctr->error, PE_DEV_ERR_WD_CONSUMER); reason = 1; break; }
+                    }
+                    if (reason) break;
+                }
+                if (reason) break;
+            }
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            (void)par;
 #if PE_SEQ_PROFILE
             const long long tp1 = clock64();
             dbg.cyc_wait += tp1 - tp0;
 #endif
-            uint32_t nc[PE_SEQ_GROUP], c[PE_SEQ_GROUP], u[PE_SEQ_GROUP];
+            // k[q]: this lane's candidate for task q if it is still untouched, else PE_NONE.  Lists are in node
+            // order, so the first untouched candidate is the smallest key: one warp reduction per task.
+            uint32_t nc[PE_SEQ_GROUP], k[PE_SEQ_GROUP];
             const uint32_t *qk = &S.quick[slot0];
             const uint32_t *cd = &S.cands[slot0][lane];
 #pragma unroll
-            for (int q = 0; q < PE_SEQ_GROUP; q++) { nc[q] = qk[q]; c[q] = cd[q * PE_SEQ_NCAND]; }
+            for (int q = 0; q < PE_SEQ_GROUP; q++) { nc[q] = qk[q]; k[q] = cd[q * PE_SEQ_NCAND]; }
 #pragma unroll
             for (int q = 0; q < PE_SEQ_GROUP; q++) {
                 const bool in = nc[q] != PE_NONE && lane < nc[q];      // (slots hold stale words past the candidate count)
-                c[q] = in ? c[q] : 0u;
-                const uint32_t tw = ld_touched<TS>(touched, c[q] >> 5);
-                u[q] = (in ? 1u : 0u) & ~(tw >> (c[q] & 31u));
+                const uint32_t c = in ? k[q] : 0u;
+                const uint32_t tw = ld_touched<TS>(touched, c >> 5);
+                k[q] = (in && !((tw >> (c & 31u)) & 1u)) ? c : PE_NONE;
             }
 #if PE_SEQ_PROFILE
             { uint32_t any = 0;
 #pragma unroll
-              for (int q = 0; q < PE_SEQ_GROUP; q++) any |= u[q];
-              if (__any_sync(0xFFFFFFFFu, any == 77u)) dbg.prof[15]++; }
+              for (int q = 0; q < PE_SEQ_GROUP; q++) any |= k[q];
+              if (__any_sync(0xFFFFFFFFu, any == 77u)) dbg.prof[7]++; }
             const long long tp2 = clock64();
             dbg.prof[8] += (unsigned long long)(tp2 - tp1);       // loads + touched bits
 #endif
-            uint32_t *lg = &S.log[i % PE_SEQ_LOGN];
-            uint32_t done = 0;
+            uint32_t done = 0, mine = 0;
 #pragma unroll
             for (int q = 0; q < PE_SEQ_GROUP; q++) {
                 if (done != (uint32_t)q) continue;
-                const uint32_t b = __ballot_sync(0xFFFFFFFFu, u[q] != 0u);
-                if (b == 0u) continue;                                           // the general routine takes it
-                const uint32_t n = __shfl_sync(0xFFFFFFFFu, c[q], __ffs((int)b) - 1);
+                const uint32_t n = __reduce_min_sync(0xFFFFFFFFu, k[q]);
+                if (n == PE_NONE) continue;                                      // the general routine takes it
 #pragma unroll
-                for (int r = q + 1; r < PE_SEQ_GROUP; r++) u[r] &= (c[r] != n) ? 1u : 0u;   // what this choice takes from the later ones
-                if (lane == 0) {
-                    mark_touched<TS>(touched, n);
-                    lg[q] = n;                                                   // out_node + reservation: committer warp
-                }
+                for (int r = q + 1; r < PE_SEQ_GROUP; r++) k[r] = (k[r] == n) ? PE_NONE : k[r];   // what this choice takes from the later ones
+                mine = lane == (uint32_t)q ? n : mine;
                 done = (uint32_t)q + 1u;
+            }
+            if (lane < done) {
+                mark_touched<TS>(touched, mine);
+                S.log[(i % PE_SEQ_LOGN) + lane] = mine;                          // out_node + reservation: committer warp
             }
 #if PE_SEQ_PROFILE
             const long long tp3 = clock64();
@@ -629,7 +658,14 @@ __device__ __forceinline__ void fast_consumer(const SeqParams &P, SeqShared &S, 
         }
         // ---- one task, every case
         const uint32_t slot = i % PE_SEQ_RING;
-        if (!sq_mbar_wait_wd(&S.full_bar[slot], (i / PE_SEQ_RING) & 1u, P.ctr, PE_DEV_ERR_WD_CONSUMER)) { reason = 1; break; }
+        {
+            const long long t0 = clock64();
+            while (ld_acquire_smem(&S.ready[slot]) != i + 1u) {
+                __nanosleep(20);
+                if (clock64() - t0 > 2000000000LL) { atomicOr(&P.ctr->error, PE_DEV_ERR_WD_CONSUMER); reason = 1; break; }
+            }
+            if (reason) break;
+        }
         const uint32_t r = consume_one(P, S, touched, ring, rowcur2, start + i, slot, lane, i, dbg);
         if (r == 0u || r >= 16u) {
             i++;
@@ -702,12 +738,22 @@ __device__ __forceinline__ ProdTask stage_issue(const SeqParams &P, SeqShared &S
     if (lane == 0) {
         const uint32_t nwords = (P.T.n_nodes + 31u) >> 5;
         volatile uint32_t *vstop = &S.stop;
+#if PE_SEQ_PROFILE
+        const long long ta = clock64();
+#endif
         const unsigned long long c0 = d.c0;
         const uint4 meta = d.meta;
+#if PE_SEQ_PROFILE
+        const long long tb = clock64() + (long long)(meta.x & 0u) + (long long)(c0 & 0ull);   // (depends on the loads)
+#endif
         while (ld_acquire_smem(&S.pub) + (uint32_t)PE_SEQ_RING <= i) {      // the slot's previous task (i - RING) is not consumed yet
             if (*vstop) { t.go = 0; break; }
             __nanosleep(32);
         }
+#if PE_SEQ_PROFILE
+        const long long tc = clock64();
+        if (threadIdx.x == 32) { atomicAdd(&P.ctr->prof[12], (unsigned long long)(tb - ta)); atomicAdd(&P.ctr->prof[13], (unsigned long long)(tc - tb)); }
+#endif
         if (*vstop) t.go = 0;
         if (t.go) {
             const bool valid = (meta.w & PE_SR_K1) && c0 != PE_PREF_NONE;
@@ -747,12 +793,11 @@ __device__ __forceinline__ ProdTask stage_issue(const SeqParams &P, SeqShared &S
             t.copy = has_copy ? 1u : 0u;
         }
     }
-    t.go = __shfl_sync(0xFFFFFFFFu, t.go, 0);
-    t.n_list = __shfl_sync(0xFFFFFFFFu, t.n_list, 0);
-    t.base = __shfl_sync(0xFFFFFFFFu, t.base, 0);
-    t.n_listed = __shfl_sync(0xFFFFFFFFu, t.n_listed, 0);
+    // lane 0 -> warp: (go, copy, n_list <= 256, base < 1024, n_listed <= 1024) in one word, the row in another
+    uint32_t pk = t.go | (t.copy << 1) | (t.n_list << 2) | (t.base << 11) | (t.n_listed << 21);
+    pk = __shfl_sync(0xFFFFFFFFu, pk, 0);
     t.row = __shfl_sync(0xFFFFFFFFu, t.row, 0);
-    t.copy = __shfl_sync(0xFFFFFFFFu, t.copy, 0);
+    t.go = pk & 1u; t.copy = (pk >> 1) & 1u; t.n_list = (pk >> 2) & 0x1FFu; t.base = (pk >> 11) & 0x3FFu; t.n_listed = pk >> 21;
     return t;
 }
 
@@ -768,7 +813,13 @@ __device__ __forceinline__ bool stage_finish(const SeqParams &P, SeqShared &S, u
         __syncwarp();
         return true;
     };
+#if PE_SEQ_PROFILE
+    const long long td = clock64();
+#endif
     if (t.copy && !wait_copy()) return false;
+#if PE_SEQ_PROFILE
+    const long long te = clock64();
+#endif
     if (t.n_list) {
         const uint32_t lane_lt = (1u << lane) - 1u;
         uint32_t found = 0, first_at = 0;
@@ -822,11 +873,15 @@ __device__ __forceinline__ bool stage_finish(const SeqParams &P, SeqShared &S, u
             S.quick[slot] = (fl & PE_FT_PLAIN) == PE_FT_PLAIN ? min(found, (uint32_t)PE_SEQ_NCAND) : PE_NONE;
             S.ft[slot].n_cand = min(found, (uint32_t)PE_SEQ_NCAND);
             S.ft[slot].n_list = t.base + t.n_list;     // list members known to the pipeline (all touched, or candidates)
+            S.ft[slot].tie_start = t.n_list;           // list mode (tie_start == 0): the field carries the staged count
             S.ft[slot].last = buf[t.n_list - 1u];
         }
     }
     __syncwarp();
-    if (lane == 0) sq_mbar_arrive(&S.full_bar[slot]);   // release: descriptor, candidates and the copied words are visible
+    if (lane == 0) st_release_smem(&S.ready[slot], i + 1u);   // release: descriptor, candidates and the copied words are visible
+#if PE_SEQ_PROFILE
+    if (threadIdx.x == 32) { atomicAdd(&P.ctr->prof[14], (unsigned long long)(te - td)); atomicAdd(&P.ctr->prof[15], (unsigned long long)(clock64() - te)); }
+#endif
     return true;
 }
 
@@ -845,24 +900,51 @@ __device__ __forceinline__ void fast_producer(const SeqParams &P, SeqShared &S, 
     auto load_scan = [&](uint32_t i, ProdDesc &d) {
         if (lane == 0 && i < total) { d.c0 = P.scan[d.row].c0; d.meta = *reinterpret_cast<const uint4 *>(&P.scan[d.row].n0); }
     };
-    ProdDesc dA{}, dB{}, dC{};
-    load_row(pw, dA); load_row(pw + PE_SEQ_NPW, dB); load_row(pw + 2u * PE_SEQ_NPW, dC);
-    load_scan(pw, dA); load_scan(pw + PE_SEQ_NPW, dB);
-    ProdTask cur = stage_issue(P, S, ring, rowcur, start, pw, lane, dA);
-    if (!cur.go) return;
-    for (uint32_t i = pw;; i += PE_SEQ_NPW) {
-        const uint32_t nxt = i + PE_SEQ_NPW;
-        ProdTask nx; nx.go = 0; nx.n_list = 0; nx.base = 0; nx.n_listed = 0; nx.row = 0; nx.copy = 0;
-        if (nxt < total) {
-            load_scan(nxt + PE_SEQ_NPW, dC);
-            ProdDesc dN{};
-            load_row(nxt + 2u * PE_SEQ_NPW, dN);
-            nx = stage_issue(P, S, ring, rowcur, start, nxt, lane, dB);   // the next copy flies while this task's list is walked
-            dB = dC; dC = dN;
+    // software pipeline over this warp's tasks t_m = pw + m * NPW.  In iteration m: the row of t_{m+DEPTH+1} is
+    // requested, then the row record of t_{m+DEPTH} (its row arrived an iteration ago), then the copy of
+    // t_{m+DEPTH-1} is started (its record arrived an iteration ago), then t_m is walked and handed over --
+    // no global load is waited for in the iteration that issued it.
+    ProdDesc dI{}, dS{};
+    ProdTask pt[PE_SEQ_DEPTH];
+    {
+        ProdDesc d[PE_SEQ_DEPTH + 1];
+#pragma unroll
+        for (int k = 0; k <= PE_SEQ_DEPTH; k++) { d[k] = ProdDesc{}; load_row(pw + (uint32_t)k * PE_SEQ_NPW, d[k]); }
+#pragma unroll
+        for (int k = 0; k < PE_SEQ_DEPTH; k++) load_scan(pw + (uint32_t)k * PE_SEQ_NPW, d[k]);
+#pragma unroll
+        for (int k = 0; k < PE_SEQ_DEPTH - 1; k++) {
+            pt[k].go = 0; pt[k].n_list = 0; pt[k].base = 0; pt[k].n_listed = 0; pt[k].row = 0; pt[k].copy = 0;
+            const uint32_t ti = pw + (uint32_t)k * PE_SEQ_NPW;
+            if (ti < total && (k == 0 || pt[k - 1].go)) pt[k] = stage_issue(P, S, ring, rowcur, start, ti, lane, d[k]);
         }
-        if (!stage_finish(P, S, ring, rowcur, touched, i, lane, cur)) return;
-        if (nxt >= total || !nx.go) return;     // (stage_issue starts no copy when it returns go == 0)
-        cur = nx;
+        dI = d[PE_SEQ_DEPTH - 1];   // row + record
+        dS = d[PE_SEQ_DEPTH];       // row only
+    }
+    for (uint32_t i = pw;; i += PE_SEQ_NPW) {
+        if (!pt[0].go) return;                       // (stage_issue starts no copy when it returns go == 0)
+        const uint32_t ahead = i + (uint32_t)(PE_SEQ_DEPTH - 1) * PE_SEQ_NPW;
+        ProdDesc dR{};
+        load_row(ahead + 2u * PE_SEQ_NPW, dR);
+        load_scan(ahead + PE_SEQ_NPW, dS);
+        ProdTask nx; nx.go = 0; nx.n_list = 0; nx.base = 0; nx.n_listed = 0; nx.row = 0; nx.copy = 0;
+        if (ahead < total && pt[PE_SEQ_DEPTH - 2].go)
+            nx = stage_issue(P, S, ring, rowcur, start, ahead, lane, dI);   // this copy flies while earlier lists are walked
+        pt[PE_SEQ_DEPTH - 1] = nx;
+        const bool ok = stage_finish(P, S, ring, rowcur, touched, i, lane, pt[0]);
+        if (!ok) {
+            // leaving: whatever was issued must land first
+#pragma unroll
+            for (int k = 1; k < PE_SEQ_DEPTH; k++) {
+                const uint32_t slot = (i + (uint32_t)k * PE_SEQ_NPW) % PE_SEQ_RING;
+                if (pt[k].go && pt[k].copy) sq_mbar_wait_wd(&S.tma_bar[slot], S.tma_ph[slot], P.ctr, PE_DEV_ERR_WD_DRAIN);
+            }
+            return;
+        }
+        if (i + PE_SEQ_NPW >= total) return;
+#pragma unroll
+        for (int k = 0; k < PE_SEQ_DEPTH - 1; k++) pt[k] = pt[k + 1];
+        dI = dS; dS = dR;
     }
 }
 
@@ -913,8 +995,8 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
             { const long long t1 = clock64(); cyc_generic += t1 - t_mark; t_mark = t1; }
             if (tid == 0) {
                 for (int r = 0; r < PE_SEQ_RING; r++) {
-                    if (S.bars_live) { sq_mbar_inval(&S.full_bar[r]); sq_mbar_inval(&S.tma_bar[r]); }
-                    sq_mbar_init(&S.full_bar[r], 1);
+                    if (S.bars_live) sq_mbar_inval(&S.tma_bar[r]);
+                    S.ready[r] = 0;
                     sq_mbar_init(&S.tma_bar[r], 1);
                     S.tma_ph[r] = 0;
                 }
@@ -1414,7 +1496,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
         P.ctr->cyc_generic += (unsigned long long)cyc_generic;
         P.ctr->cyc_cons_wait += (unsigned long long)dbg.cyc_wait; P.ctr->cyc_cons_work += (unsigned long long)dbg.cyc_work; P.ctr->iters += dbg.iters;
         for (int r = 0; r < 5; r++) P.ctr->stops[r] += dbg.stops[r];
-        for (int r = 0; r < 16; r++) P.ctr->prof[r] += dbg.prof[r];
+        for (int r = 0; r < 12; r++) P.ctr->prof[r] += dbg.prof[r];   // 12..15: producer warp 1 (load wait, slot wait, copy wait, walk)
         P.ctr->slow_path += n_slow;
         P.ctr->placements += n_placed;
         P.ctr->evals_generic += n_evalg;
