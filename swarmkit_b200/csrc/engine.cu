@@ -89,6 +89,8 @@ struct pe_engine {
     void *cls_buf = nullptr; size_t cls_cap = 0;     // per-run arrays
     void *rows_buf = nullptr; size_t rows_cap = 0;   // per-batch arrays
     uint32_t *Sbuf = nullptr; size_t S_words = 0;    // signature bitmaps
+    void *chunk_buf = nullptr; size_t chunk_cap = 0; // per-chunk partial results of the scan (p1 | Cc | Lc)
+    uint32_t n_chunks = 1, local_chunks = 1;         // node-axis chunks of the scan (all ranks) / owned by this rank
     uint32_t *d_cls_counters = nullptr;              // [0] signatures [1] classes [2] rows of the current batch
     DevCounters *d_ctr = nullptr;
     void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
@@ -118,8 +120,10 @@ struct pe_engine {
         CU(cudaMalloc(&d_cls_counters, 16));
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
         CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(12288)));
-        CU(cudaFuncSetAttribute(k_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CU(cudaFuncSetAttribute(k_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CU(cudaFuncSetAttribute(k_scan<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         int32_t rc = ensure_cap(cfg->node_capacity ? cfg->node_capacity : 1);
         if (rc) return rc;
         // the five fixed attribute columns always exist
@@ -138,7 +142,7 @@ struct pe_engine {
         for (auto p : gen) fr(p);
         for (auto p : d_tab) fr(p);
         fr(tick_buf); fr(d_out_node); fr(d_out_fail); fr(ff8); fr(pref64); fr(cand_g); fr(st_cpu_g); fr(st_mem_g); fr(st_gen_g);
-        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters);
+        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters); fr(chunk_buf);
         for (auto &p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         if (stream) cudaStreamDestroy(stream);
     }
@@ -563,9 +567,16 @@ struct pe_engine {
         P.K = K;
         P.n_nodes = n_nodes;
         P.svc = reinterpret_cast<uint32_t *const *>(d_tab[2]);
-        P.out = scan_out; P.E = E; P.e_stride = e_stride(); P.L = Lbuf;
         P.S = Sbuf; P.s_stride = e_stride();
         P.ctr = d_ctr;
+        // node-axis chunks: enough (row, chunk) warps to fill the machine when descriptors repeat (few rows per batch);
+        // every chunk starts on a 32-word boundary of the class bitmaps
+        const uint32_t steps = TN / 32u;
+        const uint32_t gran = steps >= 32u ? 1u : 32u / steps;
+        n_chunks = local_chunks = std::min<uint32_t>(4u, std::max<uint32_t>(1u, P.n_tiles / gran));
+        P.tiles_per_chunk = round_up((P.n_tiles + n_chunks - 1) / n_chunks, gran);
+        P.n_chunks = n_chunks; P.chunk0 = 0;
+        P.Eout = E; P.e_row_stride = e_stride(); P.e_word_off = 0;
         return true;
     }
 
@@ -585,6 +596,17 @@ struct pe_engine {
         dcls = ht_static + ht; scls = dcls + n; srow = scls + n; static_reps = srow + n; mark = static_reps + n; rowof = mark + n;
         if ((rc = ensure_buf(rows_buf, rows_cap, (size_t)3 * Bmax * 4 + 64))) return rc;
         row_group = reinterpret_cast<uint32_t *>(rows_buf); row_srow = row_group + Bmax; task_row = row_srow + Bmax;
+        // per-chunk partial results: p1 [chunks][Bmax] 16 B | Cc [chunks][Bmax][2] | Lc [chunks][Bmax][2][PE_LIST_CAP]
+        const size_t p1_bytes = (size_t)n_chunks * Bmax * 16, cc_bytes = (size_t)n_chunks * Bmax * 8,
+                     lc_bytes = (size_t)n_chunks * Bmax * 2 * PE_LIST_CAP * 4;
+        if ((rc = ensure_buf(chunk_buf, chunk_cap, p1_bytes + cc_bytes + lc_bytes + 64))) return rc;
+        SP.p1 = reinterpret_cast<ulonglong2 *>(chunk_buf);
+        SP.Cc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1_bytes);
+        SP.Lc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1_bytes + cc_bytes);
+        SP.rows_cap = Bmax;
+        MergeParams MP;
+        MP.K = K; MP.svc = SP.svc; MP.n_chunks = n_chunks; MP.rows_cap = Bmax; MP.p1 = SP.p1; MP.Lc = SP.Lc; MP.Cc = SP.Cc;
+        MP.out = scan_out; MP.L = Lbuf; MP.Eall = nullptr; MP.E = E; MP.n_ranks = 1; MP.seg_words = 0; MP.e_stride = e_stride();
 
         EvPair *evp = ev_begin(5);
         CU(cudaMemsetAsync(ht_full, 0xFF, (size_t)2 * ht * 4, stream));
@@ -635,14 +657,20 @@ struct pe_engine {
             if (!cached) launch_static(row_group, d_cls_counters + 2, B);
             ev_end(evr);
             SP.row_group = row_group; SP.row_srow = row_srow; SP.n_rows = d_cls_counters + 2;
-            const uint32_t grid = std::max((B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS, std::min(B, (uint32_t)num_sms * 2u));
+            // grid.x: enough CTAs that rows-per-CTA adapts to the row count (k_scan reads it from the device)
+            SP.target_ctas = (uint32_t)num_sms * 2u;
+            const dim3 grid(std::max((B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS, std::min(B, SP.target_ctas)), local_chunks);
             const size_t dyn = 2 * (size_t)SP.stage_bytes;
+            MP.row_group = row_group; MP.n_rows = d_cls_counters + 2;
             EvPair *ev = ev_begin(0);
-            if (use_dyn) k_scan<true><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
-            else k_scan<false><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            if (use_dyn) k_scan<true, 1><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            else k_scan<false, 1><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            if (use_dyn) k_scan<true, 2><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            else k_scan<false, 2><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            k_merge<<<(B + 7) / 8, 256, 0, stream>>>(MP);
             ev_end(ev);
             CU(cudaGetLastError());
-            stats.kernel_launches++; stats.scan_launches++;
+            stats.kernel_launches += 3; stats.scan_launches++;
             stats.pairs += (uint64_t)B * n_nodes;
             if ((rc = launch_sequencer(b0, b0 + B, true))) return rc;
         }

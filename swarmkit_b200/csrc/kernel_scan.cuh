@@ -54,11 +54,31 @@ struct ScanParams {
     uint32_t *const *svc;        // per-service counter columns (read straight from L2)
     const uint32_t *S;           // signature bitmaps
     uint32_t s_stride;
-    ScanResult *out;             // [row]
-    uint32_t *E;                 // class bitmaps [row][2][e_stride]
-    uint32_t e_stride;
-    uint32_t *L;                 // member lists  [row][2][PE_LIST_CAP]
+    // The node axis is cut into n_chunks chunks of tiles_per_chunk tiles; one warp owns one (row, chunk).
+    // blockIdx.y = local chunk; this rank owns chunks [chunk0, chunk0 + gridDim.y).  (Multi-GPU: the other
+    // chunks' partial results arrive by all-gather; single GPU: chunk0 = 0 and gridDim.y = n_chunks.)
+    uint32_t n_chunks, chunk0, tiles_per_chunk, rows_cap;
+    uint32_t target_ctas;        // CTAs the launch should end up using (2 per SM)
+    ulonglong2 *p1;              // [n_chunks][rows_cap] two smallest prefixes of the chunk (sweep 1)
+    uint32_t *Lc;                // [n_chunks][rows_cap][2][PE_LIST_CAP] first members of each class inside the chunk
+    uint32_t *Cc;                // [n_chunks][rows_cap][2] members of each class inside the chunk
+    uint32_t *Eout;              // class bitmaps: word w of (row, cls) at Eout[(row * 2 + cls) * e_row_stride + w - e_word_off]
+    uint32_t e_row_stride, e_word_off;
     DevCounters *ctr;
+};
+
+// what k_merge needs to finish the rows
+struct MergeParams {
+    TickDev K;
+    const uint32_t *row_group, *n_rows;
+    uint32_t *const *svc;
+    uint32_t n_chunks, rows_cap;
+    const ulonglong2 *p1;
+    const uint32_t *Lc, *Cc;
+    ScanResult *out;             // [row]
+    uint32_t *L;                 // member lists [row][2][PE_LIST_CAP]
+    // multi-GPU: gathered bitmap segments [rank][rows_cap][2][seg_words] -> canonical rows [row][2][e_stride]
+    const uint32_t *Eall; uint32_t *E; uint32_t n_ranks, seg_words, e_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,9 +107,33 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  : "memory");
 }
 
+__device__ __forceinline__ void wmin64(uint32_t &h, uint32_t &l) {   // warp minimum of (h:l)
+    const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, h);
+    l = __reduce_min_sync(0xFFFFFFFFu, h == mh ? l : 0xFFFFFFFFu);
+    h = mh;
+}
+// The two smallest distinct prefixes of a row over all chunks, from the per-chunk pairs (n_chunks <= 32).
+__device__ __forceinline__ void merge_p1(const ulonglong2 *p1, uint32_t n_chunks, uint32_t rows_cap, uint32_t row, uint32_t lane,
+                                         unsigned long long &c0, unsigned long long &c1) {
+    ulonglong2 v = make_ulonglong2(~0ull, ~0ull);
+    if (lane < n_chunks) v = p1[(size_t)lane * rows_cap + row];
+    uint32_t h = (uint32_t)(v.x >> 32), l = (uint32_t)v.x;
+    wmin64(h, l);
+    c0 = ((unsigned long long)h << 32) | l;
+    // second: the smallest value above c0 among every chunk's first and second
+    uint32_t ah = (v.x != c0) ? (uint32_t)(v.x >> 32) : 0xFFFFFFFFu, al = (v.x != c0) ? (uint32_t)v.x : 0xFFFFFFFFu;
+    wmin64(ah, al);
+    uint32_t bh = (uint32_t)(v.y >> 32), bl = (uint32_t)v.y;
+    wmin64(bh, bl);
+    const unsigned long long a = ((unsigned long long)ah << 32) | al, b = ((unsigned long long)bh << 32) | bl;
+    c1 = a < b ? a : b;
+}
+
 // DYN = some row of the run uses a state-dependent filter (resources, host
 // ports, max replicas) or carries recent-failure counts.
-template <bool DYN>
+// PASS 1: the two smallest rank prefixes of (row, chunk).  PASS 2: given the row's two smallest prefixes
+// over ALL chunks, the chunk's part of the two class bitmaps and its first PE_LIST_CAP members of each.
+template <bool DYN, int PASS>
 __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_constant__ ScanParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -99,9 +143,12 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
     const uint32_t TN = P.tile_nodes, N = P.n_nodes;
     // rows per CTA: spread a small batch over every SM instead of filling a few CTAs
     const uint32_t n_rows = *P.n_rows;
-    uint32_t rpc = (n_rows + gridDim.x - 1u) / gridDim.x;
+    uint32_t rpc = (n_rows * gridDim.y + P.target_ctas - 1u) / P.target_ctas;   // (row, chunk) warps over ~2 CTAs per SM
     rpc = rpc < 1u ? 1u : (rpc > PE_SCAN_WARPS ? PE_SCAN_WARPS : rpc);
     if (blockIdx.x * rpc >= n_rows) return;
+    const uint32_t chunk = P.chunk0 + blockIdx.y;
+    const uint32_t t_begin = chunk * P.tiles_per_chunk;
+    const uint32_t t_end = min(t_begin + P.tiles_per_chunk, P.n_tiles);
     unsigned char *stage0 = smem, *stage1 = smem + P.stage_bytes;
 
     if (tid == 0) {
@@ -127,7 +174,7 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
             tma_bulk_g2s(stage + col.smem_off, (const unsigned char *)col.base + (size_t)tile * bytes, bytes, bar);
         }
     };
-    if (tid == 0) issue_tile(0, stage0, &full_bar[0]);
+    if (tid == 0 && t_begin < t_end) issue_tile(t_begin, stage0, &full_bar[0]);
 
     // ---- warp-uniform row state
     const uint32_t fm = active ? G.filter_mask : 0u;
@@ -140,29 +187,30 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
     const uint32_t steps = TN >> 5;
     const uint32_t lane_lt = (1u << lane) - 1u;
 
-    // sweep 1: the two smallest distinct rank prefixes (hi:lo), warp-uniform
+    // the two smallest distinct rank prefixes (hi:lo), warp-uniform: PASS 1 finds the chunk's, PASS 2 is given the row's
     uint32_t m1h = 0xFFFFFFFFu, m1l = 0xFFFFFFFFu, m2h = 0xFFFFFFFFu, m2l = 0xFFFFFFFFu;
-    // sweep 2: member counts, this lane's word of each class bitmap for the current 32-step block
+    if (PASS == 2 && active) {
+        unsigned long long c0, c1;
+        merge_p1(P.p1, P.n_chunks, P.rows_cap, row, lane, c0, c1);
+        m1h = (uint32_t)(c0 >> 32); m1l = (uint32_t)c0; m2h = (uint32_t)(c1 >> 32); m2l = (uint32_t)c1;
+    }
+    // PASS 2: member counts, this lane's word of each class bitmap for the current 32-step block
     uint32_t cnt1 = 0, cnt2 = 0, my1 = 0, my2 = 0;
     uint32_t swl = 0;   // this lane's word of the signature bitmap for the current 32-step block
-    uint32_t *Lrows = P.L + (size_t)row * 2u * PE_LIST_CAP;
-    uint32_t *Erows = P.E + (size_t)row * 2u * P.e_stride;
+    uint32_t *Lrows = P.Lc + ((size_t)chunk * P.rows_cap + row) * 2u * PE_LIST_CAP;
+    uint32_t *Erows = P.Eout + (size_t)row * 2u * P.e_row_stride - P.e_word_off;
+    const bool have = !(m1h == 0xFFFFFFFFu && m1l == 0xFFFFFFFFu);   // PASS 2: a row without a feasible node has nothing to list
 
-    const uint32_t total_tiles = 2u * P.n_tiles;
-    for (uint32_t q = 0; q < total_tiles; q++) {
-        const uint32_t cur = q & 1u;
-        const bool second = q >= P.n_tiles;
-        const uint32_t tile = second ? q - P.n_tiles : q;
+    for (uint32_t tile = t_begin; tile < t_end; tile++) {
+        const uint32_t q = tile - t_begin, cur = q & 1u;
         unsigned char *stage = cur ? stage1 : stage0;
-        if (tid == 0 && q + 1 < total_tiles) {
+        if (tid == 0 && tile + 1 < t_end) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t nq = q + 1u;
-            issue_tile(nq >= P.n_tiles ? nq - P.n_tiles : nq, cur ? stage0 : stage1, &full_bar[cur ^ 1u]);
+            issue_tile(tile + 1, cur ? stage0 : stage1, &full_bar[cur ^ 1u]);
         }
         mbar_wait(&full_bar[cur], (q >> 1) & 1u);
 
-        // a row without a feasible node has nothing to list
-        if (active && !(second && m1h == 0xFFFFFFFFu && m1l == 0xFFFFFFFFu)) {
+        if (active && (PASS == 1 || have)) {
             const uint32_t tile_base = tile * TN;
             const uint32_t *svcp = svccol + tile_base + lane;
             for (uint32_t sb = 0; sb < steps; sb += 8) {
@@ -172,7 +220,7 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
 #pragma unroll
                 for (int u = 0; u < 8; u++) svcv[u] = svcp[(sb + u) * 32u];
                 const uint32_t wb = tile * steps + sb;           // bitmap word of step sb
-                if ((wb & 31u) == 0u) swl = Srow[wb + lane];     // (8 divides 32: a block never straddles)
+                if ((wb & 31u) == 0u || (tile == t_begin && sb == 0u)) swl = Srow[(wb & ~31u) + lane];   // (8 divides 32: a block never straddles)
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     const uint32_t s = sb + u;
@@ -211,7 +259,7 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
                     }
                     // rank prefix of nodeLess (scheduler.go:708-735): hi = (f5 << 24) | svc, lo = total; all ones = infeasible
                     const uint32_t kh = ok ? hi : 0xFFFFFFFFu, kl = ok ? lo : 0xFFFFFFFFu;
-                    if (!second) {
+                    if (PASS == 1) {
                         const bool below2 = (kh < m2h) | ((kh == m2h) & (kl < m2l));
                         const bool ne1 = (kh != m1h) | (kl != m1l);
                         if (__any_sync(0xFFFFFFFFu, below2 & ne1)) {
@@ -248,7 +296,8 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
                         if (lane == (widx & 31u)) { my1 = word1; my2 = word2; }
                         if ((widx & 31u) == 31u) {
                             Erows[(widx & ~31u) + lane] = my1;
-                            Erows[P.e_stride + (widx & ~31u) + lane] = my2;
+                            Erows[P.e_row_stride + (widx & ~31u) + lane] = my2;
+                            my1 = 0; my2 = 0;
                         }
                     }
                 }
@@ -257,33 +306,80 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
         __syncthreads();   // everyone is done with this stage before it is refilled
     }
     if (active) {
-        const bool have = !(m1h == 0xFFFFFFFFu && m1l == 0xFFFFFFFFu);
-        const uint32_t W = P.n_tiles * steps;
-        if (have && (W & 31u) && lane < (W & 31u)) {   // the last, partial 32-word block
-            Erows[(W & ~31u) + lane] = my1;
-            Erows[P.e_stride + (W & ~31u) + lane] = my2;
+        if (PASS == 1) {
+            if (lane == 0) {
+                P.p1[(size_t)chunk * P.rows_cap + row] =
+                    make_ulonglong2(((unsigned long long)m1h << 32) | m1l, ((unsigned long long)m2h << 32) | m2l);   // all ones = none
+                // algorithmic bytes of this (row, chunk): signature bit + total + service count [+ cpu/mem, generic cells, port words]
+                const unsigned long long nn = t_begin < t_end ? (unsigned long long)(min(t_end * TN, N) - min(t_begin * TN, N)) : 0ull;
+                unsigned long long per = 8ull;
+                if ((fm >> PE_F_RESOURCE) & 1u) per += 16ull + 8ull * G.gen_cnt;
+                if ((fm >> PE_F_HOSTPORT) & 1u) per += 4ull * G.port_cnt;
+                atomicAdd(&P.ctr->scan_evals, nn);
+                atomicAdd(&P.ctr->scan_bytes, nn * per + nn / 8u);
+                if (blockIdx.y == 0) atomicAdd(&P.ctr->scan_rows, 1ull);
+            }
+        } else {
+            const uint32_t W = t_end * steps;      // chunks start on 32-word boundaries; only the last one can end inside a block
+            if (have && t_begin < t_end && (W & 31u) && lane < (W & 31u)) {
+                Erows[(W & ~31u) + lane] = my1;
+                Erows[P.e_row_stride + (W & ~31u) + lane] = my2;
+            }
+            if (lane == 0) {
+                uint32_t *cc = P.Cc + ((size_t)chunk * P.rows_cap + row) * 2u;
+                cc[0] = cnt1; cc[1] = cnt2;
+            }
         }
-        if (lane == 0) {
-            ScanResult r;
-            r.c0 = ((unsigned long long)m1h << 32) | m1l;   // all ones = PE_PREF_NONE
-            r.c1 = ((unsigned long long)m2h << 32) | m2l;
-            r.n0 = cnt1; r.n1 = cnt2;
-            r.tie_start = G.tie_start;
-            r.flags = ((G.gen_cnt == 0 && G.port_cnt == 0) ? PE_SR_SIMPLE : 0u) | (G.n_tasks == 1 ? PE_SR_K1 : 0u) |
-                      ((G.n_tasks >= 1 && (P.K.task_flags[G.task_off] & PE_T_COUNTS)) ? PE_SR_COUNTS : 0u) |
-                      ((!(fm & ((1u << PE_F_RESOURCE) | (1u << PE_F_HOSTPORT) | (1u << PE_F_MAXREPLICAS))) && G.fail_cnt == 0) ? PE_SR_STATIC_ONLY : 0u);
-            r.cpu_res = G.cpu_res; r.mem_res = G.mem_res;
-            r.svccol = const_cast<uint32_t *>(svccol);
-            r.pad = 0;
-            P.out[row] = r;
-            // algorithmic bytes of this row: signature bit + total + service count [+ cpu/mem, generic cells, port words]
-            unsigned long long per = 8ull;
-            if ((fm >> PE_F_RESOURCE) & 1u) per += 16ull + 8ull * G.gen_cnt;
-            if ((fm >> PE_F_HOSTPORT) & 1u) per += 4ull * G.port_cnt;
-            atomicAdd(&P.ctr->scan_evals, (unsigned long long)N);
-            atomicAdd(&P.ctr->scan_bytes, (unsigned long long)N * per + N / 8u);
-            atomicAdd(&P.ctr->scan_rows, 1ull);
+    }
+}
+
+// One warp per row: the row record and the member lists from the chunks' parts (chunks are in node order, so
+// concatenating their lists keeps node order).
+__global__ void __launch_bounds__(256) k_merge(const MergeParams P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t n_rows = *P.n_rows;
+    if (row >= n_rows) return;
+    unsigned long long c0, c1;
+    merge_p1(P.p1, P.n_chunks, P.rows_cap, row, lane, c0, c1);
+    uint32_t tot[2] = {0, 0};
+    for (uint32_t cls = 0; cls < 2u; cls++) {
+        uint32_t pos = 0;
+        uint32_t *dst = P.L + ((size_t)row * 2u + cls) * PE_LIST_CAP;
+        for (uint32_t g = 0; g < P.n_chunks; g++) {
+            const uint32_t n = P.Cc[((size_t)g * P.rows_cap + row) * 2u + cls];
+            tot[cls] += n;
+            const uint32_t take = min(min(n, (uint32_t)PE_LIST_CAP), (uint32_t)PE_LIST_CAP - pos);
+            const uint32_t *src = P.Lc + (((size_t)g * P.rows_cap + row) * 2u + cls) * PE_LIST_CAP;
+            for (uint32_t j = lane; j < take; j += 32u) dst[pos + j] = src[j];
+            pos += take;
         }
+    }
+    if (P.Eall != nullptr) {
+        // gathered bitmap segments -> canonical rows
+        for (uint32_t cls = 0; cls < 2u; cls++) {
+            uint32_t *dst = P.E + ((size_t)row * 2u + cls) * P.e_stride;
+            for (uint32_t r = 0; r < P.n_ranks; r++) {
+                const uint32_t *src = P.Eall + (((size_t)r * P.rows_cap + row) * 2u + cls) * P.seg_words;
+                for (uint32_t j = lane; j < P.seg_words && r * P.seg_words + j < P.e_stride; j += 32u) dst[r * P.seg_words + j] = src[j];
+            }
+        }
+    }
+    if (lane == 0) {
+        const pe_group G = P.K.groups[P.row_group[row]];
+        const uint32_t fm = G.filter_mask;
+        ScanResult r;
+        r.c0 = c0; r.c1 = c1;
+        r.n0 = c0 == PE_PREF_NONE ? 0u : tot[0];
+        r.n1 = (c0 == PE_PREF_NONE || c1 == PE_PREF_NONE) ? 0u : tot[1];
+        r.tie_start = G.tie_start;
+        r.flags = ((G.gen_cnt == 0 && G.port_cnt == 0) ? PE_SR_SIMPLE : 0u) | (G.n_tasks == 1 ? PE_SR_K1 : 0u) |
+                  ((G.n_tasks >= 1 && (P.K.task_flags[G.task_off] & PE_T_COUNTS)) ? PE_SR_COUNTS : 0u) |
+                  ((!(fm & ((1u << PE_F_RESOURCE) | (1u << PE_F_HOSTPORT) | (1u << PE_F_MAXREPLICAS))) && G.fail_cnt == 0) ? PE_SR_STATIC_ONLY : 0u);
+        r.cpu_res = G.cpu_res; r.mem_res = G.mem_res;
+        r.svccol = P.svc[G.svc_id];
+        r.pad = 0;
+        P.out[row] = r;
     }
 }
 
