@@ -221,6 +221,11 @@ typedef struct pe_stats {
 
 /* ---- lifecycle ----------------------------------------------------------- */
 int32_t pe_create(const pe_config *cfg, pe_engine **out);
+/* Node sharding: rank 0 obtains a 128-byte ncclUniqueId here, the host ships it to the other
+ * ranks (the Go shim would use its own RPC; bench.py uses torch.distributed), and every rank passes it in
+ * pe_config.nccl_unique_id.  All ranks mirror ALL nodes and submit the SAME ticks; each rank scans its slice
+ * of the node axis, partial results are all-gathered, placements come out identical on every rank. */
+int32_t pe_nccl_unique_id(void *out128);
 void pe_destroy(pe_engine *h);
 const char *pe_last_error(const pe_engine *h); /* h may be NULL: last create error */
 uint32_t pe_abi_version(void);

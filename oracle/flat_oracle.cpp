@@ -560,6 +560,7 @@ int32_t ope_snapshot_ports(pe_engine *h, uint32_t slot, uint32_t first, uint32_t
     return PE_OK;
 }
 
+int32_t ope_nccl_unique_id(void *) { return PE_ERR_UNSUPPORTED; }   // the oracle is one process, one table
 int32_t ope_get_stats(pe_engine *h, pe_stats *out) { *out = h->o.stats; return PE_OK; }
 int32_t ope_stats_reset(pe_engine *h) { h->o.stats = pe_stats{}; return PE_OK; }
 

@@ -24,6 +24,7 @@
 #define pe_get_stats ope_get_stats
 #define pe_stats_reset ope_stats_reset
 #define pe_fold_value ope_fold_value
+#define pe_nccl_unique_id ope_nccl_unique_id
 #define ss_create sso_create
 #define ss_destroy sso_destroy
 #define ss_apply sso_apply

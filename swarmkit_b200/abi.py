@@ -108,6 +108,7 @@ ABI_SYMBOLS = [
     "abi_version", "create", "destroy", "last_error", "node_upsert", "node_remove", "set_node_count",
     "node_task_delta", "schedule", "tick_upload", "tick_run", "tick_download", "fit", "snapshot",
     "snapshot_service", "snapshot_generic", "snapshot_ports", "get_stats", "stats_reset", "fold_value",
+    "nccl_unique_id",
 ]
 
 
@@ -184,7 +185,7 @@ class FlatABI:
     """Binds one implementation of the placement ABI (symbol prefix + library)."""
 
     def __init__(self, lib_path: str, prefix: str, node_capacity: int = 0, device: int = -1, flags: int = 0,
-                 max_batch: int = 0):
+                 max_batch: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id: bytes | None = None):
         self.lib = C.CDLL(lib_path)
         self.prefix = prefix
         self.f = {}
@@ -214,9 +215,16 @@ class FlatABI:
         self.f["get_stats"].argtypes = [C.c_void_p, C.POINTER(pe_stats)]
         self.f["stats_reset"].argtypes = [C.c_void_p]
         self.f["fold_value"].argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
+        self.f["nccl_unique_id"].argtypes = [C.c_void_p]
         if self.f["abi_version"]() != PE_ABI_VERSION:
             raise RuntimeError("ABI version mismatch")
-        cfg = pe_config(PE_ABI_VERSION, device, node_capacity, flags, max_batch, 0, 1, None)
+        self._nccl_id = None
+        if world_size > 1:
+            if nccl_unique_id is None or len(nccl_unique_id) != 128:
+                raise ValueError("world_size > 1 needs the 128-byte id from nccl_unique_id() of rank 0")
+            self._nccl_id = C.create_string_buffer(bytes(nccl_unique_id), 128)
+        cfg = pe_config(PE_ABI_VERSION, device, node_capacity, flags, max_batch, rank, world_size,
+                        C.cast(self._nccl_id, C.c_void_p) if self._nccl_id is not None else None)
         self.h = C.c_void_p()
         rc = self.f["create"](C.byref(cfg), C.byref(self.h))
         if rc != PE_OK:

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kernel_misc.cuh"
+#include "nccl_dl.h"
 #include "kernel_classify.cuh"
 #include "kernel_scan.cuh"
 #include "kernel_sequencer.cuh"
@@ -91,6 +92,11 @@ struct pe_engine {
     uint32_t *Sbuf = nullptr; size_t S_words = 0;    // signature bitmaps
     void *chunk_buf = nullptr; size_t chunk_cap = 0; // per-chunk partial results of the scan (p1 | Cc | Lc)
     uint32_t n_chunks = 1, local_chunks = 1;         // node-axis chunks of the scan (all ranks) / owned by this rank
+    // node sharding across ranks: every rank mirrors all nodes and runs the same sequencer; the scan of a
+    // batch is split by node range and the partial results are exchanged with NCCL all-gathers
+    int rank = 0, world = 1;
+    pe_nccl::ncclComm_t comm = nullptr;
+    uint32_t *Eall = nullptr; size_t Eall_words = 0; // [rank][rows][2][seg_words] gathered bitmap segments
     uint32_t *d_cls_counters = nullptr;              // [0] signatures [1] classes [2] rows of the current batch
     DevCounters *d_ctr = nullptr;
     void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
@@ -116,6 +122,17 @@ struct pe_engine {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         cfg_flags = cfg->flags;
         max_batch = cfg->max_batch;
+        if (cfg->world_size > 1) {
+            if (cfg->rank < 0 || cfg->rank >= cfg->world_size || !cfg->nccl_unique_id) { err = "bad rank / world_size / nccl_unique_id"; return PE_ERR_INVALID; }
+            if (cfg->world_size > 32) { err = "world_size > 32"; return PE_ERR_UNSUPPORTED; }
+            const pe_nccl::Api &nc = pe_nccl::api();
+            if (!nc.ok) { err = "world_size > 1 needs libnccl.so.2 in the process or on the loader path"; return PE_ERR_UNSUPPORTED; }
+            pe_nccl::ncclUniqueId id;
+            memcpy(&id, cfg->nccl_unique_id, sizeof id);
+            const pe_nccl::ncclResult_t r = nc.CommInitRank(&comm, cfg->world_size, id, cfg->rank);
+            if (r != 0) { err = std::string("ncclCommInitRank: ") + nc.GetErrorString(r); return PE_ERR_CUDA; }
+            rank = cfg->rank; world = cfg->world_size;
+        }
         CU(cudaMalloc(&d_ctr, sizeof(DevCounters)));
         CU(cudaMalloc(&d_cls_counters, 16));
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
@@ -133,7 +150,9 @@ struct pe_engine {
 
     void destroy() {
         if (stream) cudaStreamSynchronize(stream);
+        if (comm) { pe_nccl::api().CommDestroy(comm); comm = nullptr; }
         auto fr = [](void *p) { if (p) cudaFree(p); };
+        fr(Eall);
         fr(meta); fr(cpu); fr(mem); fr(total); fr(ip);
         for (auto p : attr) fr(p);
         for (auto p : svc) fr(p);
@@ -504,7 +523,7 @@ struct pe_engine {
 
     // device arrays of the current k == 1 run / batch (carved from cls_buf / rows_buf)
     uint32_t *ht_full = nullptr, *ht_static = nullptr, *dcls = nullptr, *scls = nullptr, *srow = nullptr, *static_reps = nullptr,
-             *mark = nullptr, *rowof = nullptr;
+             *mark = nullptr, *rowof = nullptr, *firstof = nullptr;
     uint32_t *row_group = nullptr, *row_srow = nullptr, *task_row = nullptr;
 
     int32_t launch_sequencer(uint32_t g0, uint32_t g1, bool with_scan) {
@@ -573,10 +592,16 @@ struct pe_engine {
         // every chunk starts on a 32-word boundary of the class bitmaps
         const uint32_t steps = TN / 32u;
         const uint32_t gran = steps >= 32u ? 1u : 32u / steps;
-        n_chunks = local_chunks = std::min<uint32_t>(4u, std::max<uint32_t>(1u, P.n_tiles / gran));
-        P.tiles_per_chunk = round_up((P.n_tiles + n_chunks - 1) / n_chunks, gran);
-        P.n_chunks = n_chunks; P.chunk0 = 0;
-        P.Eout = E; P.e_row_stride = e_stride(); P.e_word_off = 0;
+        if (world == 1) {
+            n_chunks = local_chunks = std::min<uint32_t>(4u, std::max<uint32_t>(1u, P.n_tiles / gran));
+        } else {
+            local_chunks = std::max<uint32_t>(1u, 4u / (uint32_t)world);
+            n_chunks = local_chunks * (uint32_t)world;
+            if (n_chunks > 32u) return false;
+        }
+        P.tiles_per_chunk = round_up(std::max<uint32_t>(1u, (P.n_tiles + n_chunks - 1) / n_chunks), gran);
+        P.n_chunks = n_chunks; P.chunk0 = (uint32_t)rank * local_chunks;
+        P.Eout = E; P.e_row_stride = e_stride(); P.e_word_off = 0;   // (multi-rank: set per batch in run_k1)
         return true;
     }
 
@@ -591,9 +616,9 @@ struct pe_engine {
         }
         uint32_t ht = 1024;
         while (ht < 2u * n) ht <<= 1;
-        if ((rc = ensure_buf(cls_buf, cls_cap, ((size_t)2 * ht + (size_t)6 * n) * 4 + 64))) return rc;
+        if ((rc = ensure_buf(cls_buf, cls_cap, ((size_t)2 * ht + (size_t)7 * n) * 4 + 64))) return rc;
         ht_full = reinterpret_cast<uint32_t *>(cls_buf); ht_static = ht_full + ht;
-        dcls = ht_static + ht; scls = dcls + n; srow = scls + n; static_reps = srow + n; mark = static_reps + n; rowof = mark + n;
+        dcls = ht_static + ht; scls = dcls + n; srow = scls + n; static_reps = srow + n; mark = static_reps + n; rowof = mark + n; firstof = rowof + n;
         if ((rc = ensure_buf(rows_buf, rows_cap, (size_t)3 * Bmax * 4 + 64))) return rc;
         row_group = reinterpret_cast<uint32_t *>(rows_buf); row_srow = row_group + Bmax; task_row = row_srow + Bmax;
         // per-chunk partial results: p1 [chunks][Bmax] 16 B | Cc [chunks][Bmax][2] | Lc [chunks][Bmax][2][PE_LIST_CAP]
@@ -607,6 +632,23 @@ struct pe_engine {
         MergeParams MP;
         MP.K = K; MP.svc = SP.svc; MP.n_chunks = n_chunks; MP.rows_cap = Bmax; MP.p1 = SP.p1; MP.Lc = SP.Lc; MP.Cc = SP.Cc;
         MP.out = scan_out; MP.L = Lbuf; MP.Eall = nullptr; MP.E = E; MP.n_ranks = 1; MP.seg_words = 0; MP.e_stride = e_stride();
+        // node sharding: this rank's words of the class bitmaps go to its segment of Eall, which is all-gathered
+        const uint32_t seg_words = local_chunks * SP.tiles_per_chunk * (SP.tile_nodes / 32u);
+        if (world > 1) {
+            const size_t need = (size_t)world * Bmax * 2 * seg_words;
+            if (need > Eall_words) {
+                void *p = Eall; size_t c = Eall_words * 4;
+                if ((rc = ensure_buf(p, c, need * 4))) return rc;
+                Eall = reinterpret_cast<uint32_t *>(p); Eall_words = c / 4;
+            }
+        }
+        auto gather = [&](void *base, size_t bytes_per_rank) -> int32_t {
+            const pe_nccl::Api &nc = pe_nccl::api();
+            const pe_nccl::ncclResult_t r = nc.AllGather(reinterpret_cast<char *>(base) + (size_t)rank * bytes_per_rank, base, bytes_per_rank,
+                                                         pe_nccl::ncclUint8, comm, stream);
+            if (r != 0) { err = std::string("ncclAllGather: ") + nc.GetErrorString(r); return PE_ERR_CUDA; }
+            return PE_OK;
+        };
 
         EvPair *evp = ev_begin(5);
         CU(cudaMemsetAsync(ht_full, 0xFF, (size_t)2 * ht * 4, stream));
@@ -649,7 +691,7 @@ struct pe_engine {
             const uint32_t B = std::min(Bmax, e - b0);
             EvPair *evr = ev_begin(5);
             RowsParams RP;
-            RP.dcls = dcls; RP.scls = scls; RP.srow = srow; RP.g0 = g; RP.b0 = b0; RP.B = B; RP.mark = mark; RP.rowof = rowof;
+            RP.dcls = dcls; RP.scls = scls; RP.srow = srow; RP.g0 = g; RP.b0 = b0; RP.B = B; RP.mark = mark; RP.rowof = rowof; RP.firstof = firstof;
             RP.stamp = ++stamp; RP.static_cached = cached ? 1u : 0u;
             RP.row_group = row_group; RP.row_srow = row_srow; RP.task_row = task_row; RP.n_rows = d_cls_counters + 2;
             k_rows<<<1, 1024, 0, stream>>>(RP);
@@ -662,11 +704,32 @@ struct pe_engine {
             const dim3 grid(std::max((B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS, std::min(B, SP.target_ctas)), local_chunks);
             const size_t dyn = 2 * (size_t)SP.stage_bytes;
             MP.row_group = row_group; MP.n_rows = d_cls_counters + 2;
+            uint32_t rcap = Bmax;
+            if (world > 1) {
+                // the exchanged arrays are strided by the row count of THIS batch (k_rows numbers rows identically on every rank)
+                uint32_t h_rows = 0;
+                CU(cudaMemcpyAsync(&h_rows, d_cls_counters + 2, 4, cudaMemcpyDeviceToHost, stream));
+                CU(cudaStreamSynchronize(stream));
+                rcap = std::max<uint32_t>(8u, round_up(h_rows, 8u));
+                const size_t p1b = (size_t)n_chunks * rcap * 16, ccb = (size_t)n_chunks * rcap * 8;
+                SP.Cc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1b);
+                SP.Lc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1b + ccb);
+                SP.rows_cap = rcap;
+                SP.Eout = Eall + (size_t)rank * rcap * 2 * seg_words; SP.e_row_stride = seg_words;
+                SP.e_word_off = SP.chunk0 * SP.tiles_per_chunk * (SP.tile_nodes / 32u);
+                MP.rows_cap = rcap; MP.Cc = SP.Cc; MP.Lc = SP.Lc; MP.Eall = Eall; MP.n_ranks = (uint32_t)world; MP.seg_words = seg_words;
+            }
             EvPair *ev = ev_begin(0);
             if (use_dyn) k_scan<true, 1><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
             else k_scan<false, 1><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            if (world > 1 && (rc = gather(SP.p1, (size_t)local_chunks * rcap * 16))) return rc;
             if (use_dyn) k_scan<true, 2><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
             else k_scan<false, 2><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
+            if (world > 1) {
+                if ((rc = gather(SP.Cc, (size_t)local_chunks * rcap * 8))) return rc;
+                if ((rc = gather(SP.Lc, (size_t)local_chunks * rcap * 2 * PE_LIST_CAP * 4))) return rc;
+                if ((rc = gather(Eall, (size_t)rcap * 2 * seg_words * 4))) return rc;
+            }
             k_merge<<<(B + 7) / 8, 256, 0, stream>>>(MP);
             ev_end(ev);
             CU(cudaGetLastError());
@@ -782,7 +845,6 @@ uint32_t pe_abi_version(void) { return PE_ABI_VERSION; }
 int32_t pe_create(const pe_config *cfg, pe_engine **out) {
     if (!cfg || !out) { g_create_err = "null argument"; return PE_ERR_INVALID; }
     if (cfg->abi_version != PE_ABI_VERSION) { g_create_err = "ABI version mismatch"; return PE_ERR_INVALID; }
-    if (cfg->world_size > 1) { g_create_err = "world_size > 1: build with node sharding (see DESIGN.md)"; return PE_ERR_UNSUPPORTED; }
     pe_engine *h = new pe_engine();
     int32_t rc = h->init(cfg);
     if (rc) { g_create_err = h->err; h->destroy(); delete h; return rc; }
@@ -856,6 +918,17 @@ int32_t pe_snapshot_ports(pe_engine *h, uint32_t slot, uint32_t first, uint32_t 
 
 int32_t pe_get_stats(pe_engine *h, pe_stats *out) { *out = h->stats; return PE_OK; }
 int32_t pe_stats_reset(pe_engine *h) { h->stats = pe_stats{}; return PE_OK; }
+
+int32_t pe_nccl_unique_id(void *out128) {
+    if (!out128) return PE_ERR_INVALID;
+    const pe_nccl::Api &nc = pe_nccl::api();
+    if (!nc.ok) { g_create_err = "libnccl.so.2 is not available"; return PE_ERR_UNSUPPORTED; }
+    pe_nccl::ncclUniqueId id;
+    const pe_nccl::ncclResult_t r = nc.GetUniqueId(&id);
+    if (r != 0) { g_create_err = std::string("ncclGetUniqueId: ") + nc.GetErrorString(r); return PE_ERR_CUDA; }
+    memcpy(out128, &id, sizeof id);
+    return PE_OK;
+}
 
 int32_t pe_fold_value(const char *in, uint32_t len, char *out, uint32_t cap) {
     uint32_t w = 0;

@@ -226,6 +226,7 @@ struct RowsParams {
     uint32_t g0;               // run start (absolute group index)
     uint32_t b0, B;            // batch [b0, b0 + B), absolute
     uint32_t *mark;            // [run length] last batch stamp that saw the class (zeroed per run)
+    uint32_t *firstof;         // [run length] first task of the class in that batch
     uint32_t *rowof;           // [run length] row of the class in that batch
     uint32_t stamp;            // batch number + 1
     uint32_t static_cached;    // 1: bitmap rows are per signature for the whole run; 0: one per row of this batch
@@ -235,23 +236,51 @@ struct RowsParams {
     uint32_t *n_rows;          // device count
 };
 
+// Rows are numbered in order of first appearance in the batch, so every rank of a node-sharded engine
+// builds the same table (the rows index the partial results the ranks exchange).  One CTA.
 __global__ void __launch_bounds__(1024) k_rows(const RowsParams P) {
-    __shared__ uint32_t nrows;
-    if (threadIdx.x == 0) nrows = 0;
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t t = tid; t < P.B; t += blockDim.x) {
+        const uint32_t c = P.dcls[P.b0 + t - P.g0] - P.g0;
+        if (atomicExch(&P.mark[c], P.stamp) != P.stamp) P.firstof[c] = 0xFFFFFFFFu;   // first visit of the class in this batch
+    }
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < P.B; t += blockDim.x) {
+    for (uint32_t t = tid; t < P.B; t += blockDim.x) atomicMin(&P.firstof[P.dcls[P.b0 + t - P.g0] - P.g0], t);
+    __syncthreads();
+    // thread k owns the contiguous tasks [k * per, (k + 1) * per): count its representatives, scan, number them
+    const uint32_t per = (P.B + blockDim.x - 1u) / blockDim.x;
+    const uint32_t lo = min(tid * per, P.B), hi = min(lo + per, P.B);
+    uint32_t cnt = 0;
+    for (uint32_t t = lo; t < hi; t++) cnt += P.firstof[P.dcls[P.b0 + t - P.g0] - P.g0] == t ? 1u : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+    if (lane == 31u) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = lane < (blockDim.x >> 5) ? wsum[lane] : 0u, w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= (uint32_t)o) w += x; }
+        wsum[lane] = w - v;                 // exclusive
+        if (lane == 31u) total = w;
+    }
+    __syncthreads();
+    uint32_t r = wsum[warp] + incl - cnt;
+    for (uint32_t t = lo; t < hi; t++) {
         const uint32_t i = P.b0 + t - P.g0;
         const uint32_t c = P.dcls[i] - P.g0;
-        if (atomicExch(&P.mark[c], P.stamp) != P.stamp) {
-            const uint32_t r = atomicAdd(&nrows, 1u);
+        if (P.firstof[c] == t) {
             P.rowof[c] = r;
             P.row_group[r] = P.b0 + t;
             P.row_srow[r] = P.static_cached ? P.srow[P.scls[i] - P.g0] : r;
+            r++;
         }
     }
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < P.B; t += blockDim.x) P.task_row[t] = P.rowof[P.dcls[P.b0 + t - P.g0] - P.g0];
-    if (threadIdx.x == 0) *P.n_rows = nrows;
+    for (uint32_t t = tid; t < P.B; t += blockDim.x) P.task_row[t] = P.rowof[P.dcls[P.b0 + t - P.g0] - P.g0];
+    if (tid == 0) *P.n_rows = total;
 }
 
 }  // namespace pe

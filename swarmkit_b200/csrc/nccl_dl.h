@@ -1,0 +1,46 @@
+// nccl_dl.h -- the five NCCL entry points the engine uses, resolved at run time.
+//
+// The engine is a plain C-ABI shared library; NCCL is only needed when
+// pe_config.world_size > 1 (node-sharded scan), so it is not a link
+// dependency: the library already in the process (e.g. the one torch loaded) is
+// preferred, then libnccl.so.2 from the loader path.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stddef.h>
+
+namespace pe_nccl {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;          // 0 = ncclSuccess
+enum { ncclUint8 = 1 };
+
+struct Api {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+inline const Api &api() {
+    static Api a = [] {
+        Api r;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return r;
+        r.GetUniqueId = reinterpret_cast<decltype(r.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        r.CommInitRank = reinterpret_cast<decltype(r.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        r.CommDestroy = reinterpret_cast<decltype(r.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        r.AllGather = reinterpret_cast<decltype(r.AllGather)>(dlsym(h, "ncclAllGather"));
+        r.GetErrorString = reinterpret_cast<decltype(r.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        r.ok = r.GetUniqueId && r.CommInitRank && r.CommDestroy && r.AllGather && r.GetErrorString;
+        return r;
+    }();
+    return a;
+}
+
+}  // namespace pe_nccl
