@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--workload", default="cfg3-oneoff")
     ap.add_argument("--tasks", type=int, default=1_000_000)
     ap.add_argument("--nodes", type=int, default=100_000)
-    ap.add_argument("--cpu-sample", type=int, default=2000, help="tasks in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=30000, help="tasks in the CPU baseline sample (~14 s on one core)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--max-batch", type=int, default=0)
     args = ap.parse_args()
