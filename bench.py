@@ -245,6 +245,7 @@ def main():
 
     # ---- end-to-end arm: host buffers in, host buffers out
     e2e_ms, e2e_placed = 0.0, 0
+    e2e_lat = []
     s_before = eng.stats()
     for i in range(1 + args.steps):
         reset_state()
@@ -253,7 +254,8 @@ def main():
         on, _ = eng.schedule(w.tick)
         barrier()
         if i > 0:
-            e2e_ms += 1e3 * (time.perf_counter() - t0)
+            e2e_lat.append(1e3 * (time.perf_counter() - t0))
+            e2e_ms += e2e_lat[-1]
             e2e_placed += int((on != 0xFFFFFFFF).sum())
     s_after = eng.stats()
     h2d = (s_after["h2d_bytes"] - s_before["h2d_bytes"]) // (1 + args.steps)
@@ -290,7 +292,10 @@ def main():
                                  "fast_exits": st["seq_stops"], "ordered_warp_wait": st["seq_cons_wait"],
                                  "ordered_warp_work": st["seq_cons_work"], "candidate_taken": st["seq_rewalks"], "prof": st["seq_prof"]},
             "e2e": {"value": e2e_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps,
+                    # BASELINE's second metric: latency of one schedule batch (= one tick: upload, place, download)
+                    "tick_latency_ms": {"min": min(e2e_lat), "median": sorted(e2e_lat)[len(e2e_lat) // 2], "max": max(e2e_lat),
+                                        "samples": len(e2e_lat)}},
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
