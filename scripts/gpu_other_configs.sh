@@ -1,0 +1,8 @@
+# bench lines for the other BASELINE configurations that fit one GPU (not the headline): cfg2 (100k x 10k, resources), cfg4 small
+for args in "--workload cfg2-oneoff --tasks 100000 --nodes 10000" "--workload cfg2-grouped --tasks 100000 --nodes 10000" "--workload cfg3-grouped --tasks 1000000 --nodes 100000" "--workload cfg4-oneoff --tasks 200000 --nodes 200000"; do
+  timeout 300 python bench.py $args --steps 2 --warmup 1 --no-cpu 2>&1 | tail -1 | python -c "import sys,json
+t=sys.stdin.read()
+try:
+    d=json.loads(t); print('$args', {k:d[k] for k in ('value','ms_per_step','split_ms_per_step','paths')}, d['e2e']['value'])
+except Exception as e: print('$args', 'FAILED', t[-400:])"
+done

@@ -66,7 +66,8 @@ struct ScanResult {
 #define PE_SR_SIMPLE 1u     // no generic resources / host ports: the reservation is four reductions
 #define PE_SR_COUNTS 2u     // DesiredState <= COMPLETED: bumps the spread counters
 #define PE_SR_K1 4u         // the group really has exactly one task
-#define PE_SR_STATIC_ONLY 8u // no resource / host-port / max-replicas filter and no recent-failure counts: feasibility cannot change inside a tick
+#define PE_SR_INLINE 8u     // cpu / memory / max-replicas at most (no generic resources, host ports, recent-failure counts):
+                            // the ordered warp can re-rank a consumed best class itself (inline_medium)
 
 struct DevCounters {
     unsigned long long fast_path, medium_path, slow_path, placements, evals_generic;

@@ -744,8 +744,10 @@ struct pe_engine {
         int32_t rc;
         if ((rc = sync_tabs())) return rc;
         if ((rc = ensure_scratch())) return rc;
+        // batch = tasks placed against one scan.  A wave of the scan kernel, but not more than a sixteenth of the nodes: a
+        // batch that touches most of the nodes consumes its own rank classes and falls back to re-ranking per task
         const uint32_t wave = (uint32_t)num_sms * 2u * PE_SCAN_WARPS;
-        const uint32_t Bmax = max_batch ? max_batch : wave;
+        const uint32_t Bmax = max_batch ? max_batch : std::min(wave, std::max(256u, round_up(n_nodes / 16u, 16u)));
         const bool spec = !(cfg_flags & PE_CFG_NO_SPECULATION) && n_nodes > 0;
         if (spec) {
             size_t need = (size_t)Bmax * 2u * e_stride();   // two class rows per scan row

@@ -159,7 +159,7 @@ struct FastTask {
 #define PE_FT_SIMPLE 2u   // reservation = counters (+ cpu / mem): deferred, applied when fast mode ends
 #define PE_FT_COUNTS 4u   // DesiredState <= COMPLETED
 #define PE_FT_PLAIN (PE_FT_VALID | PE_FT_SIMPLE | PE_FT_COUNTS)
-#define PE_FT_INLINE 8u   // no state-dependent filter: a consumed best class is resolved by the ordered warp itself
+#define PE_FT_INLINE 8u   // only cpu / memory / max-replicas can change feasibility: a consumed best class is resolved by the ordered warp itself
 #define PE_SEQ_NCAND 32   // candidates per task = how far ahead of the ordered warp a list is walked (see fast_consumer)
 #define PE_SEQ_GROUP 8    // tasks the ordered warp resolves per iteration
 #define PE_SEQ_LOGN 512   // placements the ordered warp may run ahead of the committer warp
@@ -340,13 +340,14 @@ __device__ __forceinline__ bool wait_applied(const SeqParams &P, SeqShared &S, u
     return true;
 }
 
-// The best class of a task is consumed (every member was taken earlier in the batch) and the task has
-// no state-dependent filter.  Every node outside the two recorded classes ranked strictly worse than
-// the second class when the batch began and ranks only grow, so the arg-min is the first untouched
-// member of the second class or a member of the best class at its LIVE rank.  PE_NONE: not resolvable
-// here (no second class / no untouched member of it / best class not fully listed).
+// The best class of a task is consumed (every member was taken earlier in the batch).  Every node outside
+// the two recorded classes ranked strictly worse than the second class -- or was infeasible -- when the
+// batch began; inside a batch ranks only grow and feasibility only shrinks (resources are only reserved,
+// counts only rise).  So the arg-min is the first untouched member of the second class (untouched: still
+// feasible, still at rank c1) or a member of the best class that is STILL feasible, at its LIVE rank.
+// PE_NONE: not resolvable here (no second class / no untouched member of it / best class not fully listed).
 __device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared &S, const uint32_t *touched, uint32_t *rowcur2, uint32_t row,
-                                                  uint32_t i, uint32_t lane, SeqDebug &dbg) {
+                                                  uint32_t gq, uint32_t i, uint32_t lane, SeqDebug &dbg) {
     const uint32_t N = P.T.n_nodes, nwords = (N + 31u) >> 5;
     const ScanResult *sr = &P.scan[row];
     const uint32_t *L1 = P.L + (size_t)row * 2u * PE_LIST_CAP, *L2 = L1 + PE_LIST_CAP;
@@ -359,6 +360,9 @@ __device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared 
     const unsigned long long c1 = sr->c1;
     const uint4 meta = *reinterpret_cast<const uint4 *>(&sr->n0);   // n0, n1, tie_start, flags
     const uint32_t *svccol = sr->svccol;
+    const long long cpu_res = sr->cpu_res, mem_res = sr->mem_res;
+    const uint32_t fm = P.K.groups[gq].filter_mask;
+    const unsigned long long max_replicas = P.K.groups[gq].max_replicas;
     const uint32_t head1 = L1[lane];                                 // (rows are PE_LIST_CAP long: in bounds)
     const uint32_t n0 = meta.x, n1 = meta.y;
     if (c1 == PE_PREF_NONE || n0 > (uint32_t)PE_LIST_CAP) return PE_NONE;
@@ -414,8 +418,12 @@ __device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared 
     for (uint32_t j = lane; j < n0; j += 32u) {
         const uint32_t n = j < 32u ? head1 : L1[j];   // (j < 32 only in the first round, where j == lane)
         const uint32_t sv = __ldcg(svccol + n), tot = __ldcg(P.T.total + n);    // live: the committer's reductions land in L2
+        bool ok = true;
+        if (fm & (1u << PE_F_RESOURCE))       // ResourceFilter.Check on the live amounts, filter.go:76-84
+            ok = cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) && mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n));
+        if (fm & (1u << PE_F_MAXREPLICAS)) ok = ok && (unsigned long long)sv < max_replicas;   // filter.go:379-381
         const unsigned long long pref = make_pref(0u, sv, tot);
-        if (pref < bp || (pref == bp && n < bn)) { bp = pref; bn = n; }
+        if (ok && (pref < bp || (pref == bp && n < bn))) { bp = pref; bn = n; }
     }
     const uint32_t hi = (uint32_t)(bp >> 32), lo = (uint32_t)bp;
     const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
@@ -485,7 +493,7 @@ __device__ __forceinline__ uint32_t consume_one(const SeqParams &P, SeqShared &S
             const long long tm0 = clock64();
             dbg.prof[4]++;
 #endif
-            n = inline_medium(P, S, touched, rowcur2, row, i, lane, dbg);
+            n = inline_medium(P, S, touched, rowcur2, row, gq, i, lane, dbg);
             if (n != PE_NONE) dbg.n_medium++;
 #if PE_SEQ_PROFILE
             dbg.prof[5] += (unsigned long long)(clock64() - tm0);
@@ -772,7 +780,7 @@ __device__ __forceinline__ ProdTask stage_issue(const SeqParams &P, SeqShared &S
             f.n_class = meta.x;
             f.row = row;
             f.flags = (valid ? PE_FT_VALID : 0u) | ((meta.w & PE_SR_SIMPLE) ? PE_FT_SIMPLE : 0u) | ((meta.w & PE_SR_COUNTS) ? PE_FT_COUNTS : 0u) |
-                      ((meta.w & PE_SR_STATIC_ONLY) ? PE_FT_INLINE : 0u);
+                      ((meta.w & PE_SR_INLINE) ? PE_FT_INLINE : 0u);
             f.tie_start = meta.z;
             bool has_copy = false;
             if (t.n_list) {
