@@ -10,19 +10,22 @@
 //   NodeInfo.addTask (the reservation)         manager/scheduler/nodeinfo.go:108-154
 //   Pipeline failure counters / Explain        manager/scheduler/pipeline.go:56-103
 //
-// Two paths per group:
-//  * fast path (k == 1, scan result available): the batched scan kernel already
-//    evaluated this task against the node table as it stood when the batch began
-//    and left the bitmap of its best rank class.  Within a batch node state only
-//    gets worse, so the first class member not yet touched in this batch is the
-//    sequentially-correct argmin; it is found with one masked find-first over the
-//    bitmap.  Tasks are taken in chunks: descriptors and the first 32k-node
-//    window of each bitmap are staged in shared memory together, so the ordered
-//    part touches shared memory only.
-//  * generic path (any k; also the fall-back when a class was consumed): full
-//    table evaluation against the live state; k == 1: block arg-min; k > 1:
-//    radix-select of the k smallest rank keys, bitonic sort, sequential fill on
-//    staged rows, parallel write-back.
+// Paths per group (all exact):
+//  * fast mode (k == 1, scan result available): the batched scan kernel already
+//    evaluated this task's descriptor against the node table as it stood when the
+//    batch began and left its two best rank classes (bitmaps + member lists).
+//    Within a batch node state only gets worse, so the first class member not yet
+//    touched in this batch is the sequentially-correct argmin.  Warp-specialised:
+//    producer warps stage each task's candidates (TMA copy of the list window at
+//    the row's cursor, walk against the touched bitmap), warp 0 consumes tasks in
+//    order, eight per iteration, a committer warp applies the reservations.
+//  * best class consumed: re-rank its members at their live state against the
+//    first untouched member of the second class -- by the ordered warp itself
+//    (inline_medium) or, for tasks with generic resources / host ports /
+//    recent-failure counts, by the whole block.
+//  * generic path (any k; also the fall-back): full table evaluation against the
+//    live state; k == 1: block arg-min; k > 1: radix-select of the k smallest rank
+//    keys, bitonic sort, sequential fill on staged rows, parallel write-back.
 #pragma once
 #include "kernels_common.cuh"
 
@@ -156,7 +159,7 @@ struct FastTask {
     uint32_t tie_start;
 };
 #define PE_FT_VALID 1u    // the scan found a feasible node and the group has exactly one task
-#define PE_FT_SIMPLE 2u   // reservation = counters (+ cpu / mem): deferred, applied when fast mode ends
+#define PE_FT_SIMPLE 2u   // reservation = counters (+ cpu / mem): logged by the ordered warp, applied by the committer warp
 #define PE_FT_COUNTS 4u   // DesiredState <= COMPLETED
 #define PE_FT_PLAIN (PE_FT_VALID | PE_FT_SIMPLE | PE_FT_COUNTS)
 #define PE_FT_INLINE 8u   // only cpu / memory / max-replicas can change feasibility: a consumed best class is resolved by the ordered warp itself
@@ -993,11 +996,9 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     uint32_t gi = P.g_begin;
     while (gi < P.g_end) {
         // ================= fast mode: warp-specialised pipeline over k == 1 tasks ====
-        // Producer warps prefetch, per task, the scan record and the first PE_SEQ_WIN
-        // words of its best-class bitmap (one TMA bulk copy, completion on the slot's
-        // mbarrier) into a ring of shared-memory slots; warp 0 consumes the slots IN
-        // ORDER, so the ordered part touches shared memory only.  The mode ends at the
-        // first task the bitmaps cannot resolve; that task takes the block-wide path.
+        // (see the comment above fast_consumer).  The mode ends at the first task the
+        // ordered warp cannot resolve from the scan's classes; that task takes the
+        // block-wide path below and fast mode starts again after it.
         if (P.scan != nullptr && !S.neutral) {
             __syncthreads();
             { const long long t1 = clock64(); cyc_generic += t1 - t_mark; t_mark = t1; }
