@@ -162,3 +162,13 @@ def test_engine_requires_extension():
     import os
     from swarmkit_b200 import engine_library_path
     assert os.path.exists(engine_library_path())
+
+
+def test_cfg3_many_nodes_touched_bitmap_in_global_memory():
+    # more than 12288 bitmap words: the sequencer keeps `touched` in global memory instead of shared memory
+    w = W.cfg3("oneoff", n_nodes=450_000, n_tasks=3000, n_services=30)
+    gpu, cpu, res = run_both(w.nodes, w.tick, w.n_nodes)
+    for t, a, b in res:
+        R.compare_results(t, a, b, "cfg3-450k-nodes")
+    st = gpu.stats()
+    assert st["scan_launches"] > 0 and st["fast_path"] > 0
