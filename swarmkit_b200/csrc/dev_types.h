@@ -61,11 +61,13 @@ struct ScanResult {
     uint32_t flags;         // PE_SR_*
     long long cpu_res, mem_res;
     uint32_t *svccol;       // the row's per-service counter column
-    unsigned long long pad;
+    unsigned long long max_replicas;   // Placement.MaxReplicas (meaningful with PE_SR_MAXREP)
 };
 #define PE_SR_SIMPLE 1u     // no generic resources / host ports: the reservation is four reductions
 #define PE_SR_COUNTS 2u     // DesiredState <= COMPLETED: bumps the spread counters
 #define PE_SR_K1 4u         // the group really has exactly one task
+#define PE_SR_RES 16u       // ResourceFilter enabled (cpu / memory reservations)
+#define PE_SR_MAXREP 32u    // MaxReplicasFilter enabled
 #define PE_SR_INLINE 8u     // cpu / memory / max-replicas at most (no generic resources, host ports, recent-failure counts):
                             // the ordered warp can re-rank a consumed best class itself (inline_medium)
 

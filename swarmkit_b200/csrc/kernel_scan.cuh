@@ -375,10 +375,11 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams P) {
         r.tie_start = G.tie_start;
         r.flags = ((G.gen_cnt == 0 && G.port_cnt == 0) ? PE_SR_SIMPLE : 0u) | (G.n_tasks == 1 ? PE_SR_K1 : 0u) |
                   ((G.n_tasks >= 1 && (P.K.task_flags[G.task_off] & PE_T_COUNTS)) ? PE_SR_COUNTS : 0u) |
-                  ((G.gen_cnt == 0 && G.port_cnt == 0 && !(fm & (1u << PE_F_HOSTPORT)) && G.fail_cnt == 0) ? PE_SR_INLINE : 0u);
+                  ((G.gen_cnt == 0 && G.port_cnt == 0 && !(fm & (1u << PE_F_HOSTPORT)) && G.fail_cnt == 0) ? PE_SR_INLINE : 0u) |
+                  ((fm & (1u << PE_F_RESOURCE)) ? PE_SR_RES : 0u) | ((fm & (1u << PE_F_MAXREPLICAS)) ? PE_SR_MAXREP : 0u);
         r.cpu_res = G.cpu_res; r.mem_res = G.mem_res;
         r.svccol = P.svc[G.svc_id];
-        r.pad = 0;
+        r.max_replicas = G.max_replicas;
         P.out[row] = r;
     }
 }

@@ -364,8 +364,8 @@ __device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared 
     const uint4 meta = *reinterpret_cast<const uint4 *>(&sr->n0);   // n0, n1, tie_start, flags
     const uint32_t *svccol = sr->svccol;
     const long long cpu_res = sr->cpu_res, mem_res = sr->mem_res;
-    const uint32_t fm = P.K.groups[gq].filter_mask;
-    const unsigned long long max_replicas = P.K.groups[gq].max_replicas;
+    const unsigned long long max_replicas = sr->max_replicas;   // (the row record is L2-hot; the 112-byte group descriptors are not)
+    (void)gq;
     const uint32_t head1 = L1[lane];                                 // (rows are PE_LIST_CAP long: in bounds)
     const uint32_t n0 = meta.x, n1 = meta.y;
     if (c1 == PE_PREF_NONE || n0 > (uint32_t)PE_LIST_CAP) return PE_NONE;
@@ -422,9 +422,9 @@ __device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared 
         const uint32_t n = j < 32u ? head1 : L1[j];   // (j < 32 only in the first round, where j == lane)
         const uint32_t sv = __ldcg(svccol + n), tot = __ldcg(P.T.total + n);    // live: the committer's reductions land in L2
         bool ok = true;
-        if (fm & (1u << PE_F_RESOURCE))       // ResourceFilter.Check on the live amounts, filter.go:76-84
+        if (meta.w & PE_SR_RES)               // ResourceFilter.Check on the live amounts, filter.go:76-84
             ok = cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) && mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n));
-        if (fm & (1u << PE_F_MAXREPLICAS)) ok = ok && (unsigned long long)sv < max_replicas;   // filter.go:379-381
+        if (meta.w & PE_SR_MAXREP) ok = ok && (unsigned long long)sv < max_replicas;   // filter.go:379-381
         const unsigned long long pref = make_pref(0u, sv, tot);
         if (ok && (pref < bp || (pref == bp && n < bn))) { bp = pref; bn = n; }
     }
