@@ -1,7 +1,7 @@
 """Node-sharded engine group against the CPU oracle (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/multi_gpu_check.py
+        tests/multi_gpu_check.py
 
 Every rank mirrors all nodes and submits the same ticks; each scans its slice of the node axis
 (SURVEY 8e).  Checks: rank 0's placements / failure counters / final node state equal the oracle's,

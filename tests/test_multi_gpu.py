@@ -1,4 +1,4 @@
-"""Node-sharded engine group on two GPUs of one box: scripts/multi_gpu_check.py under torchrun.
+"""Node-sharded engine group on two GPUs of one box: tests/multi_gpu_check.py under torchrun.
 Skipped on boxes with fewer than two devices."""
 import os
 import subprocess
@@ -15,6 +15,6 @@ def test_two_rank_node_sharding_matches_oracle():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
+           "--master-port", "29517", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
