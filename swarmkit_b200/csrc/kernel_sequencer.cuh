@@ -63,14 +63,6 @@ __device__ __forceinline__ void sq_mbar_init(unsigned long long *bar, uint32_t c
 __device__ __forceinline__ void sq_mbar_inval(unsigned long long *bar) {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(seq_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void sq_mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(seq_smem_u32(bar)) : "memory");
-}
-// Arrive without release ordering: the consumer's empty-slot signal must not wait for its
-// outstanding global reductions / stores to be acknowledged (that costs ~1 us per task).
-__device__ __forceinline__ void sq_mbar_arrive_relaxed(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(seq_smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ bool sq_mbar_try_wait(unsigned long long *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -97,9 +89,6 @@ __device__ __forceinline__ uint32_t ld_acquire_smem(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(seq_smem_u32(p)) : "memory");
     return v;
-}
-__device__ __forceinline__ void sq_mbar_wait(unsigned long long *bar, uint32_t parity) {
-    while (!sq_mbar_try_wait(bar, parity)) {}
 }
 // Same, but gives up after ~1 s and raises a device error instead of hanging the GPU.
 __device__ __forceinline__ bool sq_mbar_wait_wd(unsigned long long *bar, uint32_t parity, DevCounters *ctr, uint32_t code) {
