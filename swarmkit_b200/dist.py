@@ -1,8 +1,10 @@
 """Rank plumbing for the N>1 benchmark arm (one process per GPU, launched by torchrun).
 
-The placement path itself has no data-path collective in round 1 (DESIGN.md section 7:
-"replicas only"); what crosses ranks is the timing reduction the bench contract asks for:
-MAX over ranks of the device time, SUM over ranks of the work done."""
+The placement path's own collectives (NCCL all-gathers of the per-chunk scan results of a
+node-sharded engine group) live inside libplacement.so; what crosses
+ranks HERE is the timing reduction the bench contract asks for: MAX over ranks of the device
+time, SUM over ranks of the work done (the ranks of a group hold replicas of the same
+decisions, so bench.py lets only rank 0 contribute work)."""
 from __future__ import annotations
 
 import os
