@@ -132,7 +132,54 @@ def cpu_sample(w, sample_tasks: int):
     out, _ = o.schedule(sub)
     dt = time.perf_counter() - t0
     placed = int((out != 0xFFFFFFFF).sum())
-    return placed, sub.n_tasks, dt
+    return placed, sub.n_tasks, dt, out
+
+
+def golden_prefix(args, n_tasks: int, n_nodes: int):
+    """Committed full-size golden placements (tests/golden/big_*.npz, CPU oracle) for this workload, if one covers it.
+    The tick is sequential, so the vector of the 1M-task tick pins every shorter tick over the same nodes."""
+    table = {("cfg3-oneoff", 100_000): "big_cfg3_oneoff_1m_100k", ("cfg2-oneoff", 10_000): "big_cfg2_oneoff_100k_10k",
+             ("cfg3-grouped", 100_000): "big_cfg3_grouped_1m_100k", ("cfg2-grouped", 10_000): "big_cfg2_grouped_100k_10k"}
+    name = table.get((args.workload, n_nodes))
+    if name is None:
+        return None, None
+    try:
+        from tests.golden import make_golden_big as GB
+        gold, _ = GB.load(name)
+    except Exception:
+        return None, None
+    if args.workload.endswith("grouped") and gold.size != n_tasks:
+        return None, None       # (grouped ticks change with the replica count: only the full size is pinned)
+    return (gold[:n_tasks], name) if gold.size >= n_tasks else (None, None)
+
+
+def latency_arm(eng, w, reset_state, tick_tasks: int, n_ticks: int, gold):
+    """BASELINE's second metric: latency of ONE schedule batch (one tick = one pe_schedule call, host buffers in, host
+    buffers out) against the resident node mirror.  The pending tasks of the workload arrive `tick_tasks` at a time, the
+    way the scheduler's debounce (scheduler.go:149-155) hands them over; state carries from tick to tick, and when the
+    workload is used up it is offered again on top of what is already placed.  The placements of the first pass over the
+    workload are, by the tick's sequential semantics, exactly the golden placements of the one big tick."""
+    n = w.tick.n_groups
+    per_pass = max(n // tick_tasks, 1)
+    subs = [w.tick.slice_groups(i * tick_tasks, (i + 1) * tick_tasks) for i in range(per_pass)]
+    reset_state()
+    for s in subs[:3]:                                   # warm-up ticks (allocations, first-use paths), then a clean mirror
+        eng.schedule(s)
+    reset_state()
+    lat, mism, checked = [], 0, 0
+    for i in range(n_ticks):
+        s = subs[i % per_pass]
+        t0 = time.perf_counter()
+        on, _ = eng.schedule(s)
+        lat.append(1e3 * (time.perf_counter() - t0))
+        if gold is not None and i < per_pass:
+            g = gold[i * tick_tasks:(i + 1) * tick_tasks]
+            mism += int((on[:g.size] != g).sum())
+            checked += int(g.size)
+    a = np.sort(np.array(lat))
+    q = lambda p: float(a[min(len(a) - 1, int(p * len(a)))])
+    return {"tasks_per_tick": tick_tasks, "ticks": n_ticks, "p50": q(0.50), "p90": q(0.90), "p99": q(0.99), "max": float(a[-1]),
+            "mean": float(a.mean()), "parity": {"tasks": checked, "mismatches": mism}}
 
 
 def run_reference(args, rank, world):
@@ -142,7 +189,7 @@ def run_reference(args, rank, world):
     sample = args.cpu_sample
     vals = []
     for i in range(args.warmup + args.steps):
-        placed, n, dt = cpu_sample(w, sample)
+        placed, n, dt, _ = cpu_sample(w, sample)
         if i >= args.warmup:
             vals.append((placed, dt))
     placed = sum(p for p, _ in vals)
@@ -174,6 +221,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=30000, help="tasks in the CPU baseline sample (~14 s on one core)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--max-batch", type=int, default=0)
+    ap.add_argument("--latency-ticks", type=int, default=1000, help="ticks per size in the p99 tick-latency arm (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,6 +255,13 @@ def main():
     # pinned host copies of what crosses PCIe each step
     w.tick.groups = pinned_copy(w.tick.groups)
     w.tick.task_flags = pinned_copy(w.tick.task_flags)
+    for name in ("cons", "plats", "gens", "ports"):
+        a = getattr(w.tick, name)
+        if a.size:
+            setattr(w.tick, name, pinned_copy(a))
+    # ... and of what comes back (the caller owns the result buffers of pe_schedule)
+    pin_node = pinned_copy(np.zeros(max(n_tasks, 1), np.uint32))
+    pin_fail = pinned_copy(np.zeros(max(w.tick.n_groups, 1) * 8, np.uint32))
 
     def reset_state():
         eng.node_upsert(w.nodes)   # rewrites every row and zeroes every per-service counter column
@@ -251,7 +306,7 @@ def main():
         reset_state()
         barrier()
         t0 = time.perf_counter()
-        on, _ = eng.schedule(w.tick)
+        on, _ = eng.schedule(w.tick, pin_node, pin_fail)
         barrier()
         if i > 0:
             e2e_lat.append(1e3 * (time.perf_counter() - t0))
@@ -261,12 +316,21 @@ def main():
     h2d = (s_after["h2d_bytes"] - s_before["h2d_bytes"]) // (1 + args.steps)
     d2h = (s_after["d2h_bytes"] - s_before["d2h_bytes"]) // (1 + args.steps)
 
+    # ---- tick latency: >= 1000 ticks of 1k and of 10k pending tasks against the resident mirror
+    tick_lat = {}
+    if args.latency_ticks > 0 and world == 1:
+        gold_l, _ = golden_prefix(args, n_tasks, w.n_nodes)
+        for tt in (1000, 10000):
+            if n_tasks >= tt:
+                tick_lat[f"{tt // 1000}k"] = latency_arm(eng, w, reset_state, tt, args.latency_ticks, gold_l)
+
     # ---- max over ranks of the times, sum over ranks of the work (swarmkit_b200/dist.py)
     from swarmkit_b200.dist import reduce_step
     # the ranks hold replicas of the same decisions: count them once
     (dev_ms, wall_ms, e2e_ms), (placed_all, e2e_all) = reduce_step(
         [dev_ms, wall_ms, e2e_ms], [placed_total if rank == 0 else 0, e2e_placed if rank == 0 else 0])
 
+    parity_failed = False
     if rank == 0:
         peak, peak_src = measured_peak()
         scan_s = st["scan_ms"] / 1e3
@@ -285,17 +349,24 @@ def main():
             "evals_per_s_per_gpu": st["evals"] / scan_s if scan_s > 0 else None,
             "pairs_per_s_per_gpu": st["pairs"] / world / (dev_ms / 1e3),   # (task,node) pairs covered: each rank covers 1/N of the nodes
             "scan_rows_per_task": st["scan_rows"] / max(placed_total, 1),
-            "split_ms_per_step": {"scan": st["scan_ms"] / args.steps, "sequencer": st["sequencer_ms"] / args.steps,
+            "split_ms_per_step": {"scan": st["scan_ms"] / args.steps, "place": st["place_ms"] / args.steps,
+                                  "sequencer": st["sequencer_ms"] / args.steps,
                                   "classify_static_rows": st["prep_ms"] / args.steps},
+            "place": {"tasks": st["place_tasks"], "handed_over_batches": st["place_cuts"], "reranked_lanes": st["place_amb"],
+                      "tails": st["place_tails"], "chunks": st["place_chunks"],
+                      "cta0_cycles": {"stage": st["place_cyc"][0], "resolve": st["place_cyc"][1], "commit": st["place_cyc"][2]},
+                      "resolve": {"passes": st["seq_prof"][0], "rounds": st["seq_prof"][1], "short_chunks": st["seq_prof"][2],
+                                  "thread0_cycles": {"masks": st["seq_prof"][3], "attempts": st["seq_prof"][4], "recheck": st["seq_prof"][5], "finalize": st["seq_prof"][6]}, "warps_work_whole": st["seq_prof"][8:16]}},
             "paths": {"fast": st["fast_path"], "medium": st["medium_path"], "slow": st["slow_path"]},
             "sequencer_cycles": {"fast": st["seq_cycles_fast"], "medium": st["seq_cycles_medium"], "generic": st["seq_cycles_generic"],
                                  "fast_exits": st["seq_stops"], "ordered_warp_wait": st["seq_cons_wait"],
                                  "ordered_warp_work": st["seq_cons_work"], "candidate_taken": st["seq_rewalks"], "prof": st["seq_prof"]},
             "e2e": {"value": e2e_all / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps,
-                    # BASELINE's second metric: latency of one schedule batch (= one tick: upload, place, download)
-                    "tick_latency_ms": {"min": min(e2e_lat), "median": sorted(e2e_lat)[len(e2e_lat) // 2], "max": max(e2e_lat),
-                                        "samples": len(e2e_lat)}},
+                    # BASELINE's second metric: latency of one schedule batch (= one tick: upload, place, download).
+                    # "whole_workload": the 1M-task tick above; "1k" / "10k": latency_arm()
+                    "tick_latency_ms": dict({"whole_workload": {"min": min(e2e_lat), "median": sorted(e2e_lat)[len(e2e_lat) // 2],
+                                                                "max": max(e2e_lat), "samples": len(e2e_lat)}}, **tick_lat)},
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -309,14 +380,30 @@ def main():
                          "bytes_per_launch": st["scan_bytes"] / max(st["scan_launches"], 1),
                          "ms_per_launch": st["scan_ms"] / max(st["scan_launches"], 1)},
         }
+        # ---- parity of the TIMED tick (every --gpus N): the placements it produced against (a) the committed
+        # full-size golden vector of the CPU oracle and (b) the oracle run right here on the tick's first tasks
+        mismatches = sum(v["parity"]["mismatches"] for v in tick_lat.values())
+        gold, gold_name = golden_prefix(args, n_tasks, w.n_nodes)
+        if gold is not None:
+            bad = int((out_node != gold).sum())
+            mismatches += bad
+            line["parity_full"] = {"tasks": int(gold.size), "mismatches": bad, "golden": f"tests/golden/{gold_name}.npz"}
         if not args.no_cpu:
-            placed, n, dt = cpu_sample(w, args.cpu_sample)
+            placed, n, dt, cpu_out = cpu_sample(w, args.cpu_sample)
             line["cpu_baseline"] = {"value": placed / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"first {n} tasks of the same workload against all {w.n_nodes} nodes "
                                               f"({n * w.n_nodes:.3g} (task,node) visits, {dt:.1f} s), oracle/flat_oracle.cpp, 1 thread"}
+            bad = int((out_node[:cpu_out.size] != cpu_out).sum())
+            mismatches += bad
+            line["parity_prefix"] = {"tasks": int(cpu_out.size), "mismatches": bad}
         print(json.dumps(line))
+        if mismatches:
+            sys.stderr.write(f"PARITY FAILURE: {mismatches} placements of the timed tick differ from the CPU oracle\n")
+            parity_failed = True
     if world > 1:
         dist.destroy_process_group()
+    if parity_failed:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -174,6 +174,8 @@ typedef struct pe_tick {
 
 /* ---- engine configuration ----------------------------------------------- */
 #define PE_CFG_NO_SPECULATION 0x1u /* disable the batched k=1 scan (debug / A-B)  */
+#define PE_CFG_ORDERED_ONLY 0x2u   /* place scanned batches with the ordered sequencer alone (A-B against the
+                                      chunked parallel placement step)             */
 
 typedef struct pe_config {
     uint32_t abi_version;   /* PE_ABI_VERSION                                  */
@@ -217,6 +219,12 @@ typedef struct pe_stats {
     uint64_t seq_stops[5];
     uint64_t seq_cons_wait, seq_cons_work, seq_rewalks;
     uint64_t seq_prof[16];      /* see SeqDebug in kernel_sequencer.cuh */
+    /* the chunked parallel placement step (kernel_place.cuh): CUDA-event time, tasks it placed or examined, batches it
+     * handed to the ordered sequencer part-way, lanes re-ranked from the chunk log, candidate tails, chunks, and SM
+     * cycles of CTA 0 in the stage / resolve / commit phases */
+    double place_ms;
+    uint64_t place_tasks, place_cuts, place_amb, place_tails, place_chunks;
+    uint64_t place_cyc[3];
 } pe_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */

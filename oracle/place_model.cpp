@@ -16,7 +16,7 @@
 // prefix mpe_; everything but the k == 1 batch path is the oracle's own code.
 //
 // Knobs (environment, read per schedule call): PM_BATCH (tasks per scan batch),
-// PM_CHUNK (tasks per chunk), PM_K (candidates per task; 0 = position in the chunk + 1), PM_LISTCAP (members
+// PM_CHUNK (tasks per chunk), PM_K (cap on the candidates per task: task i of a chunk gets min(i + 1, K); 0 = no cap), PM_LISTCAP (members
 // listed per class), PM_GROUP (lanes per resolve group).
 #define ope_abi_version mpe_abi_version
 #define ope_create mpe_create
@@ -86,7 +86,8 @@ struct Model {
     const Tick &t;
     uint32_t *out_node, *out_fail;
     uint32_t Bmax, C, K, LISTCAP, GROUP;
-    uint64_t n_par = 0, n_cut = 0, n_amb = 0, n_tail = 0;
+    uint64_t n_par = 0, n_cut = 0, n_amb = 0, n_tail = 0, n_retry = 0;
+    uint64_t n_rounds = 0, n_skips = 0, n_groups_run = 0, n_maxskip = 0;   // diagnostics of the resolve loop
 
     bool desc_equal(const pe_group &a, const pe_group &b) const {
         if (a.svc_id != b.svc_id || a.filter_mask != b.filter_mask || a.cpu_res != b.cpu_res || a.mem_res != b.mem_res ||
@@ -226,27 +227,35 @@ struct Model {
         }
         std::vector<uint8_t> touched(N, 0);
         uint32_t cut = B;
-        for (uint32_t c0 = 0; c0 < B && cut == B; c0 += C) {
+        uint32_t done = 0;
+        for (uint32_t c0 = 0; c0 < B && cut == B; c0 += done) {
             const uint32_t nc = std::min(C, B - c0);
+            done = nc;      // tasks this chunk settles; fewer when a lane runs out of a capped candidate list
             // ---- stage: any order (parallel on the device); here reversed to expose order dependence
             std::vector<Slot> slots(nc);
-            for (uint32_t i = nc; i-- > 0;) slots[i] = stage(rows[task_row[c0 + i]], touched, K ? K : i + 1);
+            for (uint32_t i = nc; i-- > 0;) slots[i] = stage(rows[task_row[c0 + i]], touched, K ? std::min(K, i + 1) : i + 1);
             // ---- resolve: groups of GROUP lanes in task order
             std::map<uint32_t, std::vector<uint32_t>> H;   // node -> in-chunk placements (log indices)
             std::vector<LogEntry> log;
-            for (uint32_t gb = 0; gb < nc && cut == B; gb += GROUP) {
+            for (uint32_t gb = 0; gb < nc && cut == B && done == nc; gb += GROUP) {
                 const uint32_t ng = std::min(GROUP, nc - gb);
                 uint32_t first_active = 0;
-                while (first_active < ng && cut == B) {
+                while (first_active < ng && cut == B && done == nc) {
                     // the monotone loop: every active lane proposes its first candidate that is neither taken in
                     // this chunk nor proposed by a lower lane; a lane only ever moves forward
                     std::vector<uint32_t> j(ng, 0), prop(ng, PE_NONE);
+                    n_groups_run++;
                     for (;;) {
+                        n_rounds++;
+                        uint64_t mx = 0;
                         for (uint32_t l = first_active; l < ng; l++) {
                             const Slot &sl = slots[gb + l];
-                            while (j[l] < sl.cand.size() && H.count(sl.cand[j[l]])) j[l]++;
+                            uint64_t sk = 0;
+                            while (j[l] < sl.cand.size() && H.count(sl.cand[j[l]])) { j[l]++; n_skips++; sk++; }
+                            mx = std::max(mx, sk);
                             prop[l] = (!sl.cut && j[l] < sl.cand.size()) ? sl.cand[j[l]] : PE_NONE;
                         }
+                        n_maxskip += mx;
                         bool any = false;
                         std::vector<uint8_t> kicked(ng, 0);
                         for (uint32_t l = first_active; l < ng; l++) {
@@ -269,6 +278,9 @@ struct Model {
                     };
                     for (uint32_t l = first_active; l < bad; l++) commit_lane(l, prop[l]);
                     if (bad == ng) break;
+                    if (why == 1 && K && !slots[gb + bad].cut && slots[gb + bad].cand.size() == K && gb + bad + 1 > K) {
+                        done = gb + bad; n_retry++; break;     // its list was cut at K candidates: the next chunk starts with this task
+                    }
                     if (why == 1) { cut = c0 + gb + bad; if (std::getenv("PM_DEBUG")) { const Slot &sl = slots[gb + bad]; const Row &r = rows[task_row[cut]]; fprintf(stderr, "cut task %u: slotcut=%d why=%d ncand=%zu c0=%llx c1=%llx n0=%u n1=%u inline=%d\n", cut, (int)sl.cut, sl.why, sl.cand.size(), (unsigned long long)r.c0, (unsigned long long)r.c1, r.n0, r.n1, (int)r.inline_ok); } break; }
                     // ---- ambiguous lane: a skipped candidate ranked strictly better than the chosen one when the
                     // chunk began; it was taken inside the chunk, so its rank moved -- recompute it exactly
@@ -349,6 +361,7 @@ int32_t mpe_schedule(pe_engine *h, const pe_tick *tk, uint32_t *out_node, uint32
             env_u32("PM_LISTCAP", 1024), env_u32("PM_GROUP", 32)};
     m.run();
     g_model_counters[0] += m.n_par; g_model_counters[1] += m.n_cut; g_model_counters[2] += m.n_amb; g_model_counters[3] += m.n_tail;
+    if (std::getenv("PM_DEBUG")) fprintf(stderr, "resolve: passes %llu rounds %llu skips %llu sum-of-max-skips-per-round %llu\n", (unsigned long long)m.n_groups_run, (unsigned long long)m.n_rounds, (unsigned long long)m.n_skips, (unsigned long long)m.n_maxskip);
     return PE_OK;
 }
 

@@ -22,6 +22,7 @@ PE_ATTR_NODE_ID, PE_ATTR_HOSTNAME, PE_ATTR_ROLE, PE_ATTR_OS, PE_ATTR_ARCH, PE_AT
 PE_G_CONSTRAINT_NEVER, PE_G_LOG_DRIVER = 0x1, 0x2
 PE_T_COUNTS = 0x1
 PE_CFG_NO_SPECULATION = 0x1
+PE_CFG_ORDERED_ONLY = 0x2
 
 PE_OK, PE_ERR_INVALID, PE_ERR_CUDA, PE_ERR_NOMEM, PE_ERR_UNSUPPORTED, PE_ERR_NO_DEVICE, PE_ERR_OVERFLOW = range(7)
 
@@ -92,7 +93,9 @@ class pe_stats(C.Structure):
                 ("seq_cycles_medium", C.c_uint64), ("seq_cycles_generic", C.c_uint64),
                 ("pairs", C.c_uint64), ("scan_rows", C.c_uint64), ("static_evals", C.c_uint64), ("prep_ms", C.c_double),
                 ("seq_stops", C.c_uint64 * 5), ("seq_cons_wait", C.c_uint64), ("seq_cons_work", C.c_uint64),
-                ("seq_rewalks", C.c_uint64), ("seq_prof", C.c_uint64 * 16)]
+                ("seq_rewalks", C.c_uint64), ("seq_prof", C.c_uint64 * 16),
+                ("place_ms", C.c_double), ("place_tasks", C.c_uint64), ("place_cuts", C.c_uint64), ("place_amb", C.c_uint64),
+                ("place_tails", C.c_uint64), ("place_chunks", C.c_uint64), ("place_cyc", C.c_uint64 * 3)]
 
     def as_dict(self) -> dict:
         return {n: (list(getattr(self, n)) if hasattr(getattr(self, n), "__len__") else getattr(self, n)) for n, _ in self._fields_}
@@ -274,9 +277,15 @@ class FlatABI:
         self._check(self.f["node_task_delta"](self.h, _ptr(d), d.size, _ptr(g), _ptr(p)))
 
     # -- hot path
-    def schedule(self, tick: Tick):
-        out_node = np.full(max(tick.n_tasks, 1), PE_NONE, np.uint32)
-        out_fail = np.zeros(max(tick.n_groups, 1) * PE_NUM_FILTERS, np.uint32)
+    def schedule(self, tick: Tick, out_node=None, out_fail=None):
+        """pe_schedule.  out_node / out_fail: optional caller-owned result buffers (uint32, at least n_tasks and
+        n_groups * 8 long) -- e.g. page-locked arrays, so the copy back does not go through a staging buffer."""
+        if out_node is None:
+            out_node = np.full(max(tick.n_tasks, 1), PE_NONE, np.uint32)
+        if out_fail is None:
+            out_fail = np.zeros(max(tick.n_groups, 1) * PE_NUM_FILTERS, np.uint32)
+        assert out_node.dtype == np.uint32 and out_fail.dtype == np.uint32
+        assert out_node.size >= tick.n_tasks and out_fail.size >= tick.n_groups * PE_NUM_FILTERS
         ts = tick.c_struct()
         self._check(self.f["schedule"](self.h, C.byref(ts), _ptr(out_node), _ptr(out_fail)))
         return out_node[:tick.n_tasks], out_fail[:tick.n_groups * PE_NUM_FILTERS].reshape(-1, PE_NUM_FILTERS)

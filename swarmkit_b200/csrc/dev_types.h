@@ -78,6 +78,9 @@ struct DevCounters {
     unsigned long long scan_evals, scan_bytes;     // (row,node) evaluations the scan kernel executed / their algorithmic bytes
     unsigned long long prof[16];                    // sequencer diagnostics (PE_SEQ_PROFILE builds)
     unsigned long long static_evals, scan_rows;    // (signature,node) evaluations of k_static; rows scanned
+    // the chunked parallel placement step (kernel_place.cuh): tasks it handled, batches it had to hand to the ordered
+    // sequencer part-way, lanes that re-ranked from the chunk log, candidate tails built, chunks, SM cycles per phase
+    unsigned long long place_tasks, place_cuts, place_amb, place_tails, place_chunks, place_cyc[3];
     uint32_t error;
     uint32_t pad;
 };

@@ -21,6 +21,7 @@
 #include "kernel_classify.cuh"
 #include "kernel_scan.cuh"
 #include "kernel_sequencer.cuh"
+#include "kernel_place.cuh"
 
 using namespace pe;
 
@@ -40,6 +41,18 @@ std::string g_create_err;
     } while (0)
 
 uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+// PE_DEBUG_SYNC=1 in the environment: wait after every kernel of the tick and say which one it was on stderr (finds the
+// kernel that hangs or faults; never set in measurements)
+bool debug_sync() { static const bool on = getenv("PE_DEBUG_SYNC") != nullptr; return on; }
+#define DBG_SYNC(what, a, b)                                                                         \
+    do {                                                                                             \
+        if (debug_sync()) {                                                                          \
+            fprintf(stderr, "[pe] %s %u %u ...", what, (unsigned)(a), (unsigned)(b));                \
+            cudaError_t e_ = cudaStreamSynchronize(stream);                                          \
+            fprintf(stderr, " %s\n", cudaGetErrorString(e_));                                        \
+        }                                                                                            \
+    } while (0)
 
 struct EvPair { cudaEvent_t a, b; int kind; };
 
@@ -96,8 +109,10 @@ struct pe_engine {
     // batch is split by node range and the partial results are exchanged with NCCL all-gathers
     int rank = 0, world = 1;
     pe_nccl::ncclComm_t comm = nullptr;
-    uint32_t *Eall = nullptr; size_t Eall_words = 0; // [rank][rows][2][seg_words] gathered bitmap segments
-    uint32_t *d_cls_counters = nullptr;              // [0] signatures [1] classes [2] rows of the current batch
+    uint32_t *Eall = nullptr; size_t Eall_words = 0; // node sharding: merged member lists [rows][2][x_cap] (k_xpack + all-reduce)
+    uint32_t *d_cls_counters = nullptr;              // [0] signatures [1] classes [2] rows of the current batch [3] where the
+                                                     //     parallel placement step stopped in the current batch
+    uint32_t *cursors = nullptr; size_t cursors_cap = 0;   // [rows][2] class-list cursors of the placement step
     DevCounters *d_ctr = nullptr;
     void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
 
@@ -137,6 +152,7 @@ struct pe_engine {
         CU(cudaMalloc(&d_cls_counters, 16));
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
         CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(12288)));
+        CU(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem_bytes(PE_PL_TK_MAX_WORDS)));
         CU(cudaFuncSetAttribute(k_scan<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CU(cudaFuncSetAttribute(k_scan<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CU(cudaFuncSetAttribute(k_scan<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -161,7 +177,8 @@ struct pe_engine {
         for (auto p : gen) fr(p);
         for (auto p : d_tab) fr(p);
         fr(tick_buf); fr(d_out_node); fr(d_out_fail); fr(ff8); fr(pref64); fr(cand_g); fr(st_cpu_g); fr(st_mem_g); fr(st_gen_g);
-        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters); fr(chunk_buf);
+        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters); fr(chunk_buf); fr(cursors);
+        if (h_ctr) cudaFreeHost(h_ctr);
         for (auto &p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         if (stream) cudaStreamDestroy(stream);
     }
@@ -281,6 +298,7 @@ struct pe_engine {
                 else if (ev_pool[i].kind == 2) stats.h2d_ms += ms;
                 else if (ev_pool[i].kind == 3) stats.d2h_ms += ms;
                 else if (ev_pool[i].kind == 5) stats.prep_ms += ms;
+                else if (ev_pool[i].kind == 6) stats.place_ms += ms;
                 else stats.run_ms += ms;
             }
         }
@@ -441,7 +459,8 @@ struct pe_engine {
         return sync_tabs();
     }
 
-    int32_t tick_upload(const pe_tick *tk) {
+    // sync = false: pe_schedule keeps the caller's buffers alive itself and waits once, at the end of the whole call
+    int32_t tick_upload(const pe_tick *tk, bool sync = true) {
         int32_t rc = validate_and_prepare(tk);
         if (rc) return rc;
         n_groups = tk->n_groups; n_tasks = tk->n_tasks;
@@ -489,7 +508,7 @@ struct pe_engine {
         if ((rc = ensure_buf(p, c, (size_t)std::max(n_groups, 1u) * PE_NUM_FILTERS * 4))) return rc;
         d_out_fail = reinterpret_cast<uint32_t *>(p); out_fail_cap = c;
         K.out_node = d_out_node; K.out_fail = d_out_fail;
-        CU(cudaStreamSynchronize(stream));  // caller buffers may be reused after return
+        if (sync) CU(cudaStreamSynchronize(stream));  // caller buffers may be reused after return
         return PE_OK;
     }
 
@@ -526,8 +545,9 @@ struct pe_engine {
              *mark = nullptr, *rowof = nullptr, *firstof = nullptr;
     uint32_t *row_group = nullptr, *row_srow = nullptr, *task_row = nullptr;
 
-    int32_t launch_sequencer(uint32_t g0, uint32_t g1, bool with_scan) {
+    int32_t launch_sequencer(uint32_t g0, uint32_t g1, bool with_scan, const uint32_t *resume = nullptr) {
         SeqParams P;
+        P.resume = resume;
         P.T = table(); P.K = K;
         P.g_begin = g0; P.g_end = g1;
         P.scan = with_scan ? scan_out : nullptr;
@@ -610,7 +630,9 @@ struct pe_engine {
         int32_t rc;
         const uint32_t n = e - g;
         ScanParams SP;
-        if (!plan_scan(SP)) {
+        // (node sharding exchanges what the parallel placement step needs, not the class bitmaps the ordered sequencer's
+        // scan mode walks: with PE_CFG_ORDERED_ONLY a sharded engine places from the live table alone)
+        if (!plan_scan(SP) || (world > 1 && (cfg_flags & PE_CFG_ORDERED_ONLY))) {
             for (uint32_t b0 = g; b0 < e; b0 += Bmax) if ((rc = launch_sequencer(b0, std::min(e, b0 + Bmax), false))) return rc;
             return PE_OK;
         }
@@ -632,16 +654,17 @@ struct pe_engine {
         MergeParams MP;
         MP.K = K; MP.svc = SP.svc; MP.n_chunks = n_chunks; MP.rows_cap = Bmax; MP.p1 = SP.p1; MP.Lc = SP.Lc; MP.Cc = SP.Cc;
         MP.out = scan_out; MP.L = Lbuf; MP.Eall = nullptr; MP.E = E; MP.n_ranks = 1; MP.seg_words = 0; MP.e_stride = e_stride();
-        // node sharding: this rank's words of the class bitmaps go to its segment of Eall, which is all-gathered
-        const uint32_t seg_words = local_chunks * SP.tiles_per_chunk * (SP.tile_nodes / 32u);
-        if (world > 1) {
-            const size_t need = (size_t)world * Bmax * 2 * seg_words;
-            if (need > Eall_words) {
-                void *p = Eall; size_t c = Eall_words * 4;
-                if ((rc = ensure_buf(p, c, need * 4))) return rc;
-                Eall = reinterpret_cast<uint32_t *>(p); Eall_words = c / 4;
-            }
+        // the chunked parallel placement step (kernel_place.cuh) places what it can of every batch; the ordered sequencer
+        // continues from where it stopped (nothing, normally)
+        const bool parallel = !(cfg_flags & PE_CFG_ORDERED_ONLY);
+        MP.touched = nullptr; MP.touched_words = 0; MP.cursors = nullptr;
+        if (parallel) {
+            void *p = cursors; size_t c = cursors_cap;
+            if ((rc = ensure_buf(p, c, (size_t)Bmax * 8 + 64))) return rc;
+            cursors = reinterpret_cast<uint32_t *>(p); cursors_cap = c;
+            MP.touched = touched_g; MP.touched_words = (n_nodes + 31) / 32; MP.cursors = cursors;
         }
+        MP.Lx = nullptr; MP.x_cap = 0;
         auto gather = [&](void *base, size_t bytes_per_rank) -> int32_t {
             const pe_nccl::Api &nc = pe_nccl::api();
             const pe_nccl::ncclResult_t r = nc.AllGather(reinterpret_cast<char *>(base) + (size_t)rank * bytes_per_rank, base, bytes_per_rank,
@@ -659,11 +682,40 @@ struct pe_engine {
         CP.dcls = dcls; CP.scls = scls; CP.srow = srow; CP.static_reps = static_reps; CP.counters = d_cls_counters;
         k_classify<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)num_sms * 8u), 256, 0, stream>>>(CP);
         stats.kernel_launches++;
-        uint32_t h_cnt[4] = {0, 0, 0, 0};
-        CU(cudaMemcpyAsync(h_cnt, d_cls_counters, 16, cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
-        const uint32_t n_sig = h_cnt[0];
+        // How many signature bitmaps are there?  A short run (a small tick: the latency case) does not ask: it sizes for
+        // one per task, so that nothing waits on the host in the middle of the tick.
         const size_t stride = e_stride();
+        uint32_t n_sig = n, n_cls = n;      // signatures / descriptor classes of the run (upper bounds for a short run)
+        if ((size_t)n * stride * 4 > ((size_t)256 << 20)) {
+            uint32_t h_cnt[4] = {0, 0, 0, 0};
+            CU(cudaMemcpyAsync(h_cnt, d_cls_counters, 16, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            n_sig = h_cnt[0]; n_cls = h_cnt[1];
+        }
+        // ---- node sharding.  Per batch the ranks exchange: the chunks' two smallest rank prefixes (16 B per row
+        // and chunk, all-gather), the chunks' class sizes (8 B, all-gather), and the merged member lists -- x_cap members per
+        // (row, class) in ONE all-reduce over a buffer every rank fills only where its own chunks' members belong (k_xpack).
+        // No rank ever waits on the host: the arrays are strided by a bound on the rows of a batch (the run's descriptor
+        // classes), not by the batch's own row count.
+        uint32_t rcap = Bmax, x_cap = PE_LIST_CAP;
+        uint32_t *Lx = nullptr;
+        if (world > 1) {
+            rcap = std::max<uint32_t>(8u, round_up(std::min(Bmax, n_cls), 8u));
+            x_cap = 256u;
+            while (x_cap < PE_LIST_CAP && x_cap < Bmax / 4u) x_cap <<= 1;     // a batch consumes about B x (row density) members of a class
+            const size_t need = (size_t)rcap * 2 * x_cap;
+            if (need > Eall_words) {
+                void *p = Eall; size_t c = Eall_words * 4;
+                if ((rc = ensure_buf(p, c, need * 4))) return rc;
+                Eall = reinterpret_cast<uint32_t *>(p); Eall_words = c / 4;
+            }
+            Lx = Eall;
+            const size_t p1b = (size_t)n_chunks * rcap * 16, ccb = (size_t)n_chunks * rcap * 8;
+            SP.Cc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1b);
+            SP.Lc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1b + ccb);
+            SP.rows_cap = rcap;
+            MP.rows_cap = rcap; MP.Cc = SP.Cc; MP.Lc = SP.Lc; MP.Lx = Lx; MP.x_cap = x_cap;
+        }
         // signature bitmaps for the whole run when they fit in 1 GB, else one bitmap per row of each batch
         const bool cached = (size_t)n_sig * stride * 4 <= ((size_t)1 << 30);
         const size_t s_rows = cached ? n_sig : Bmax;
@@ -704,21 +756,6 @@ struct pe_engine {
             const dim3 grid(std::max((B + PE_SCAN_WARPS - 1) / PE_SCAN_WARPS, std::min(B, SP.target_ctas)), local_chunks);
             const size_t dyn = 2 * (size_t)SP.stage_bytes;
             MP.row_group = row_group; MP.n_rows = d_cls_counters + 2;
-            uint32_t rcap = Bmax;
-            if (world > 1) {
-                // the exchanged arrays are strided by the row count of THIS batch (k_rows numbers rows identically on every rank)
-                uint32_t h_rows = 0;
-                CU(cudaMemcpyAsync(&h_rows, d_cls_counters + 2, 4, cudaMemcpyDeviceToHost, stream));
-                CU(cudaStreamSynchronize(stream));
-                rcap = std::max<uint32_t>(8u, round_up(h_rows, 8u));
-                const size_t p1b = (size_t)n_chunks * rcap * 16, ccb = (size_t)n_chunks * rcap * 8;
-                SP.Cc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1b);
-                SP.Lc = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(chunk_buf) + p1b + ccb);
-                SP.rows_cap = rcap;
-                SP.Eout = Eall + (size_t)rank * rcap * 2 * seg_words; SP.e_row_stride = seg_words;
-                SP.e_word_off = SP.chunk0 * SP.tiles_per_chunk * (SP.tile_nodes / 32u);
-                MP.rows_cap = rcap; MP.Cc = SP.Cc; MP.Lc = SP.Lc; MP.Eall = Eall; MP.n_ranks = (uint32_t)world; MP.seg_words = seg_words;
-            }
             EvPair *ev = ev_begin(0);
             if (use_dyn) k_scan<true, 1><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
             else k_scan<false, 1><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
@@ -727,27 +764,62 @@ struct pe_engine {
             else k_scan<false, 2><<<grid, PE_SCAN_THREADS, dyn, stream>>>(SP);
             if (world > 1) {
                 if ((rc = gather(SP.Cc, (size_t)local_chunks * rcap * 8))) return rc;
-                if ((rc = gather(SP.Lc, (size_t)local_chunks * rcap * 2 * PE_LIST_CAP * 4))) return rc;
-                if ((rc = gather(Eall, (size_t)rcap * 2 * seg_words * 4))) return rc;
+                CU(cudaMemsetAsync(Lx, 0, (size_t)rcap * 2 * x_cap * 4, stream));
+                XPackParams XQ;
+                XQ.n_rows = d_cls_counters + 2; XQ.n_chunks = n_chunks; XQ.chunk0 = SP.chunk0; XQ.local_chunks = local_chunks; XQ.rows_cap = rcap;
+                XQ.Cc = SP.Cc; XQ.Lc = SP.Lc; XQ.Lx = Lx; XQ.x_cap = x_cap;
+                k_xpack<<<(B + 7) / 8, 256, 0, stream>>>(XQ);
+                stats.kernel_launches++;
+                const pe_nccl::Api &nc = pe_nccl::api();
+                const pe_nccl::ncclResult_t r = nc.AllReduce(Lx, Lx, (size_t)rcap * 2 * x_cap, pe_nccl::ncclUint32, pe_nccl::ncclSum, comm, stream);
+                if (r != 0) { err = std::string("ncclAllReduce: ") + nc.GetErrorString(r); return PE_ERR_CUDA; }
             }
+            DBG_SYNC("scan", b0, B);
             k_merge<<<(B + 7) / 8, 256, 0, stream>>>(MP);
             ev_end(ev);
+            DBG_SYNC("merge", b0, B);
             CU(cudaGetLastError());
             stats.kernel_launches += 3; stats.scan_launches++;
             stats.pairs += (uint64_t)B * n_nodes;
-            if ((rc = launch_sequencer(b0, b0 + B, true))) return rc;
+            if (parallel) {
+                PlaceParams PP;
+                PP.T = table(); PP.K = K; PP.b0 = b0; PP.B = B; PP.scan = scan_out; PP.task_row = task_row; PP.L = Lbuf;
+                PP.touched = touched_g; PP.cursors = cursors; PP.resume = d_cls_counters + 3; PP.ctr = d_ctr;
+                PP.list_cap = world > 1 ? x_cap : (uint32_t)PE_LIST_CAP;
+                const uint32_t tkw = (n_nodes + 31) / 32;
+                PP.tk_words = tkw <= PE_PL_TK_MAX_WORDS ? tkw : 0u;
+                EvPair *evq = ev_begin(6);
+                k_place<<<PE_PL_CLUSTER, PE_PL_THREADS, place_smem_bytes(PP.tk_words), stream>>>(PP);
+                ev_end(evq);
+                stats.kernel_launches++;
+                CU(cudaGetLastError());
+                DBG_SYNC("place", b0, B);
+            }
+            if ((rc = launch_sequencer(b0, b0 + B, world == 1, parallel ? d_cls_counters + 3 : nullptr))) return rc;
+            DBG_SYNC("sequencer", b0, B);
         }
         return PE_OK;
     }
 
+    DevCounters *h_ctr = nullptr;      // pinned landing area of the device counters
+
     int32_t tick_run() {
+        int32_t rc = tick_enqueue();
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(stream));
+        return counters_finish();
+    }
+
+    // everything of pe_tick_run that is stream work; the counters come back asynchronously into pinned memory
+    int32_t tick_enqueue() {
         int32_t rc;
         if ((rc = sync_tabs())) return rc;
         if ((rc = ensure_scratch())) return rc;
         // batch = tasks placed against one scan.  A wave of the scan kernel, but not more than a sixteenth of the nodes: a
         // batch that touches most of the nodes consumes its own rank classes and falls back to re-ranking per task
         const uint32_t wave = (uint32_t)num_sms * 2u * PE_SCAN_WARPS;
-        const uint32_t Bmax = max_batch ? max_batch : std::min(wave, std::max(256u, round_up(n_nodes / 16u, 16u)));
+        // (a multiple of 8, at least 8: the multi-rank exchange strides its arrays by the batch's row count rounded up to 8)
+        const uint32_t Bmax = max_batch ? std::max(8u, round_up(max_batch, 8u)) : std::min(wave, std::max(256u, round_up(n_nodes / 16u, 16u)));
         const bool spec = !(cfg_flags & PE_CFG_NO_SPECULATION) && n_nodes > 0;
         if (spec) {
             size_t need = (size_t)Bmax * 2u * e_stride();   // two class rows per scan row
@@ -779,14 +851,26 @@ struct pe_engine {
             }
         }
         ev_end(ev_run);
-        CU(cudaStreamSynchronize(stream));
-        return collect_counters();
+        return counters_enqueue();
     }
 
-    int32_t collect_counters() {
-        DevCounters c;
-        CU(cudaMemcpy(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost));
-        CU(cudaMemset(d_ctr, 0, sizeof c));
+    int32_t counters_enqueue() {
+        if (!h_ctr) CU(cudaMallocHost(reinterpret_cast<void **>(&h_ctr), sizeof(DevCounters)));
+        CU(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
+        return PE_OK;
+    }
+
+    int32_t collect_counters() {       // (synchronous form: pe_fit)
+        int32_t rc = counters_enqueue();
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(stream));
+        return counters_finish();
+    }
+
+    // after the stream has drained
+    int32_t counters_finish() {
+        const DevCounters &c = *h_ctr;
         stats.fast_path += c.fast_path; stats.medium_path += c.medium_path; stats.slow_path += c.slow_path;
         stats.placements += c.placements; stats.evals_generic += c.evals_generic;
         stats.seq_cycles_fast += c.cyc_fast; stats.seq_cycles_medium += c.cyc_medium; stats.seq_cycles_generic += c.cyc_generic;
@@ -794,6 +878,9 @@ struct pe_engine {
         for (int r = 0; r < 16; r++) stats.seq_prof[r] += c.prof[r];
         stats.seq_cons_wait += c.cyc_cons_wait; stats.seq_cons_work += c.cyc_cons_work; stats.seq_rewalks += c.iters;
         stats.evals += c.scan_evals; stats.scan_bytes += c.scan_bytes; stats.static_evals += c.static_evals; stats.scan_rows += c.scan_rows;
+        stats.place_tasks += c.place_tasks; stats.place_cuts += c.place_cuts; stats.place_amb += c.place_amb; stats.place_tails += c.place_tails;
+        stats.place_chunks += c.place_chunks;
+        for (int r = 0; r < 3; r++) stats.place_cyc[r] += c.place_cyc[r];
         ev_collect();
         if (c.error & (PE_DEV_ERR_WD_CONSUMER | PE_DEV_ERR_WD_DRAIN | PE_DEV_ERR_WD_SCAN)) {
             char b[160]; snprintf(b, sizeof b, "device watchdog fired (code 0x%x): a kernel pipeline stalled for more than a second", c.error);
@@ -803,11 +890,12 @@ struct pe_engine {
         return PE_OK;
     }
 
-    int32_t tick_download(uint32_t *out_node, uint32_t *out_fail) {
+    int32_t tick_download(uint32_t *out_node, uint32_t *out_fail, bool sync = true) {
         EvPair *ev = ev_begin(3);
         if (out_node && n_tasks) { CU(cudaMemcpyAsync(out_node, d_out_node, (size_t)n_tasks * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (size_t)n_tasks * 4; }
         if (out_fail && n_groups) { CU(cudaMemcpyAsync(out_fail, d_out_fail, (size_t)n_groups * PE_NUM_FILTERS * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (size_t)n_groups * PE_NUM_FILTERS * 4; }
         ev_end(ev);
+        if (!sync) return PE_OK;
         CU(cudaStreamSynchronize(stream));
         ev_collect();
         return PE_OK;
@@ -828,6 +916,11 @@ struct pe_engine {
         if (out_fail) CU(cudaMemcpyAsync(out_fail, d_out_fail, (size_t)n_groups * PE_NUM_FILTERS * 4, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         return collect_counters();
+    }
+
+    int32_t finish_schedule() {
+        CU(cudaStreamSynchronize(stream));
+        return counters_finish();      // (also collects the event timings)
     }
 
     template <class T> int32_t snap_col(const T *col, uint32_t first, uint32_t n, T *out) {
@@ -882,10 +975,12 @@ int32_t pe_tick_run(pe_engine *h) { return h->tick_run(); }
 int32_t pe_tick_download(pe_engine *h, uint32_t *out_node, uint32_t *out_fail) { return h->tick_download(out_node, out_fail); }
 
 int32_t pe_schedule(pe_engine *h, const pe_tick *tick, uint32_t *out_node, uint32_t *out_fail) {
-    int32_t rc = h->tick_upload(tick);
+    // one wait for the whole call: descriptors in, kernels, placements + counters out, all in stream order
+    int32_t rc = h->tick_upload(tick, false);
     if (rc) return rc;
-    if ((rc = h->tick_run())) return rc;
-    return h->tick_download(out_node, out_fail);
+    if ((rc = h->tick_enqueue())) return rc;
+    if ((rc = h->tick_download(out_node, out_fail, false))) return rc;
+    return h->finish_schedule();
 }
 
 int32_t pe_fit(pe_engine *h, const pe_tick *tick, const uint32_t *node_idx, uint8_t *out_ok, uint32_t *out_fail) {

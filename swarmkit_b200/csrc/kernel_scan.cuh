@@ -32,7 +32,8 @@ namespace pe {
 #define PE_SCAN_MAXCOLS 32
 #define PE_SCAN_MAXGENK 16
 #define PE_SCAN_MAXW 8         // port bit words
-#define PE_LIST_CAP 1024       // class members listed explicitly per class (the sequencer's fast path reads these)
+#define PE_LIST_CAP 4096       // class members listed explicitly per class: what the placement step walks.  A batch can
+                               // consume about PE_LIST_CAP members of one class before that row has to wait for the next scan
 
 struct ScanCol {
     const void *base;
@@ -79,7 +80,44 @@ struct MergeParams {
     uint32_t *L;                 // member lists [row][2][PE_LIST_CAP]
     // multi-GPU: gathered bitmap segments [rank][rows_cap][2][seg_words] -> canonical rows [row][2][e_stride]
     const uint32_t *Eall; uint32_t *E; uint32_t n_ranks, seg_words, e_stride;
+    // per-batch state of the placement step (kernel_place.cuh), zeroed here: touched bitmap, list cursors [rows_cap][2]
+    uint32_t *touched; uint32_t touched_words;
+    uint32_t *cursors;
+    // node sharding: the lists arrive already merged over the ranks (k_xpack + all-reduce), x_cap members per class
+    const uint32_t *Lx; uint32_t x_cap;
 };
+
+// Node sharding: what one rank contributes to the merged member lists.  The merged list of (row, class) is the
+// concatenation of the chunks' lists in chunk (= node) order, cut at x_cap; every rank knows every chunk's member count
+// (all-gathered), so it knows where its own chunks' members land and writes them there into a zeroed buffer -- the
+// all-reduce(sum) of those buffers is the merged list on every rank, with x_cap * 4 bytes per (row, class) on the wire
+// instead of one full list per rank.
+struct XPackParams {
+    const uint32_t *n_rows;
+    uint32_t n_chunks, chunk0, local_chunks, rows_cap;
+    const uint32_t *Cc, *Lc;
+    uint32_t *Lx;                // [rows_cap][2][x_cap], zeroed
+    uint32_t x_cap;
+};
+
+__global__ void __launch_bounds__(256) k_xpack(const XPackParams P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= *P.n_rows) return;
+    for (uint32_t cls = 0; cls < 2u; cls++) {
+        uint32_t pos = 0;
+        for (uint32_t g = 0; g < P.chunk0 + P.local_chunks && pos < P.x_cap; g++) {
+            const uint32_t n = min(P.Cc[((size_t)g * P.rows_cap + row) * 2u + cls], (uint32_t)PE_LIST_CAP);
+            const uint32_t take = min(n, P.x_cap - pos);
+            if (g >= P.chunk0) {
+                const uint32_t *src = P.Lc + (((size_t)g * P.rows_cap + row) * 2u + cls) * PE_LIST_CAP;
+                uint32_t *dst = P.Lx + ((size_t)row * 2u + cls) * P.x_cap + pos;
+                for (uint32_t j = lane; j < take; j += 32u) dst[j] = src[j];
+            }
+            pos += take;
+        }
+    }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -339,7 +377,10 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams P) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t n_rows = *P.n_rows;
+    if (P.touched != nullptr)
+        for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < P.touched_words; w += gridDim.x * blockDim.x) P.touched[w] = 0u;
     if (row >= n_rows) return;
+    if (P.cursors != nullptr && lane < 2u) P.cursors[(size_t)row * 2u + lane] = 0u;
     unsigned long long c0, c1;
     merge_p1(P.p1, P.n_chunks, P.rows_cap, row, lane, c0, c1);
     uint32_t tot[2] = {0, 0};
@@ -349,10 +390,16 @@ __global__ void __launch_bounds__(256) k_merge(const MergeParams P) {
         for (uint32_t g = 0; g < P.n_chunks; g++) {
             const uint32_t n = P.Cc[((size_t)g * P.rows_cap + row) * 2u + cls];
             tot[cls] += n;
+            if (P.Lx != nullptr) continue;
             const uint32_t take = min(min(n, (uint32_t)PE_LIST_CAP), (uint32_t)PE_LIST_CAP - pos);
             const uint32_t *src = P.Lc + (((size_t)g * P.rows_cap + row) * 2u + cls) * PE_LIST_CAP;
             for (uint32_t j = lane; j < take; j += 32u) dst[pos + j] = src[j];
             pos += take;
+        }
+        if (P.Lx != nullptr) {      // the merged list of every rank's chunks (k_xpack + all-reduce)
+            const uint32_t take = min(tot[cls], P.x_cap);
+            const uint32_t *src = P.Lx + ((size_t)row * 2u + cls) * P.x_cap;
+            for (uint32_t j = lane; j < take; j += 32u) dst[j] = src[j];
         }
     }
     if (P.Eall != nullptr) {

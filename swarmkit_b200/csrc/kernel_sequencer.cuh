@@ -44,6 +44,7 @@ __device__ __forceinline__ bool key_less(const CandKey &a, const CandKey &b) {
 #define PE_SEQ_PROFILE 0        // 1: the consumer warp also tallies wait / work cycles (diagnostic builds)
 #endif
 #define PE_SEQ_THREADS 512     // 128 registers per thread: the ordered fast path must not spill
+#define PE_SEQ_LISTED 1024      // members of a class list this kernel looks at (the lists hold PE_LIST_CAP; beyond -> class bitmap)
 #define PE_SEQ_KS 2048          // candidates staged in shared memory
 #define PE_SEQ_RING 64          // fast-mode ring slots (copies are started this far ahead of the ordered warp)
 #define PE_SEQ_NPW 11           // producer warps: 1-3, 5-7, 9-11, 13-14.  Warp 15 commits; warps 4, 8, 12 sit fast mode out so
@@ -121,6 +122,9 @@ struct SeqParams {
     uint32_t *touched_g;          // [touched_words] global fallback
     uint32_t touched_words;
     uint32_t touched_in_smem;
+    // continuation of a batch the chunked parallel placement step (kernel_place.cuh) began: start at task *resume of the
+    // batch (nothing to do if that is the batch's end) with the touched bitmap it left in touched_g
+    const uint32_t *resume;
     DevCounters *ctr;
 };
 
@@ -348,7 +352,7 @@ __device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared 
     const uint32_t cur2 = row < (uint32_t)PE_SEQ_ROWCUR ? (rowcur2[row] & ~31u) : 0u;
     uint32_t v2[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { const uint32_t idx = cur2 + (uint32_t)k * 32u + lane; v2[k] = idx < (uint32_t)PE_LIST_CAP ? L2[idx] : 0u; }
+    for (int k = 0; k < 4; k++) { const uint32_t idx = cur2 + (uint32_t)k * 32u + lane; v2[k] = idx < (uint32_t)PE_SEQ_LISTED ? L2[idx] : 0u; }
     const unsigned long long c1 = sr->c1;
     const uint4 meta = *reinterpret_cast<const uint4 *>(&sr->n0);   // n0, n1, tie_start, flags
     const uint32_t *svccol = sr->svccol;
@@ -357,8 +361,8 @@ __device__ __forceinline__ uint32_t inline_medium(const SeqParams &P, SeqShared 
     (void)gq;
     const uint32_t head1 = L1[lane];                                 // (rows are PE_LIST_CAP long: in bounds)
     const uint32_t n0 = meta.x, n1 = meta.y;
-    if (c1 == PE_PREF_NONE || n0 > (uint32_t)PE_LIST_CAP) return PE_NONE;
-    const uint32_t nl = min(n1, (uint32_t)PE_LIST_CAP);
+    if (c1 == PE_PREF_NONE || n0 > (uint32_t)PE_SEQ_LISTED) return PE_NONE;
+    const uint32_t nl = min(n1, (uint32_t)PE_SEQ_LISTED);
     uint32_t n2 = PE_NONE;
     for (uint32_t j = cur2; j < nl && n2 == PE_NONE; j += 128u) {
         if (j != cur2) {
@@ -761,7 +765,7 @@ __device__ __forceinline__ ProdTask stage_issue(const SeqParams &P, SeqShared &S
             // list mode: stage the window of the member list that starts at the row's cursor (every member
             // before the cursor is known to be touched: tasks that share the row, and windows already walked)
             if (meta.z == 0u && valid) {
-                t.n_listed = min(meta.x, (uint32_t)PE_LIST_CAP);
+                t.n_listed = min(meta.x, (uint32_t)PE_SEQ_LISTED);
                 t.base = row < (uint32_t)PE_SEQ_ROWCUR ? (min(rowcur[row], t.n_listed - 1u) & ~3u) : 0u;
                 t.n_list = min(t.n_listed - t.base, (uint32_t)PE_SEQ_WIN);
             }
@@ -972,9 +976,16 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     uint32_t *ring = reinterpret_cast<uint32_t *>(dyn_smem);   // [PE_SEQ_RING][PE_SEQ_WIN]
     uint32_t *rowcur = ring + PE_SEQ_RING * PE_SEQ_WIN;        // [PE_SEQ_ROWCUR]
     uint32_t *rowcur2 = rowcur + PE_SEQ_ROWCUR;                // second-class cursors (inline_medium)
+    uint32_t gi = P.g_begin;
+    if (P.resume != nullptr) {
+        const uint32_t r = *P.resume;
+        if (r >= P.g_end - P.g_begin) return;        // the parallel step placed the whole batch
+        gi += r;
+    }
     if (P.scan != nullptr) for (uint32_t r = tid; r < 2u * PE_SEQ_ROWCUR; r += nth) rowcur[r] = 0;
 
-    for (uint32_t w = tid; w < P.touched_words; w += nth) touched[w] = 0;
+    if (P.resume == nullptr) { for (uint32_t w = tid; w < P.touched_words; w += nth) touched[w] = 0; }
+    else if (P.touched_in_smem) { for (uint32_t w = tid; w < P.touched_words; w += nth) touched_s[w] = P.touched_g[w]; }
     if (tid == 0) { S.neutral = 0; S.bars_live = 0; S.bestv[0] = S.bestv[1] = S.bestv[2] = PE_NONE; }
     uint32_t slot = 0;   // uniform across the block
     unsigned long long n_fast = 0, n_medium = 0, n_slow = 0, n_placed = 0, n_evalg = 0;
@@ -982,7 +993,6 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
     SeqDebug dbg{};   // thread 0's private tallies
     __syncthreads();
 
-    uint32_t gi = P.g_begin;
     while (gi < P.g_end) {
         // ================= fast mode: warp-specialised pipeline over k == 1 tasks ====
         // (see the comment above fast_consumer).  The mode ends at the first task the
@@ -1078,7 +1088,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                 const uint32_t *L1 = P.L + (size_t)srow * 2u * PE_LIST_CAP;
                 const uint32_t *L2 = L1 + PE_LIST_CAP;
                 if (use_lists && sr.n1 > 0u) {
-                    const uint32_t nl = min(sr.n1, (uint32_t)PE_LIST_CAP);
+                    const uint32_t nl = min(sr.n1, (uint32_t)PE_SEQ_LISTED);
                     uint32_t c = PE_NONE;
                     for (uint32_t t = tid; t < nl && c == PE_NONE; t += nth) { const uint32_t p2 = L2[t]; if (!((touched[p2 >> 5] >> (p2 & 31u)) & 1u)) c = t; }
                     const uint32_t at = block_min_pos(c, S, slot);
@@ -1099,7 +1109,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
                         const uint32_t tp = tie_pos(n, G.tie_start, N);
                         if (pref < bp || (pref == bp && tp < bt)) { bp = pref; bt = tp; bn = n; }
                     };
-                    if (use_lists && sr.n0 <= (uint32_t)PE_LIST_CAP) {
+                    if (use_lists && sr.n0 <= (uint32_t)PE_SEQ_LISTED) {
                         // the complete best class is listed: one member per thread
                         for (uint32_t t = tid; t < sr.n0; t += nth) {
                             const uint32_t n = L1[t];

@@ -1,4 +1,4 @@
-// nccl_dl.h -- the five NCCL entry points the engine uses, resolved at run time.
+// nccl_dl.h -- the six NCCL entry points the engine uses, resolved at run time.
 //
 // The engine is a plain C-ABI shared library; NCCL is only needed when
 // pe_config.world_size > 1 (node-sharded scan), so it is not a link
@@ -14,13 +14,15 @@ namespace pe_nccl {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;          // 0 = ncclSuccess
-enum { ncclUint8 = 1 };
+enum { ncclUint8 = 1, ncclUint32 = 3 };   // ncclDataType_t
+enum { ncclSum = 0 };                     // ncclRedOp_t
 
 struct Api {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -36,8 +38,9 @@ inline const Api &api() {
         r.CommInitRank = reinterpret_cast<decltype(r.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
         r.CommDestroy = reinterpret_cast<decltype(r.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
         r.AllGather = reinterpret_cast<decltype(r.AllGather)>(dlsym(h, "ncclAllGather"));
+        r.AllReduce = reinterpret_cast<decltype(r.AllReduce)>(dlsym(h, "ncclAllReduce"));
         r.GetErrorString = reinterpret_cast<decltype(r.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-        r.ok = r.GetUniqueId && r.CommInitRank && r.CommDestroy && r.AllGather && r.GetErrorString;
+        r.ok = r.GetUniqueId && r.CommInitRank && r.CommDestroy && r.AllGather && r.AllReduce && r.GetErrorString;
         return r;
     }();
     return a;

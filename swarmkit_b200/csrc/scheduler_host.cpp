@@ -389,7 +389,8 @@ struct Decision { TaskP old_, new_; };
 
 struct Scheduler {
     pe_engine *eng = nullptr;
-    std::string fatal;   // engine / unsupported-feature error, surfaced to the caller
+    std::string fatal;   // engine error, surfaced to the caller (the call failed; nothing was lost: see scheduleTaskGroups)
+    std::string unsupported;   // first group of the last tick the engine could not take (its tasks stayed pending)
     std::map<std::string, TaskP> unassignedTasks, pendingPreassignedTasks, allTasks;
     std::set<std::string> preassignedTasks;
     std::map<std::string, NodeInfo> nodeSet;   // ordered: row index = rank of the node ID
@@ -614,6 +615,10 @@ struct Scheduler {
     struct TickBuf {
         std::vector<pe_group> groups; std::vector<uint8_t> flags; std::vector<pe_generic_want> gens; std::vector<pe_constraint> cons;
         std::vector<pe_ip_constraint> ips; std::vector<pe_platform> plats; std::vector<uint32_t> ports, plugs; std::vector<pe_node_fail> fails;
+        // countRecentFailures(now) per node, built ONCE per tick from the nodes that hold failure records at all and
+        // shared by every group of the same (service, spec version): (offset, count) into `fails`
+        bool fails_built = false;
+        std::map<SvcVer, std::pair<uint32_t, uint32_t>> fail_range;
         pe_tick view() const {
             pe_tick t{};
             t.groups = groups.data(); t.n_groups = (uint32_t)groups.size();
@@ -682,9 +687,10 @@ struct Scheduler {
         if (never) g.flags |= PE_G_CONSTRAINT_NEVER;
         return true;
     }
-    bool encode_group(const std::vector<TaskP> &tasks, TickBuf &b) {
+    bool encode_group(const std::vector<TaskP> &tasks, TickBuf &b, bool for_fit = false) {
         const Task &t = *tasks[0];
-        if (t.has_placement && !t.preferences.empty()) { fatal = "placement preferences are not supported by the placement engine yet (task " + t.id + ")"; return false; }
+        // (taskFitNode checks one named node: placement preferences play no part there, scheduler.go:646-690)
+        if (!for_fit && t.has_placement && !t.preferences.empty()) { fatal = "placement preferences are not supported by the placement engine yet (task " + t.id + ")"; return false; }
         for (auto &m : t.mounts) if (m.type == MountCluster) { fatal = "CSI cluster volumes are not supported by the placement engine (task " + t.id + ")"; return false; }
         pe_group g{};
         g.log_plugin = PE_NONE;
@@ -729,19 +735,29 @@ struct Scheduler {
         if (g.port_cnt) g.filter_mask |= 1u << PE_F_HOSTPORT;                                           // filter.go:328-339
         if (t.has_placement && t.max_replicas > 0) { g.filter_mask |= 1u << PE_F_MAXREPLICAS; g.max_replicas = t.max_replicas; }   // filter.go:369-376
         // countRecentFailures per node (scheduler.go:711-712); only nodes that have an entry
-        g.fail_off = (uint32_t)b.fails.size();
-        SvcVer key{t.service, t.has_spec_version ? t.spec_version : 0};
+        if (!b.fails_built) build_fail_lists(b);
+        auto fr = b.fail_range.find(SvcVer{t.service, t.has_spec_version ? t.spec_version : 0});
+        if (fr != b.fail_range.end()) { g.fail_off = fr->second.first; g.fail_cnt = fr->second.second; }
+        b.groups.push_back(g);
+        return true;
+    }
+    // One walk over the node set per tick (not per group): nodes are visited in row order, so every key's list comes out
+    // sorted by node index, which is what pe_node_fail asks for.
+    void build_fail_lists(TickBuf &b) {
+        std::map<SvcVer, std::vector<pe_node_fail>> per_key;
         uint32_t idx = 0;
         for (auto &kv : nodeSet) {
-            if (!kv.second.failures.empty()) {
-                int c = kv.second.countRecentFailures(now, key);
-                if (c > 0) b.fails.push_back({idx, (uint32_t)c});
+            for (auto &f : kv.second.failures) {
+                int c = kv.second.countRecentFailures(now, f.first);
+                if (c > 0) per_key[f.first].push_back({idx, (uint32_t)c});
             }
             idx++;
         }
-        g.fail_cnt = (uint32_t)b.fails.size() - g.fail_off;
-        b.groups.push_back(g);
-        return true;
+        for (auto &kv : per_key) {
+            b.fail_range[kv.first] = {(uint32_t)b.fails.size(), (uint32_t)kv.second.size()};
+            b.fails.insert(b.fails.end(), kv.second.begin(), kv.second.end());
+        }
+        b.fails_built = true;
     }
 
     // Pipeline.Explain, pipeline.go:84-103 + filter.go Explain methods
@@ -767,14 +783,33 @@ struct Scheduler {
     }
 
     // scheduleTaskGroup for every group of the tick in ONE engine call (scheduler.go:464-469,694-748)
-    bool scheduleTaskGroups(std::vector<std::vector<TaskP>> &groups, std::map<std::string, Decision> &decisions) {
-        if (groups.empty()) return true;
+    // A group the engine cannot take (see encode_group) does not stop the tick: its tasks stay pending with the reason in
+    // Status.Err, exactly like tasks without a suitable node (scheduler.go:958-962), and every other group is scheduled.
+    // If the engine itself fails, every task goes back to the queue and the device mirror is rebuilt from the host's
+    // NodeInfo on the next call (the device rows may have moved part-way).
+    bool scheduleTaskGroups(std::vector<std::vector<TaskP>> &all_groups, std::map<std::string, Decision> &decisions) {
+        if (all_groups.empty()) return true;
         TickBuf b;
-        for (auto &g : groups) if (!encode_group(g, b)) return false;
-        if (!flush_rows()) return false;     // after encoding: new label columns / plugin slots force a re-upload
+        std::vector<std::vector<TaskP>> groups;
+        std::string first_unsupported;
+        for (auto &g : all_groups) {
+            TickBuf probe = b;                      // (an encoder that gives up half-way must leave no side arrays behind)
+            fatal.clear();
+            if (encode_group(g, probe)) { b = std::move(probe); groups.push_back(g); continue; }
+            if (first_unsupported.empty()) first_unsupported = fatal;
+            noSuitableNode(g, "unsupported by the placement engine: " + fatal, decisions);
+        }
+        fatal.clear();
+        unsupported = first_unsupported;
+        if (groups.empty()) return true;
+        auto give_back = [&]() {
+            for (auto &g : groups) for (auto &t : g) enqueue(t);
+            layout_dirty = true;
+        };
+        if (!flush_rows()) { give_back(); return false; }     // after encoding: new label columns / plugin slots force a re-upload
         std::vector<uint32_t> out_node(b.flags.size(), PE_NONE), out_fail(b.groups.size() * PE_NUM_FILTERS, 0);
         pe_tick tk = b.view();
-        if (!check(pe_schedule(eng, &tk, out_node.data(), out_fail.data()), "pe_schedule")) return false;
+        if (!check(pe_schedule(eng, &tk, out_node.data(), out_fail.data()), "pe_schedule")) { give_back(); return false; }
         for (size_t gi = 0; gi < groups.size(); gi++) {
             auto &grp = groups[gi];
             std::vector<TaskP> left;
@@ -837,7 +872,7 @@ struct Scheduler {
         for (auto &kv : pendingPreassignedTasks) if (nodeSet.count(kv.second->node_id)) pend.push_back(kv.second);
         if (pend.empty()) return true;
         TickBuf b;
-        for (auto &t : pend) { std::vector<TaskP> one{t}; if (!encode_group(one, b)) return false; }
+        for (auto &t : pend) { std::vector<TaskP> one{t}; if (!encode_group(one, b, true)) return false; }
         if (!flush_rows()) return false;
         std::vector<uint32_t> idx; for (auto &t : pend) idx.push_back(node_index(t->node_id));
         std::vector<uint8_t> ok(pend.size(), 0); std::vector<uint32_t> fail(pend.size() * PE_NUM_FILTERS, 0);
@@ -904,6 +939,7 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         bool ok = op == "tick" ? S.tick(strset(ev.at("fail_commit")), ds) : S.processPreassignedTasks(strset(ev.at("fail_commit")), ds);
         if (!ok) { out.set("error", mj::Value::string(S.fatal)); return out; }
         out.set("decisions", decisions_json(ds));
+        if (!S.unsupported.empty()) out.set("unsupported", mj::Value::string(S.unsupported));   // those tasks stayed pending
     } else if (op == "snapshot" || op == "device_check") {
         if (!S.flush_rows()) { out.set("error", mj::Value::string(S.fatal)); return out; }
         mj::Value arr = mj::Value::array(), bad = mj::Value::array();

@@ -39,8 +39,14 @@ def path(name: str) -> str:
     return os.path.join(HERE, name + ".npz")
 
 
+_CACHE = {}
+
+
 def workload(name: str):
-    return CASES[name]()
+    """The seeded workload of a case (cached: the generators take seconds at these sizes; callers must not mutate it)."""
+    if name not in _CACHE:
+        _CACHE[name] = CASES[name]()
+    return _CACHE[name]
 
 
 def load(name: str):

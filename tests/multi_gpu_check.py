@@ -35,6 +35,26 @@ def main():
         ("cfg1", W.cfg1(), 1),
     ]
     ok = True
+    # the headline shape at its real node count and batch size, against the committed golden vector (no oracle run needed)
+    from tests.golden import make_golden_big as GB
+    wh = GB.workload("big_cfg3_oneoff_1m_100k")
+    gold, _ = GB.load("big_cfg3_oneoff_1m_100k")
+    box = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    eng = PlacementEngine(node_capacity=wh.n_nodes, device=local, rank=rank, world_size=world, nccl_id=box[0])
+    eng.node_upsert(wh.nodes)
+    eng.set_node_count(wh.n_nodes)
+    sub = wh.tick.slice_groups(0, 40_000)
+    out_node, _ = eng.schedule(sub)
+    bad = int((out_node != gold[:sub.n_tasks]).sum())
+    flag = torch.tensor([bad], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        st = eng.stats()
+        print(f"cfg3-headline-40k: mismatches(max over ranks)={int(flag.item())} place_tasks={st['place_tasks']} handed_over={st['place_cuts']}", flush=True)
+        ok = ok and int(flag.item()) == 0
+    eng.close()
+    dist.barrier()
     for name, w, n_svc in cases:
         box = [nccl_unique_id() if rank == 0 else None]      # one communicator (one id) per engine group
         dist.broadcast_object_list(box, src=0)

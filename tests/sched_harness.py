@@ -37,6 +37,8 @@ class JsonScheduler:
             self._free(p)
         if "error" in out:
             raise RuntimeError(out["error"])
+        if "unsupported" in out:   # the tick went through, but some group stayed pending: the scenarios treat that as a failure
+            raise RuntimeError(out["unsupported"])
         return out
 
     def close(self):
