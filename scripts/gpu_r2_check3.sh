@@ -1,10 +1,10 @@
 #!/bin/bash
 # round 2: full GPU suite, then the bench at two batch sizes (parity, latency arm included)
 mkdir -p gpurun_out
-echo "== gpu suite"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
-for mb in 0 16384; do
+echo "== gpu suite"; timeout 900 python -m pytest tests/test_headline_gpu.py -q -x 2>&1 | tail -6
+for mb in 16384; do
   echo "== bench max_batch=$mb"
-  timeout 300 python bench.py --steps 3 --warmup 3 --cpu-sample 3000 --max-batch $mb 2>&1 | tail -2 | tee gpurun_out/r2m_bench_mb$mb.json | python -c "
+  timeout 300 python bench.py --steps 3 --warmup 3 --cpu-sample 3000 --max-batch $mb 2>&1 | tail -2 | tee gpurun_out/r2o_bench_mb$mb.json | python -c "
 import sys, json
 for l in sys.stdin:
     try: d = json.loads(l)

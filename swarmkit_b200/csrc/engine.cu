@@ -22,6 +22,7 @@
 #include "kernel_scan.cuh"
 #include "kernel_sequencer.cuh"
 #include "kernel_place.cuh"
+#include "kernel_groups.cuh"
 
 using namespace pe;
 
@@ -113,6 +114,8 @@ struct pe_engine {
     uint32_t *d_cls_counters = nullptr;              // [0] signatures [1] classes [2] rows of the current batch [3] where the
                                                      //     parallel placement step stopped in the current batch
     uint32_t *cursors = nullptr; size_t cursors_cap = 0;   // [rows][2] class-list cursors of the placement step
+    void *groups_buf = nullptr;                            // scratch of k_groups: class table | GroupSel | per-CTA class counts
+    int groups_grid = 0;                                   // CTAs of the cooperative launch (0: not available)
     DevCounters *d_ctr = nullptr;
     void *up_buf = nullptr; size_t up_cap = 0;  // upload arena for upsert / delta / fit
 
@@ -152,6 +155,20 @@ struct pe_engine {
         CU(cudaMalloc(&d_cls_counters, 16));
         CU(cudaMemsetAsync(d_ctr, 0, sizeof(DevCounters), stream));
         CU(cudaFuncSetAttribute(k_sequencer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_dyn_smem_bytes(12288)));
+        // task groups (k > 1) on every SM: one persistent cooperative kernel, one CTA per SM (kernel_groups.cuh)
+        {
+            int coop = 0, per_sm = 0;
+            CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+            CU(cudaFuncSetAttribute(k_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)groups_smem_bytes()));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_groups, PE_GR_THREADS, groups_smem_bytes()));
+            groups_grid = (coop && per_sm > 0) ? num_sms : 0;
+            if (groups_grid) {
+                const size_t bytes = (size_t)PE_GR_TABLE * 12 + sizeof(GroupSel) + (size_t)groups_grid * PE_GR_MAXCLS * 4 + 64;
+                CU(cudaMalloc(&groups_buf, bytes));
+                CU(cudaMemsetAsync(groups_buf, 0, bytes, stream));
+                CU(cudaMemsetAsync(groups_buf, 0xFF, (size_t)PE_GR_TABLE * 8, stream));      // class keys: all ones = empty
+            }
+        }
         CU(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem_bytes(PE_PL_TK_MAX_WORDS)));
         CU(cudaFuncSetAttribute(k_scan<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CU(cudaFuncSetAttribute(k_scan<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -177,7 +194,7 @@ struct pe_engine {
         for (auto p : gen) fr(p);
         for (auto p : d_tab) fr(p);
         fr(tick_buf); fr(d_out_node); fr(d_out_fail); fr(ff8); fr(pref64); fr(cand_g); fr(st_cpu_g); fr(st_mem_g); fr(st_gen_g);
-        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters); fr(chunk_buf); fr(cursors);
+        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters); fr(chunk_buf); fr(cursors); fr(groups_buf);
         if (h_ctr) cudaFreeHost(h_ctr);
         for (auto &p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         if (stream) cudaStreamDestroy(stream);
@@ -569,6 +586,29 @@ struct pe_engine {
         return PE_OK;
     }
 
+    // A run of task groups: k_groups takes them one after the other on the whole machine; whatever it stops in front of
+    // (a group with too many distinct rank prefixes) goes to the one-CTA path, which is exact for anything.
+    int32_t launch_groups(uint32_t g0, uint32_t g1) {
+        GroupsParams P;
+        P.T = table(); P.K = K; P.g_begin = g0; P.g_end = g1;
+        P.ff8 = ff8; P.pref64 = pref64; P.cand_g = cand_g;
+        P.st_cpu_g = st_cpu_g; P.st_mem_g = st_mem_g; P.st_gen_g = st_gen_g; P.st_svc_g = st_svc_g; P.st_tot_g = st_tot_g;
+        P.st_placed_g = st_placed_g; P.st_flags_g = st_flags_g; P.st_cap = st_cap;
+        char *b = reinterpret_cast<char *>(groups_buf);
+        P.cls_key = reinterpret_cast<unsigned long long *>(b);
+        P.cls_cnt = reinterpret_cast<uint32_t *>(b + (size_t)PE_GR_TABLE * 8);
+        P.sel = reinterpret_cast<GroupSel *>(b + (size_t)PE_GR_TABLE * 12);
+        P.cntmat = reinterpret_cast<uint32_t *>(b + (size_t)PE_GR_TABLE * 12 + sizeof(GroupSel));
+        P.resume = d_cls_counters + 3; P.ctr = d_ctr;
+        void *args[] = {&P};
+        EvPair *ev = ev_begin(1);
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_groups), dim3((unsigned)groups_grid), dim3(PE_GR_THREADS), args, groups_smem_bytes(), stream));
+        ev_end(ev);
+        stats.kernel_launches++;
+        DBG_SYNC("groups", g0, g1 - g0);
+        return launch_sequencer(g0, g1, false, d_cls_counters + 3);
+    }
+
     // Which columns ride in the scan's node tiles and the tile size, from what the
     // k == 1 groups of the staged tick use.  Returns false if the scan cannot stage it.
     bool plan_scan(ScanParams &P) {
@@ -815,11 +855,12 @@ struct pe_engine {
         int32_t rc;
         if ((rc = sync_tabs())) return rc;
         if ((rc = ensure_scratch())) return rc;
-        // batch = tasks placed against one scan.  A wave of the scan kernel, but not more than a sixteenth of the nodes: a
-        // batch that touches most of the nodes consumes its own rank classes and falls back to re-ranking per task
-        const uint32_t wave = (uint32_t)num_sms * 2u * PE_SCAN_WARPS;
+        // batch = tasks placed against one scan.  Every batch costs one scan of (distinct descriptors x nodes), so batches
+        // want to be long; a batch that consumes more of a row's class than its member list holds (PE_LIST_CAP, about
+        // batch x the row's node density) hands the rest to the ordered sequencer, so they must not be too long: a sixth of
+        // the nodes, at most 16384 (measured on cfg3: 4736 -> 16384 takes the scan from 115 to 34 ms per million tasks).
         // (a multiple of 8, at least 8: the multi-rank exchange strides its arrays by the batch's row count rounded up to 8)
-        const uint32_t Bmax = max_batch ? std::max(8u, round_up(max_batch, 8u)) : std::min(wave, std::max(256u, round_up(n_nodes / 16u, 16u)));
+        const uint32_t Bmax = max_batch ? std::max(8u, round_up(max_batch, 8u)) : std::min(16384u, std::max(256u, round_up(n_nodes / 6u, 16u)));
         const bool spec = !(cfg_flags & PE_CFG_NO_SPECULATION) && n_nodes > 0;
         if (spec) {
             size_t need = (size_t)Bmax * 2u * e_stride();   // two class rows per scan row
@@ -846,6 +887,8 @@ struct pe_engine {
             // maximal run of k == 1 groups -> batched scan path; anything else -> sequencer alone
             if (r.one && spec && r.end - r.begin >= 4) {
                 if ((rc = run_k1(r.begin, r.end, Bmax))) return rc;
+            } else if (!r.one && groups_grid && !(cfg_flags & PE_CFG_ORDERED_ONLY)) {
+                if ((rc = launch_groups(r.begin, r.end))) return rc;
             } else {
                 if ((rc = launch_sequencer(r.begin, r.end, false))) return rc;
             }

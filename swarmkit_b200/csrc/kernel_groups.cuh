@@ -38,6 +38,7 @@
 namespace pe {
 
 #define PE_GR_THREADS 256
+#define PE_GR_WARPS (PE_GR_THREADS / 32)
 #define PE_GR_MAXCLS 256          // distinct rank prefixes of one group that this path sorts by counting
 #define PE_GR_LOCAL 128           // slots of the per-CTA class table
 #define PE_GR_TABLE 1024          // slots of the global class table
@@ -67,7 +68,7 @@ struct GroupsParams {
     unsigned long long *cls_key;     // [PE_GR_TABLE] global class table, all ones = empty
     uint32_t *cls_cnt;               // [PE_GR_TABLE]
     GroupSel *sel;
-    uint32_t *cntmat;                // [gridDim.x][PE_GR_MAXCLS]
+    uint32_t *cntmat;                // [gridDim.x][PE_GR_MAXCLS]: members of a class inside one CTA's slice of the tie order
     uint32_t *resume;                // out: groups of the run handled here (g_end - g_begin = all)
     DevCounters *ctr;
 };
@@ -77,7 +78,7 @@ struct GroupsShared {
     GroupCtx C;
     unsigned long long lkey[PE_GR_LOCAL];
     uint32_t lcnt[PE_GR_LOCAL];
-    uint32_t ccnt[PE_GR_MAXCLS];
+    uint32_t ccnt[PE_GR_WARPS][PE_GR_MAXCLS];
     unsigned long long skey[PE_GR_MAXCLS];
     uint32_t scnt[PE_GR_MAXCLS];
     uint32_t n_found, overflow;
@@ -87,6 +88,9 @@ struct GroupsShared {
     int64_t st_cpu[PE_SEQ_KS], st_mem[PE_SEQ_KS];
     uint32_t st_svc[PE_SEQ_KS], st_tot[PE_SEQ_KS], st_placed[PE_SEQ_KS];
     uint8_t st_flags[PE_SEQ_KS];
+    uint32_t st_node[PE_SEQ_KS];      // the candidates' node and failure band, next to the fill loop (global loads would stall it)
+    uint8_t st_f5[PE_SEQ_KS];
+    uint32_t all_count;               // every task of the group has DesiredState <= COMPLETED (the normal case)
 };
 
 __device__ __forceinline__ uint32_t gr_hash(unsigned long long k) {
@@ -112,10 +116,15 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
     const TickDev &K = P.K;
     const uint32_t tid = threadIdx.x, nth = blockDim.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t N = T.n_nodes, nb = gridDim.x, b = blockIdx.x;
-    // this CTA's slice of the TIE ORDER (positions, not node indices): a multiple of 32 positions
-    const uint32_t per = ((N + nb - 1u) / nb + 31u) & ~31u;
+    // this CTA's slice of the TIE ORDER (positions, not node indices), cut into one share per warp: multiples of 32 positions
+    const uint32_t per_w = (((N + nb - 1u) / nb + PE_GR_WARPS - 1u) / PE_GR_WARPS + 31u) & ~31u;
+    const uint32_t per = per_w * PE_GR_WARPS;
     const uint32_t p_lo = min(b * per, N), p_hi = min(p_lo + per, N);
+    const uint32_t w_lo = min(p_lo + warp * per_w, p_hi), w_hi = min(w_lo + per_w, p_hi);   // this warp's share
     unsigned long long n_placed = 0, n_slow = 0, n_evalg = 0;
+    long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // block 0: cycles per phase (evaluate, threshold, count, offsets, compact, stage rows, fill, write-back + explain)
+    long long tm = clock64();
+#define GR_MARK(slot) do { const long long t_ = clock64(); cyc[slot] += t_ - tm; tm = t_; } while (0)
 
     uint32_t gi = P.g_begin;
     for (; gi < P.g_end; gi++) {
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
         __syncthreads();
         if (tid < sizeof(pe_group) / 4) reinterpret_cast<uint32_t *>(&S.G)[tid] = reinterpret_cast<const uint32_t *>(&K.groups[gi])[tid];
         for (uint32_t i = tid; i < PE_GR_LOCAL; i += nth) { S.lkey[i] = ~0ull; S.lcnt[i] = 0; }
-        for (uint32_t i = tid; i < PE_GR_MAXCLS; i += nth) S.ccnt[i] = 0;
+        for (uint32_t i = tid; i < PE_GR_WARPS * PE_GR_MAXCLS; i += nth) (&S.ccnt[0][0])[i] = 0;
         if (tid < 8) S.cnt8[tid] = 0;
         if (tid == 0) { S.overflow = 0; S.n_found = 0; }
         __syncthreads();
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
         if (tid == 0 && S.overflow) atomicExch(&P.sel->fallback, 1u);
         __threadfence();
         grid.sync();
+        GR_MARK(0);
 
         // ================= 2 threshold (CTA 0) =================
         if (b == 0) {
@@ -221,61 +231,82 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
             __threadfence();
         }
         grid.sync();
+        GR_MARK(1);
         if (P.sel->fallback) break;                      // (uniform: every CTA reads the same flag after the barrier)
         const uint32_t ncs = P.sel->n_cls, m = P.sel->m, r_last = P.sel->r_last, F = P.sel->feasible;
 
-        // ================= 3 count the selected classes inside this slice =================
-        for (uint32_t p = p_lo + tid; p < p_hi; p += nth) {
+        // ================= 3 count the selected classes inside every warp's share =================
+        for (uint32_t c = tid; c < ncs; c += nth) S.skey[c] = P.sel->pref[c];        // (the class keys, next to the lanes)
+        __syncthreads();
+        for (uint32_t p = w_lo + lane; p < w_hi; p += 32u) {
             const uint32_t n = p + ts >= N ? p + ts - N : p + ts;
             if (P.ff8[n] != 0) continue;
-            const uint32_t c = gr_class_of(P.sel->pref, ncs, P.pref64[n]);
-            if (c < ncs) atomicAdd(&S.ccnt[c], 1u);
+            const uint32_t c = gr_class_of(S.skey, ncs, P.pref64[n]);
+            if (c < ncs) atomicAdd(&S.ccnt[warp][c], 1u);
         }
         __syncthreads();
-        for (uint32_t c = tid; c < ncs; c += nth) P.cntmat[(size_t)b * PE_GR_MAXCLS + c] = S.ccnt[c];
+        // (the per-warp counts stay in shared memory for phase 5; the grid only scans the CTAs' totals)
+        for (uint32_t c = tid; c < ncs; c += nth) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < PE_GR_WARPS; w++) t += S.ccnt[w][c];
+            P.cntmat[(size_t)b * PE_GR_MAXCLS + c] = t;
+        }
         __threadfence();
         grid.sync();
+        GR_MARK(2);
 
-        // ================= 4 offsets: exclusive scan over the CTAs, per class (CTA 0) =================
+        // ================= 4 offsets: exclusive scan over the CTAs, per class (CTA 0, one warp per class) =================
         if (b == 0) {
-            for (uint32_t c = tid; c < ncs; c += nth) {
+            for (uint32_t c = warp; c < ncs; c += PE_GR_WARPS) {
                 uint32_t run = P.sel->base[c];
-                for (uint32_t q = 0; q < nb; q++) {
-                    const uint32_t t = P.cntmat[(size_t)q * PE_GR_MAXCLS + c];
-                    P.cntmat[(size_t)q * PE_GR_MAXCLS + c] = run;
-                    run += t;
+                for (uint32_t q0 = 0; q0 < nb; q0 += 32u) {
+                    const uint32_t q = q0 + lane;
+                    const uint32_t v = q < nb ? P.cntmat[(size_t)q * PE_GR_MAXCLS + c] : 0u;
+                    uint32_t incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+                    if (q < nb) P.cntmat[(size_t)q * PE_GR_MAXCLS + c] = run + incl - v;
+                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
                 }
             }
             __threadfence();
         }
         grid.sync();
+        GR_MARK(3);
 
         // ================= 5 compact: members at their position of the sorted candidate list =================
-        if (warp == 0) {
-            // one warp walks the slice in tie order; S.ccnt[c] becomes the next free position of class c
-            for (uint32_t c = lane; c < ncs; c += 32u) S.ccnt[c] = P.cntmat[(size_t)b * PE_GR_MAXCLS + c];
-            __syncwarp();
+        {
+            // every warp walks its share in tie order; S.ccnt[warp][c] becomes the next free position of class c:
+            // the CTA's base (grid scan) + what the lower warps of this CTA hold (their counts are still in shared memory)
+            for (uint32_t c = tid; c < ncs; c += nth) {
+                uint32_t run = P.cntmat[(size_t)b * PE_GR_MAXCLS + c];
+#pragma unroll
+                for (int w = 0; w < PE_GR_WARPS; w++) { const uint32_t t = S.ccnt[w][c]; S.ccnt[w][c] = run; run += t; }
+            }
+            __syncthreads();
             const uint32_t last_end = ncs ? P.sel->base[ncs - 1u] + r_last : 0u;
-            for (uint32_t p0 = p_lo; p0 < p_hi; p0 += 32u) {
+            for (uint32_t p0 = w_lo; p0 < w_hi; p0 += 32u) {
                 const uint32_t p = p0 + lane;
                 uint32_t c = ncs, n = 0;
                 unsigned long long pref = 0;
-                if (p < p_hi) {
+                if (p < w_hi) {
                     n = p + ts >= N ? p + ts - N : p + ts;
-                    if (P.ff8[n] == 0) { pref = P.pref64[n]; c = gr_class_of(P.sel->pref, ncs, pref); }
+                    if (P.ff8[n] == 0) { pref = P.pref64[n]; c = gr_class_of(S.skey, ncs, pref); }
                 }
                 const uint32_t peers = __match_any_sync(0xFFFFFFFFu, c);
                 if (c < ncs) {
-                    const uint32_t at = S.ccnt[c] + __popc(peers & ((1u << lane) - 1u));
+                    const uint32_t at = S.ccnt[warp][c] + __popc(peers & ((1u << lane) - 1u));
                     if (c + 1u < ncs || at < last_end) { P.cand_g[at].pref = pref; P.cand_g[at].tie = p; P.cand_g[at].node = n; }
                 }
                 __syncwarp();
-                if (c < ncs && (uint32_t)(__ffs((int)peers) - 1) == lane) S.ccnt[c] += __popc(peers);
+                if (c < ncs && (uint32_t)(__ffs((int)peers) - 1) == lane) S.ccnt[warp][c] += __popc(peers);
                 __syncwarp();
             }
             __threadfence();
         }
         grid.sync();
+        GR_MARK(4);
 
         // ================= 6 fill, write-back, Explain (CTA 0) =================
         if (b == 0) {
@@ -287,28 +318,66 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
             uint32_t *st_tot = in_smem ? S.st_tot : P.st_tot_g;
             uint32_t *st_placed = in_smem ? S.st_placed : P.st_placed_g;
             uint8_t *st_flags = in_smem ? S.st_flags : P.st_flags_g;
-            if (tid == 0) { S.done = 0; S.any_pass = 0; n_evalg += N; n_slow++; }
+            if (tid == 0) { S.done = 0; S.any_pass = 0; S.all_count = 1; n_evalg += N; n_slow++; }
+            __syncthreads();
             for (uint32_t i = tid; i < m; i += nth) {
                 const uint32_t n = cand[i].node;
                 st_cpu[i] = T.cpu[n]; st_mem[i] = T.mem[n]; st_svc[i] = svccol[n]; st_tot[i] = T.total[n];
                 st_placed[i] = 0; st_flags[i] = 0;
+                if (in_smem) { S.st_node[i] = n; S.st_f5[i] = (uint8_t)(cand[i].pref >> 56); }
                 for (uint32_t w = 0; w < G.gen_cnt; w++)
                     if (gen_first_occurrence(K, G, w)) P.st_gen_g[(size_t)w * P.st_cap + i] = T.gen[K.gens[G.gen_off + w].kind][n];
             }
+            {   // do all tasks move the spread counters?  (one pass in parallel instead of a global load per fill step)
+                bool all = true;
+                for (uint32_t ti = tid; ti < k; ti += nth) all = all && (K.task_flags[G.task_off + ti] & PE_T_COUNTS) != 0;
+                if (!__all_sync(0xFFFFFFFFu, all) && lane == 0) S.all_count = 0;
+            }
             __syncthreads();
-            // ---- scheduleNTasksOnNodes (scheduler.go:844-924), one thread, staged rows
-            if (tid == 0 && m > 0) {
+            GR_MARK(5);
+            // ---- The normal shape needs no loop.  If the first k candidates share one (failure band, service count) and every
+            // task counts, scheduleNTasksOnNodes (scheduler.go:844-924) gives task t to candidate t: after its task a node
+            // holds one more of the service than the next candidate, so the walk moves on every time (:899-905), the next
+            // candidate is untouched (it passes Process as it did when it was staged), and with k <= m the first lap never ends.
+            bool uniform = k <= m && S.all_count != 0u;
+            if (uniform) {
+                const uint32_t head = (uint32_t)(cand[0].pref >> 32);
+                bool same = true;
+                for (uint32_t i = tid; i < k; i += nth) same = same && (uint32_t)(cand[i].pref >> 32) == head;
+                uniform = __syncthreads_and(same ? 1 : 0) != 0;
+            }
+            if (uniform) {
+                for (uint32_t i = tid; i < k; i += nth) {
+                    K.out_node[G.task_off + i] = cand[i].node;
+                    st_mem[i] -= G.mem_res; st_cpu[i] -= G.cpu_res;
+                    for (uint32_t w = 0; w < G.gen_cnt; w++)
+                        if (gen_first_occurrence(K, G, w)) {
+                            int64_t *cell = &P.st_gen_g[(size_t)w * P.st_cap + i];
+                            *cell = claim_cell(K, G, w, *cell);
+                        }
+                    st_svc[i]++; st_tot[i]++; st_placed[i] = 1;
+                }
+                if (tid == 0) { S.done = k; S.any_pass = 1; n_placed += k; }
+            }
+            // ---- scheduleNTasksOnNodes, the literal loop: one thread, staged rows
+            if (!uniform && tid == 0 && m > 0) {
                 const uint32_t fm = G.filter_mask;
                 const bool f_res = (fm >> PE_F_RESOURCE) & 1u, f_port = ((fm >> PE_F_HOSTPORT) & 1u) && G.port_cnt > 0;
                 const bool f_max = (fm >> PE_F_MAXREPLICAS) & 1u;
+                const bool all_count = S.all_count != 0u;
                 uint32_t cnt[PE_NUM_FILTERS];
                 for (int f = 0; f < PE_NUM_FILTERS; f++) cnt[f] = 0;
                 uint32_t done = 0, any_pass = 0;
-                unsigned long long it = 0;
+                // `it` of the reference only ever matters modulo m and through the test `it + 1 < m`: keep the position and
+                // whether the first lap is over (no 64-bit division on the one thread everybody waits for)
+                uint32_t pos = 0;
+                bool first_lap = true;
+                auto node_of = [&](uint32_t i) -> uint32_t { return in_smem ? S.st_node[i] : cand[i].node; };
+                auto f5_of = [&](uint32_t i) -> uint32_t { return in_smem ? (uint32_t)S.st_f5[i] : (uint32_t)(cand[i].pref >> 56); };
                 for (uint32_t ti = 0; ti < k; ti++) {
-                    const uint32_t i = (uint32_t)(it % m);
-                    K.out_node[G.task_off + ti] = cand[i].node;
-                    const bool counts = (K.task_flags[G.task_off + ti] & PE_T_COUNTS) != 0;
+                    const uint32_t i = pos;
+                    K.out_node[G.task_off + ti] = node_of(i);
+                    const bool counts = all_count || (K.task_flags[G.task_off + ti] & PE_T_COUNTS) != 0;
                     st_mem[i] -= G.mem_res;                  // NodeInfo.addTask on the staged row (nodeinfo.go:125-153)
                     st_cpu[i] -= G.cpu_res;
                     for (uint32_t w = 0; w < G.gen_cnt; w++)
@@ -321,18 +390,19 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
                     st_placed[i]++;
                     done++;
                     if (done == k) break;
-                    if (it + 1 < m) {  // :899-905 first pass: move on only if the next node is now strictly better
-                        const uint32_t j = (uint32_t)((it + 1) % m);
-                        const uint32_t fa = (uint32_t)(cand[j].pref >> 56), fb = (uint32_t)(cand[i].pref >> 56);
+                    if (first_lap && pos + 1u < m) {  // :899-905 first pass: move on only if the next node is now strictly better
+                        const uint32_t j = pos + 1u;
+                        const uint32_t fa = f5_of(j), fb = f5_of(i);
                         const bool less = fa != fb ? fa < fb : (st_svc[j] != st_svc[i] ? st_svc[j] < st_svc[i] : st_tot[j] < st_tot[i]);
-                        if (less) it++;
+                        if (less) pos++;
                     } else {
-                        it++;          // :906-910 later passes: round-robin
+                        first_lap = false;     // :906-910 later passes: round-robin
+                        pos = pos + 1u == m ? 0u : pos + 1u;
                     }
-                    const unsigned long long start = it;
+                    uint32_t walked = 0;
                     bool dead = false;
                     for (;;) {         // :912-920
-                        const uint32_t j = (uint32_t)(it % m);
+                        const uint32_t j = pos;
                         bool ok = !(st_flags[j] & PE_ST_FAILED);
                         if (ok) {      // Pipeline.Process on the staged row: only the dynamic filters can have changed
                             int ff = -1;
@@ -353,8 +423,9 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
                         }
                         if (ok) break;
                         st_flags[j] |= PE_ST_FAILED;
-                        it++;
-                        if (it - start == m) { dead = true; break; }
+                        // (the reference's `it` keeps counting: once it has passed m - 1 the first lap is over for good)
+                        if (pos + 1u == m) { pos = 0; first_lap = false; } else pos++;
+                        if (++walked == m) { dead = true; break; }
                     }
                     if (dead) break;
                 }
@@ -363,6 +434,7 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
                 n_placed += done;
             }
             __syncthreads();
+            GR_MARK(6);
             const uint32_t done = S.done;
             // ---- write the staged rows back
             for (uint32_t i = tid; i < m; i += nth) {
@@ -423,7 +495,8 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
             __threadfence();
         }
         (void)F;
-        grid.sync();      // the reservations of this group are in the columns before the next group reads them
+        grid.sync();
+        GR_MARK(7);      // the reservations of this group are in the columns before the next group reads them
     }
     if (b == 0 && tid == 0) {
         *P.resume = gi - P.g_begin;
@@ -431,6 +504,7 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
         P.ctr->slow_path += n_slow;
         P.ctr->placements += n_placed;
         P.ctr->evals_generic += n_evalg;
+        for (int q = 0; q < 8; q++) P.ctr->prof[8 + q] += (unsigned long long)cyc[q];
     }
 }
 

@@ -245,20 +245,20 @@ __device__ __forceinline__ PlPre pl_prefetch(const PlaceParams &P, uint32_t task
     return q;
 }
 
-// The entry of the chunk's node table (in CTA 0's shared memory: distributed shared memory atomics) for a candidate node.
-// Every stage warp of the cluster inserts its candidates, so that the resolve phase proposes with ONE atomicMin on a
-// known entry instead of probing a hash table on its critical path.
-__device__ __forceinline__ uint32_t pl_slot_of(PlShared *S0, uint32_t node) {
+// The entry of the chunk's node table for a candidate node.  Every thread of CTA 0 looks up a share of the chunk's
+// candidates before the resolve phase, so that a proposal there is ONE atomicMin on a known entry instead of a hash
+// probe on the critical path.
+__device__ __forceinline__ uint32_t pl_slot_of(PlShared &S, uint32_t node) {
     uint32_t h = pl_hash(node);
     for (uint32_t probes = 0; probes < PE_PL_HASH; probes++, h = (h + 1u) & (PE_PL_HASH - 1u)) {
-        const uint32_t k = *reinterpret_cast<volatile uint32_t *>(&S0->hkey[h]);
+        const uint32_t k = S.hkey[h];
         if (k == node) return h;
         if (k == PE_PL_EMPTY) {
-            const uint32_t old = atomicCAS(&S0->hkey[h], PE_PL_EMPTY, node);
+            const uint32_t old = atomicCAS(&S.hkey[h], PE_PL_EMPTY, node);
             if (old == PE_PL_EMPTY || old == node) return h;
         }
     }
-    atomicOr(&S0->wd, 1u);        // (cannot happen: the table outnumbers a chunk's candidates; the chunk is handed over if it does)
+    atomicOr(&S.wd, 1u);          // (cannot happen: the table outnumbers a chunk's candidates; the chunk is handed over if it does)
     return 0u;
 }
 
@@ -347,11 +347,7 @@ __device__ __forceinline__ void pl_stage(const PlaceParams &P, const PlPre &pre,
     }
     if (kind) { n_cand = 0; rs1 = rs2 = rs3 = 0; }
     __syncwarp();
-    for (uint32_t e = lane; e < n_cand; e += 32u) {
-        const uint32_t x = cand[e];
-        S0->cand[(size_t)i * PE_PL_KS + e] = x;
-        S0->cslot[(size_t)i * PE_PL_KS + e] = (uint16_t)pl_slot_of(S0, PE_PL_NODE(x));
-    }
+    for (uint32_t e = lane; e < n_cand; e += 32u) S0->cand[(size_t)i * PE_PL_KS + e] = cand[e];
     if (lane == 0) {
         S0->s_kind[i] = (uint8_t)kind; S0->s_ncand[i] = (uint16_t)n_cand;
         S0->s_rs1[i] = (uint16_t)rs1; S0->s_rs2[i] = (uint16_t)rs2; S0->s_rs3[i] = (uint16_t)rs3;
@@ -378,7 +374,7 @@ __device__ __forceinline__ unsigned long long pl_key_of(const PlSlot &s, uint32_
 // the 32 lanes stay converged: a lone warp pays ~7 cycles per instruction, divergence multiplies that.
 // BM: CTA 0 also keeps the batch's touched bitmap in shared memory (tk): candidates that were untouched when the chunk
 // began are skipped eight at a time while their bit is set (= taken inside this chunk) before anything is proposed.
-struct PlProf { unsigned long long rounds, passes, retries; long long cyc_mask, cyc_attempt, cyc_check, cyc_final, cyc_work; };   // (cycles: this thread's view)
+struct PlProf { unsigned long long rounds, passes, retries, attempts, masks; long long cyc_mask, cyc_attempt, cyc_check, cyc_final, cyc_work, cyc_own; };   // (cycles: this thread's view)
 
 
 // (every thread of CTA 0 walks through the resolve phase so that its barriers are plain __syncthreads: a named barrier
@@ -444,21 +440,26 @@ __device__ __forceinline__ void pl_resolve(const PlaceParams &P, PlShared &S, ui
         bool ranaway = false;
         for (uint32_t r = 0;; r++) {
             // a moving task proposes until a node keeps it: final placements (0) and lower tasks send it on at once
+            const long long to0 = clock64();
             while (moving) {
                 if (mask == 0u) {
                     jb += 16u;
                     if (jb >= n_cand) { moving = false; dead = true; myh = PE_PL_EMPTY; break; }    // out of candidates
                     mask = load_mask(jb);
+                    prof.masks++;
                     continue;
                 }
+                prof.attempts++;
                 const uint32_t k = (uint32_t)__ffs((int)mask) - 1u;
                 mask &= mask - 1u;
                 j = jb + k;
                 const uint32_t h = cs[j];
+                if (S.hold[h] < i + 1u) continue;                // final (0) or a lower task's (plain load: an entry only ever goes down)
                 const uint32_t prev = atomicMin(&S.hold[h], i + 1u);
                 if (prev < i + 1u) continue;
                 myh = h; moving = false;                         // (a higher task that held it finds out below)
             }
+            prof.cyc_own += clock64() - to0;
             pl_rbar();
             { const long long tq = clock64(); prof.cyc_attempt += tq - tp1; tp1 = tq; }
             if (tid == 0) { S.again[(r + 1u) & 1u] = 0; prof.rounds++; }        // (everybody has read it: see the barrier above)
@@ -571,6 +572,11 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
         pre_task = c0 + nc + slot_i;                            // the next chunk's task, if this one runs to its end: loads fly during resolve
         if (pre_task < P.B) pre = pl_prefetch(P, pre_task);
         if (crank == 0) {
+            for (uint32_t idx = tid; idx < nc * PE_PL_KS; idx += blockDim.x) {       // node-table entries of the chunk's candidates
+                const uint32_t i = idx / PE_PL_KS, e = idx - i * PE_PL_KS;
+                if (e < S.s_ncand[i]) S.cslot[idx] = (uint16_t)pl_slot_of(S, PE_PL_NODE(S.cand[idx]));
+            }
+            __syncthreads();
             if (P.tk_words) pl_resolve<true>(P, S, tk, c0, nc, tid, n_amb, prof);
             else pl_resolve<false>(P, S, tk, c0, nc, tid, n_amb, prof);
             __syncthreads();
@@ -643,8 +649,9 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
         atomicAdd(&P.ctr->prof[3], (unsigned long long)prof.cyc_mask); atomicAdd(&P.ctr->prof[4], (unsigned long long)prof.cyc_attempt);
         atomicAdd(&P.ctr->prof[5], (unsigned long long)prof.cyc_check); atomicAdd(&P.ctr->prof[6], (unsigned long long)prof.cyc_final);
     }
-    if (crank == 0 && lane == 0 && warp < 4) {      // per resolve warp: cycles between the two barriers of a round (own work / whole)
-        atomicAdd(&P.ctr->prof[8 + 2 * warp], (unsigned long long)prof.cyc_work); atomicAdd(&P.ctr->prof[9 + 2 * warp], (unsigned long long)prof.cyc_check);
+    if (crank == 0 && lane == 31 && warp < 4) {     // last task of each resolve warp: its attempts and the cycles it spent proposing
+        atomicAdd(&P.ctr->prof[8 + 2 * warp], prof.attempts); atomicAdd(&P.ctr->prof[9 + 2 * warp], (unsigned long long)prof.cyc_own);
+        if (warp == 3) atomicAdd(&P.ctr->prof[2], prof.masks);
     }
 }
 
