@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 1u
+#define PE_ABI_VERSION 2u   /* 2: pe_group.leaf_cnt (was tail padding), pe_pref_leaves */
 
 /* ---- status codes ------------------------------------------------------- */
 #define PE_OK 0
@@ -156,6 +156,14 @@ typedef struct pe_group {
     uint32_t tie_start;   /* tie-break / evaluation order is node_idx rotated by this
                              amount: pos(n) = (n - tie_start) mod N.  0 = SURVEY canonical */
     uint32_t flags;       /* PE_G_*                                                        */
+    uint32_t leaf_cnt;    /* placement preferences (nodeSet.tree nodeset.go:59-101,
+                             scheduleNTasksOnSubtree scheduler.go:772-825): this group is ONE
+                             VISIT OF ONE LEAF of the service's decision tree.  The leaf_cnt
+                             pe_constraint entries that FOLLOW the group's constraints
+                             (cons[con_off + con_cnt ...], neq ignored) name the leaf: a node
+                             belongs to it iff every (column == value) holds.  Nodes outside
+                             the leaf are not part of the node set for this group (they are
+                             neither evaluated nor counted).  0 = no preferences            */
 } pe_group;
 
 /* One scheduling pass = the group loop of Scheduler.tick, scheduler.go:464-469.
@@ -282,6 +290,18 @@ int32_t pe_tick_download(pe_engine *h, uint32_t *out_node, uint32_t *out_fail);
  * reference tick arrays exactly like pe_schedule. */
 int32_t pe_fit(pe_engine *h, const pe_tick *tick, const uint32_t *node_idx,
                uint8_t *out_ok, uint32_t *out_fail);
+
+/* ---- placement preferences: the tree's bookkeeping ------------------------ */
+/* nodeSet.tree (nodeset.go:59-101) hangs every node of the set under the branch named by its values of the
+ * preference labels and adds the node's ActiveTasksCountByService[service] to every branch on the way.  This call
+ * returns the LEAVES: every distinct tuple of values of the n_levels attribute columns `cols` among the rows of the
+ * node set (feasible or not), with the sum of that count over the leaf's nodes.  out_vals[cap * n_levels] (tuple of
+ * leaf i at out_vals[i * n_levels ...]), out_tasks[cap]; order unspecified (the shim sorts branches by label value).
+ * PE_ERR_OVERFLOW if more than cap leaves exist; n_levels <= PE_MAX_PREF_LEVELS.  The host walks the tree
+ * (scheduler.go:784-822) and submits one pe_group with leaf_cnt > 0 per leaf visit. */
+#define PE_MAX_PREF_LEVELS 8
+int32_t pe_pref_leaves(pe_engine *h, uint32_t svc_id, const uint32_t *cols, uint32_t n_levels, uint32_t cap,
+                       uint32_t *out_vals, uint32_t *out_tasks, uint32_t *out_n_leaves);
 
 /* ---- introspection (parity checker) -------------------------------------- */
 typedef struct pe_node_state {

@@ -24,14 +24,17 @@
 //
 // Pinning: this encoded oracle is cross-checked against the object-level oracle
 // (oracle/sched_oracle.cpp, which is pinned by the reference's own known-answer
-// tests) in tests/test_flat_vs_object.py; see DESIGN.md "Oracle".
+// tests) in tests/test_shim_cpu.py; see DESIGN.md "Oracle".
 //
-// Placement preferences (scheduler.go:772-825) are not expressible in the flat
-// ABI yet; the object-level oracle implements them.
+// Placement preferences: the flat ABI carries ONE LEAF VISIT of the decision tree per group (pe_group.leaf_cnt: the
+// node set is cut down to the leaf, nodeset.go:59-101) plus pref_leaves (the tree's per-leaf task sums); the tree walk
+// of scheduleNTasksOnSubtree (scheduler.go:772-825) is host code above the ABI.  The object-level oracle implements
+// the whole of it literally and pins this decomposition (tests/test_shim_cpu.py).
 
 #include "../include/placement_engine.h"
 
 #include <algorithm>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -113,6 +116,16 @@ struct Sched {
     }
 
     uint32_t pos(uint32_t n) const { return n >= g.tie_start ? n - g.tie_start : n + N - g.tie_start; }
+
+    // nodeSet.tree's branch walk, nodeset.go:59-101, seen from one leaf: is the node under it?
+    bool in_leaf(uint32_t n) const {
+        for (uint32_t i = 0; i < g.leaf_cnt; i++) {
+            const pe_constraint &c = t.cons[g.con_off + g.con_cnt + i];
+            uint32_t v = c.col < o.attr.size() && n < o.attr[c.col].size() ? o.attr[c.col][n] : 0;
+            if (v != c.value) return false;
+        }
+        return true;
+    }
 
     // countRecentFailures, nodeinfo.go:206-221 (the shim pre-counts per node)
     uint32_t failures(uint32_t n) const {
@@ -294,6 +307,7 @@ static void schedule_group(Oracle &o, const Tick &t, uint32_t gi, uint32_t *out_
     for (uint32_t p = 0; p < N; p++) {
         uint32_t n = p + g.tie_start; if (n >= N) n -= N;   // canonical evaluation order
         if (!(o.nodes[n].flags & PE_NODE_VALID)) continue;  // not in nodeSet.nodes
+        if (g.leaf_cnt && !s.in_leaf(n)) continue;          // under another leaf of the preference tree
         o.stats.evals_generic++;
         if (heap.size() < k) {
             if (s.process(n)) { heap.push_back(n); std::push_heap(heap.begin(), heap.end(), worse); }
@@ -357,7 +371,7 @@ static int32_t validate(Oracle &o, const pe_tick *tk) {
     for (uint32_t i = 0; i < tk->n_groups; i++) {
         const pe_group &g = tk->groups[i];
         if ((uint64_t)g.task_off + g.n_tasks > tk->n_tasks) { o.err = "group task range out of bounds"; return PE_ERR_INVALID; }
-        if ((uint64_t)g.gen_off + g.gen_cnt > tk->n_gens || (uint64_t)g.con_off + g.con_cnt > tk->n_cons ||
+        if ((uint64_t)g.gen_off + g.gen_cnt > tk->n_gens || (uint64_t)g.con_off + g.con_cnt + g.leaf_cnt > tk->n_cons ||
             (uint64_t)g.ip_off + g.ip_cnt > tk->n_ips || (uint64_t)g.plat_off + g.plat_cnt > tk->n_plats ||
             (uint64_t)g.port_off + g.port_cnt > tk->n_ports || (uint64_t)g.plug_off + g.plug_cnt > tk->n_plugs ||
             (uint64_t)g.fail_off + g.fail_cnt > tk->n_fails) { o.err = "group side-array range out of bounds"; return PE_ERR_INVALID; }
@@ -453,6 +467,29 @@ int32_t ope_node_task_delta(pe_engine *h, const pe_task_delta *d, uint32_t n, co
             if (sg > 0) w |= 1u << (s & 31); else w &= ~(1u << (s & 31));
         }
     }
+    return PE_OK;
+}
+
+// nodeSet.tree, nodeset.go:59-101: the leaves and their `tasks` sums (every node of the set, feasible or not)
+int32_t ope_pref_leaves(pe_engine *h, uint32_t svc_id, const uint32_t *cols, uint32_t n_levels, uint32_t cap,
+                        uint32_t *out_vals, uint32_t *out_tasks, uint32_t *out_n_leaves) {
+    Oracle &o = h->o;
+    if (n_levels > PE_MAX_PREF_LEVELS || !out_n_leaves || (n_levels && !cols)) { o.err = "pref_leaves: bad arguments"; return PE_ERR_INVALID; }
+    std::map<std::vector<uint32_t>, uint32_t> leaves;
+    const std::vector<uint32_t> &sc = o.col(o.svc, svc_id);
+    for (uint32_t n = 0; n < o.n_nodes; n++) {
+        if (!(o.nodes[n].flags & PE_NODE_VALID)) continue;
+        std::vector<uint32_t> key(n_levels);
+        for (uint32_t l = 0; l < n_levels; l++) key[l] = cols[l] < o.attr.size() && n < o.attr[cols[l]].size() ? o.attr[cols[l]][n] : 0;
+        leaves[key] += sc[n];
+    }
+    if (leaves.size() > cap) { o.err = "pref_leaves: more leaves than the caller's buffers hold"; return PE_ERR_OVERFLOW; }
+    uint32_t i = 0;
+    for (auto &kv : leaves) {
+        for (uint32_t l = 0; l < n_levels; l++) out_vals[(size_t)i * n_levels + l] = kv.first[l];
+        out_tasks[i++] = kv.second;
+    }
+    *out_n_leaves = i;
     return PE_OK;
 }
 

@@ -39,6 +39,7 @@
 #define ope_stats_reset mpe_stats_reset
 #define ope_fold_value mpe_fold_value
 #define ope_nccl_unique_id mpe_nccl_unique_id
+#define ope_pref_leaves mpe_pref_leaves
 #include "flat_oracle.cpp"
 
 #include <cstdlib>

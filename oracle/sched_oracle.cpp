@@ -40,7 +40,7 @@
 #include <string>
 #include <vector>
 
-#include "minijson.h"
+#include "../swarmkit_b200/csrc/minijson.h"   // (a JSON reader for the test-driver protocol: utility, not algorithm)
 
 namespace api {
 enum TaskState { TaskStateNew = 0, TaskStatePending = 64, TaskStateAssigned = 192, TaskStateAccepted = 256, TaskStatePreparing = 320,

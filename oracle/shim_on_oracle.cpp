@@ -25,6 +25,7 @@
 #define pe_stats_reset ope_stats_reset
 #define pe_fold_value ope_fold_value
 #define pe_nccl_unique_id ope_nccl_unique_id
+#define pe_pref_leaves ope_pref_leaves
 #define ss_create sso_create
 #define ss_destroy sso_destroy
 #define ss_apply sso_apply

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-PE_ABI_VERSION = 1
+PE_ABI_VERSION = 2
 PE_NONE = 0xFFFFFFFF
 PE_NUM_FILTERS = 8
 (PE_F_READY, PE_F_RESOURCE, PE_F_PLUGIN, PE_F_CONSTRAINT, PE_F_PLATFORM, PE_F_HOSTPORT, PE_F_MAXREPLICAS,
@@ -53,6 +53,7 @@ group_dt = np.dtype([
     ("ip_off", "<u4"), ("ip_cnt", "<u4"), ("plat_off", "<u4"), ("plat_cnt", "<u4"),
     ("port_off", "<u4"), ("port_cnt", "<u4"), ("plug_off", "<u4"), ("plug_cnt", "<u4"),
     ("log_plugin", "<u4"), ("fail_off", "<u4"), ("fail_cnt", "<u4"), ("tie_start", "<u4"), ("flags", "<u4"),
+    ("leaf_cnt", "<u4"),
 ], align=True)
 task_delta_dt = np.dtype([
     ("node_idx", "<u4"), ("svc_id", "<u4"), ("sign", "<i4"), ("counts", "<u4"), ("cpu", "<i8"), ("mem", "<i8"),
@@ -111,7 +112,7 @@ ABI_SYMBOLS = [
     "abi_version", "create", "destroy", "last_error", "node_upsert", "node_remove", "set_node_count",
     "node_task_delta", "schedule", "tick_upload", "tick_run", "tick_download", "fit", "snapshot",
     "snapshot_service", "snapshot_generic", "snapshot_ports", "get_stats", "stats_reset", "fold_value",
-    "nccl_unique_id",
+    "nccl_unique_id", "pref_leaves",
 ]
 
 
@@ -219,6 +220,7 @@ class FlatABI:
         self.f["stats_reset"].argtypes = [C.c_void_p]
         self.f["fold_value"].argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
         self.f["nccl_unique_id"].argtypes = [C.c_void_p]
+        self.f["pref_leaves"].argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         if self.f["abi_version"]() != PE_ABI_VERSION:
             raise RuntimeError("ABI version mismatch")
         self._nccl_id = None
@@ -312,6 +314,15 @@ class FlatABI:
         ts = tick.c_struct()
         self._check(self.f["fit"](self.h, C.byref(ts), _ptr(node_idx), _ptr(ok), _ptr(out_fail)))
         return ok[:tick.n_groups], out_fail[:tick.n_groups * PE_NUM_FILTERS].reshape(-1, PE_NUM_FILTERS)
+
+    def pref_leaves(self, svc: int, cols, cap: int = 4096):
+        """Leaves of the placement-preference tree of one service: (value tuples [n, levels], task sums [n])."""
+        cols = np.ascontiguousarray(cols, np.uint32)
+        vals = np.zeros(max(cap * max(cols.size, 1), 1), np.uint32)
+        tasks = np.zeros(max(cap, 1), np.uint32)
+        n = C.c_uint32(0)
+        self._check(self.f["pref_leaves"](self.h, svc, _ptr(cols), cols.size, cap, _ptr(vals), _ptr(tasks), C.byref(n)))
+        return vals[:n.value * cols.size].reshape(n.value, cols.size), tasks[:n.value]
 
     # -- introspection
     def snapshot(self, first: int, n: int):

@@ -81,7 +81,7 @@ struct pe_engine {
     // ---- staged tick
     void *tick_buf = nullptr; size_t tick_cap = 0;
     TickDev K{};
-    struct Run { uint32_t begin, end; bool one; };   // maximal runs of k == 1 / k != 1 groups
+    struct Run { uint32_t begin, end; bool one; bool seq_only; };   // maximal runs of k == 1 / k != 1 groups (seq_only: one-task leaf visits)
     std::vector<Run> runs;
     // what the k == 1 groups of the staged tick use (decides the scan's tile columns and variant)
     bool use_res = false, use_dyn = false, scan_ok = true;
@@ -114,6 +114,7 @@ struct pe_engine {
     uint32_t *d_cls_counters = nullptr;              // [0] signatures [1] classes [2] rows of the current batch [3] where the
                                                      //     parallel placement step stopped in the current batch
     uint32_t *cursors = nullptr; size_t cursors_cap = 0;   // [rows][2] class-list cursors of the placement step
+    uint32_t place_cluster = PE_PL_CLUSTER;                // CTAs per cluster of k_place (8 or 16)
     void *groups_buf = nullptr;                            // scratch of k_groups: class table | GroupSel | per-CTA class counts
     int groups_grid = 0;                                   // CTAs of the cooperative launch (0: not available)
     DevCounters *d_ctr = nullptr;
@@ -170,6 +171,24 @@ struct pe_engine {
             }
         }
         CU(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem_bytes(PE_PL_TK_MAX_WORDS)));
+        // the placement step's cluster: 16 CTAs (a chunk of 256 tasks) where the device co-schedules that many, else the
+        // portable 8.  PE_PLACE_CLUSTER=8|16 overrides (A-B measurements).
+        {
+            place_cluster = PE_PL_CLUSTER;
+            uint32_t want = PE_PL_CLUSTER_MAX;
+            if (const char *ev = getenv("PE_PLACE_CLUSTER")) want = (uint32_t)atoi(ev) == 8u ? 8u : 16u;
+            if (want > PE_PL_CLUSTER && cudaFuncSetAttribute(k_place, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t lc = {};
+                lc.gridDim = dim3(want); lc.blockDim = dim3(PE_PL_THREADS); lc.dynamicSmemBytes = place_smem_bytes(PE_PL_TK_MAX_WORDS);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                int n_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, k_place, &lc) == cudaSuccess && n_clusters >= 1) place_cluster = want;
+            }
+            (void)cudaGetLastError();
+        }
         CU(cudaFuncSetAttribute(k_scan<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CU(cudaFuncSetAttribute(k_scan<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CU(cudaFuncSetAttribute(k_scan<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -194,7 +213,7 @@ struct pe_engine {
         for (auto p : gen) fr(p);
         for (auto p : d_tab) fr(p);
         fr(tick_buf); fr(d_out_node); fr(d_out_fail); fr(ff8); fr(pref64); fr(cand_g); fr(st_cpu_g); fr(st_mem_g); fr(st_gen_g);
-        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters); fr(chunk_buf); fr(cursors); fr(groups_buf);
+        fr(st_svc_g); fr(st_tot_g); fr(st_placed_g); fr(st_flags_g); fr(touched_g); fr(E); fr(Lbuf); fr(scan_out); fr(d_ctr); fr(up_buf); fr(cls_buf); fr(rows_buf); fr(Sbuf); fr(d_cls_counters); fr(chunk_buf); fr(cursors); fr(groups_buf); fr(pref_buf);
         if (h_ctr) cudaFreeHost(h_ctr);
         for (auto &p : ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         if (stream) cudaStreamDestroy(stream);
@@ -437,15 +456,16 @@ struct pe_engine {
         for (uint32_t i = 0; i < tk->n_groups; i++) {
             const pe_group &g = tk->groups[i];
             if ((uint64_t)g.task_off + g.n_tasks > tk->n_tasks) { err = "group task range out of bounds"; return PE_ERR_INVALID; }
-            if ((uint64_t)g.gen_off + g.gen_cnt > tk->n_gens || (uint64_t)g.con_off + g.con_cnt > tk->n_cons ||
+            if ((uint64_t)g.gen_off + g.gen_cnt > tk->n_gens || (uint64_t)g.con_off + g.con_cnt + g.leaf_cnt > tk->n_cons ||
                 (uint64_t)g.ip_off + g.ip_cnt > tk->n_ips || (uint64_t)g.plat_off + g.plat_cnt > tk->n_plats ||
                 (uint64_t)g.port_off + g.port_cnt > tk->n_ports || (uint64_t)g.plug_off + g.plug_cnt > tk->n_plugs ||
                 (uint64_t)g.fail_off + g.fail_cnt > tk->n_fails) { err = "group side-array range out of bounds"; return PE_ERR_INVALID; }
             if (n_nodes && g.tie_start >= n_nodes) { err = "tie_start >= node count"; return PE_ERR_INVALID; }
             if (g.gen_cnt > PE_MAX_GEN_WANTS) { err = "more than 8 generic reservations in one task"; return PE_ERR_UNSUPPORTED; }
             if ((g.svc_id >= svc.size() || !svc[g.svc_id]) && (rc = ensure_col(svc, g.svc_id, 4))) return rc;
-            const bool one = g.n_tasks == 1;
-            if (runs.empty() || runs.back().one != one) runs.push_back({i, i + 1, one});
+            const bool one = g.n_tasks == 1 && g.leaf_cnt == 0;     // (a leaf visit of a preference tree is placed on its own)
+            const bool seq_only = g.n_tasks == 1 && g.leaf_cnt != 0; // ... by the one-CTA path when it is a single task
+            if (runs.empty() || runs.back().one != one || runs.back().seq_only != seq_only) runs.push_back({i, i + 1, one, seq_only});
             else runs.back().end = i + 1;
             if (one) {   // the scan path: which state-dependent columns ride in the node tiles
                 if ((g.filter_mask >> PE_F_RESOURCE) & 1u) {
@@ -829,7 +849,16 @@ struct pe_engine {
                 const uint32_t tkw = (n_nodes + 31) / 32;
                 PP.tk_words = tkw <= PE_PL_TK_MAX_WORDS ? tkw : 0u;
                 EvPair *evq = ev_begin(6);
-                k_place<<<PE_PL_CLUSTER, PE_PL_THREADS, place_smem_bytes(PP.tk_words), stream>>>(PP);
+                {
+                    cudaLaunchConfig_t lc = {};
+                    lc.gridDim = dim3(place_cluster); lc.blockDim = dim3(PE_PL_THREADS);
+                    lc.dynamicSmemBytes = place_smem_bytes(PP.tk_words); lc.stream = stream;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = place_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    lc.attrs = at; lc.numAttrs = 1;
+                    CU(cudaLaunchKernelEx(&lc, k_place, PP));
+                }
                 ev_end(evq);
                 stats.kernel_launches++;
                 CU(cudaGetLastError());
@@ -887,7 +916,7 @@ struct pe_engine {
             // maximal run of k == 1 groups -> batched scan path; anything else -> sequencer alone
             if (r.one && spec && r.end - r.begin >= 4) {
                 if ((rc = run_k1(r.begin, r.end, Bmax))) return rc;
-            } else if (!r.one && groups_grid && !(cfg_flags & PE_CFG_ORDERED_ONLY)) {
+            } else if (!r.one && !r.seq_only && groups_grid && !(cfg_flags & PE_CFG_ORDERED_ONLY)) {
                 if ((rc = launch_groups(r.begin, r.end))) return rc;
             } else {
                 if ((rc = launch_sequencer(r.begin, r.end, false))) return rc;
@@ -964,6 +993,50 @@ struct pe_engine {
     int32_t finish_schedule() {
         CU(cudaStreamSynchronize(stream));
         return counters_finish();      // (also collects the event timings)
+    }
+
+    // nodeSet.tree's leaves and their task sums for one service (nodeset.go:59-101); see kernel_misc.cuh
+    void *pref_buf = nullptr; size_t pref_cap = 0;
+    int32_t pref_leaves(uint32_t svc_id, const uint32_t *cols, uint32_t n_levels, uint32_t out_cap, uint32_t *out_vals, uint32_t *out_tasks, uint32_t *out_n) {
+        if (n_levels > PE_MAX_PREF_LEVELS || !out_n || (n_levels && !cols) || (out_cap && (!out_tasks || (n_levels && !out_vals)))) { err = "pref_leaves: bad arguments"; return PE_ERR_INVALID; }
+        int32_t rc;
+        if ((rc = sync_tabs())) return rc;
+        for (uint32_t l = 0; l < n_levels; l++) if ((rc = ensure_col(attr, cols[l], 4))) return rc;
+        if ((svc_id >= svc.size() || !svc[svc_id]) && (rc = ensure_col(svc, svc_id, 4))) return rc;
+        if ((rc = sync_tabs())) return rc;
+        uint32_t tsz = 1024;
+        while (tsz < 2u * std::max(n_nodes, 1u)) tsz <<= 1;
+        const size_t lv = std::max(n_levels, 1u);
+        const size_t bytes = (size_t)tsz * 16 + ((size_t)out_cap * (lv + 1) + 2) * 4 + 64;
+        if ((rc = ensure_buf(pref_buf, pref_cap, bytes))) return rc;
+        PrefParams P;
+        P.T = table(); P.svccol = svc[svc_id]; P.n_levels = n_levels; P.mask = tsz - 1; P.cap = out_cap;
+        for (uint32_t l = 0; l < PE_MAX_PREF_LEVELS; l++) P.cols[l] = l < n_levels ? cols[l] : 0u;
+        char *b = reinterpret_cast<char *>(pref_buf);
+        P.keys = reinterpret_cast<unsigned long long *>(b);
+        P.sums = reinterpret_cast<uint32_t *>(b + (size_t)tsz * 8);
+        P.reps = P.sums + tsz;
+        P.out_n = P.reps + tsz; P.out_err = P.out_n + 1; P.out_tasks = P.out_err + 1; P.out_vals = P.out_tasks + out_cap;
+        CU(cudaMemsetAsync(b, 0, (size_t)tsz * 12, stream));
+        CU(cudaMemsetAsync(P.reps, 0xFF, (size_t)tsz * 4, stream));
+        CU(cudaMemsetAsync(P.out_n, 0, 8, stream));
+        const uint32_t grid = std::max(1u, std::min<uint32_t>((std::max(n_nodes, tsz) + 255u) / 256u, (uint32_t)num_sms * 8u));
+        k_pref_leaves<<<grid, 256, 0, stream>>>(P);
+        k_pref_emit<<<grid, 256, 0, stream>>>(P);
+        stats.kernel_launches += 2;
+        CU(cudaGetLastError());
+        uint32_t head[2] = {0, 0};
+        CU(cudaMemcpyAsync(head, P.out_n, 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        if (head[1]) { err = "pref_leaves: two leaves share a 64-bit fingerprint"; return PE_ERR_UNSUPPORTED; }
+        if (head[0] > out_cap) { err = "pref_leaves: more leaves than the caller's buffers hold"; return PE_ERR_OVERFLOW; }
+        if (head[0]) {
+            CU(cudaMemcpyAsync(out_tasks, P.out_tasks, (size_t)head[0] * 4, cudaMemcpyDeviceToHost, stream));
+            if (n_levels) CU(cudaMemcpyAsync(out_vals, P.out_vals, (size_t)head[0] * n_levels * 4, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
+        *out_n = head[0];
+        return PE_OK;
     }
 
     template <class T> int32_t snap_col(const T *col, uint32_t first, uint32_t n, T *out) {
@@ -1054,6 +1127,11 @@ int32_t pe_snapshot_ports(pe_engine *h, uint32_t slot, uint32_t first, uint32_t 
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++) out[i] = (w[i] >> (slot & 31)) & 1;
     return PE_OK;
+}
+
+int32_t pe_pref_leaves(pe_engine *h, uint32_t svc_id, const uint32_t *cols, uint32_t n_levels, uint32_t cap, uint32_t *out_vals,
+                       uint32_t *out_tasks, uint32_t *out_n_leaves) {
+    return h->pref_leaves(svc_id, cols, n_levels, cap, out_vals, out_tasks, out_n_leaves);
 }
 
 int32_t pe_get_stats(pe_engine *h, pe_stats *out) { *out = h->stats; return PE_OK; }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_classify(const ClassifyParams P) {
 // (constraint.NodeMatches constraint.go:107-207), PlatformFilter :272-312.
 __device__ __forceinline__ bool static_ok(const DevTable &T, const TickDev &K, const pe_group &g, uint32_t n, uint32_t meta) {
     const uint32_t fm = g.filter_mask;
-    bool ok = (meta & PE_NODE_VALID) != 0;
+    bool ok = (meta & PE_NODE_VALID) != 0 && (g.leaf_cnt == 0u || in_leaf(T, K, g, n));   // (leaf visits never take the batched path: engine.cu)
     if (fm & (1u << PE_F_READY)) ok = ok && (meta & PE_NODE_READY);
     if ((fm & (1u << PE_F_PLUGIN)) && (meta & PE_NODE_HAS_ENGINE)) {
         for (uint32_t i = 0; i < g.plug_cnt; i++) {

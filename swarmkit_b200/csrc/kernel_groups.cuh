@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(PE_GR_THREADS, 1) k_groups(const __grid_consta
         for (uint32_t p = p_lo + tid; p < p_hi; p += nth) {
             const uint32_t n = p + ts >= N ? p + ts - N : p + ts;
             const uint32_t meta = T.meta[n];
-            if (!(meta & PE_NODE_VALID)) { P.ff8[n] = 0xFF; continue; }
+            if (!(meta & PE_NODE_VALID) || (G.leaf_cnt && !in_leaf(T, K, G, n))) { P.ff8[n] = 0xFF; continue; }   // not in the node set / under another leaf
             const uint32_t sv = svccol[n];
             const uint32_t ff = eval_ctx(T, K, G, S.C, n, meta, sv);
             const uint32_t fails = G.fail_cnt ? fail_count(K, G, n) : 0u;

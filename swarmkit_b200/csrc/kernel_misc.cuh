@@ -57,6 +57,60 @@ __global__ void k_remove(DevTable T, const uint32_t *idx, uint32_t n) {
     if (i < n) T.meta[idx[i]] = 0;
 }
 
+// ---- placement preferences: the leaves of nodeSet.tree (nodeset.go:59-101) ------------------------------------
+// Every node of the set hangs under the leaf named by its values of the preference labels; a leaf's `tasks` is the sum
+// of ActiveTasksCountByService[service] over its nodes.  Leaves are found through an open-addressing table keyed by a
+// 64-bit fingerprint of the value tuple; k_pref_emit then checks every node's tuple against its leaf's representative
+// node, so a fingerprint collision is reported, never silently merged.
+struct PrefParams {
+    DevTable T;
+    const uint32_t *svccol;                 // the service's counter column
+    uint32_t cols[PE_MAX_PREF_LEVELS], n_levels;
+    unsigned long long *keys;               // [mask + 1] 0 = empty
+    uint32_t *sums, *reps;                  // [mask + 1] task sums; lowest node of the leaf (all ones at start)
+    uint32_t mask;
+    uint32_t *out_vals, *out_tasks, *out_n, *out_err;   // device staging of the result; out_err: 1 = collision
+    uint32_t cap;
+};
+__device__ __forceinline__ unsigned long long pref_key(const PrefParams &P, uint32_t n) {
+    unsigned long long h = 0x9E3779B97F4A7C15ull;
+    for (uint32_t l = 0; l < P.n_levels; l++) {
+        h ^= P.T.attr[P.cols[l]][n] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33;
+    }
+    return h ? h : 1ull;
+}
+__global__ void __launch_bounds__(256) k_pref_leaves(const PrefParams P) {
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < P.T.n_nodes; n += gridDim.x * blockDim.x) {
+        if (!(P.T.meta[n] & PE_NODE_VALID)) continue;
+        const unsigned long long key = pref_key(P, n);
+        for (uint32_t h = (uint32_t)(key >> 20) & P.mask;; h = (h + 1u) & P.mask) {
+            unsigned long long cur = P.keys[h];
+            if (cur == 0ull) cur = atomicCAS(&P.keys[h], 0ull, key), cur = cur == 0ull ? key : cur;
+            if (cur == key) { atomicAdd(&P.sums[h], P.svccol[n]); atomicMin(&P.reps[h], n); break; }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_pref_emit(const PrefParams P) {
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t n = t0; n < P.T.n_nodes; n += stride) {          // exactness: the node's tuple IS its leaf's tuple
+        if (!(P.T.meta[n] & PE_NODE_VALID)) continue;
+        const unsigned long long key = pref_key(P, n);
+        uint32_t h = (uint32_t)(key >> 20) & P.mask;
+        while (P.keys[h] != key) h = (h + 1u) & P.mask;
+        const uint32_t r = P.reps[h];
+        for (uint32_t l = 0; l < P.n_levels; l++) if (P.T.attr[P.cols[l]][n] != P.T.attr[P.cols[l]][r]) atomicOr(P.out_err, 1u);
+    }
+    for (uint32_t h = t0; h <= P.mask; h += stride) {
+        if (P.keys[h] == 0ull) continue;
+        const uint32_t i = atomicAdd(P.out_n, 1u);
+        if (i >= P.cap) continue;
+        const uint32_t r = P.reps[h];
+        for (uint32_t l = 0; l < P.n_levels; l++) P.out_vals[(size_t)i * P.n_levels + l] = P.T.attr[P.cols[l]][r];
+        P.out_tasks[i] = P.sums[h];
+    }
+}
+
 // Commutative part of the deltas: one thread each, atomics.
 __global__ void k_delta_add(DevTable T, const pe_task_delta *d, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

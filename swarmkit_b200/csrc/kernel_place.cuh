@@ -21,14 +21,16 @@
 //           Task i of a chunk gets i + 1 candidates: the i tasks before it take
 //           one node each, so the list cannot run out.  Written straight into
 //           CTA 0's shared memory (DSMEM).
-//   resolve (ordered, ONE warp, lanes = tasks, 32 tasks per step): every lane
-//           proposes its first candidate that nobody took in this chunk and that
-//           no lower lane proposes (match.any); a lane that loses moves on.  Lanes
-//           only move forward and a node given up by one lane is held by a lower
-//           one, so the fixed point is the sequential result.  A lane that skipped
-//           a candidate ranked strictly better than its choice (the node was taken
-//           inside the chunk: its rank moved) recomputes those ranks from the
-//           chunk's log -- exactly.
+//   resolve (ordered, ONE warp of CTA 0, lanes = tasks, 32 tasks per group, the
+//           chunk's four groups one after the other): every lane proposes its
+//           first candidate that no final task took; lanes that propose the same
+//           node find each other with match.any and all but the lowest move on.
+//           Lanes only move forward and a node given up by one lane is held by a
+//           lower one, so the fixed point is the sequential result.  Nothing in a
+//           round leaves the warp: no block barrier, no shared-memory atomics.  A
+//           lane that skipped a candidate ranked strictly better than its choice
+//           (the node was taken inside the chunk: its rank moved) recomputes those
+//           ranks from the chunk's log -- exactly.
 //   commit  (parallel, CTA 0): NodeInfo.addTask for the chunk's placements as
 //           reductions on the global columns, the batch's touched bitmap.
 //
@@ -46,16 +48,16 @@
 namespace pe {
 namespace cg = cooperative_groups;
 
-#define PE_PL_CLUSTER 8
+#define PE_PL_CLUSTER 8                                        // CTAs per cluster: 8 (portable) or 16 (opt-in), chosen at launch
+#define PE_PL_CLUSTER_MAX 16
 #define PE_PL_WARPS 16
 #define PE_PL_THREADS (PE_PL_WARPS * 32)
-#define PE_PL_CHUNK (PE_PL_CLUSTER * PE_PL_WARPS)              // tasks per chunk = warps in the cluster
+#define PE_PL_CHUNK (PE_PL_CLUSTER_MAX * PE_PL_WARPS)          // most tasks per chunk (a chunk = the warps in the cluster)
+#define PE_PL_SCR 128                                          // words per scratch buffer of a staging warp (>= 2 * PE_PL_K)
 #define PE_PL_K 64                                             // candidates per task (task i of a chunk asks for min(i + 1, K))
 #define PE_PL_KS (PE_PL_K + 1)                                 // row stride of the candidate table in words: odd, so that the 32 lanes
                                                                // of the resolve warp reading candidate j of 32 consecutive rows hit 32 banks
-#define PE_PL_HASH 8192                                        // the chunk's node table: one entry per distinct candidate node (a chunk
-                                                               // stages at most 64*65/2 + 64*64 = 6176 candidates)
-#define PE_PL_FREE 0xFFFFFFFFu                                 // hold value of a node nobody holds
+#define PE_PL_HASH 2048                                        // the chunk's set of nodes given a task inside this chunk (at most PE_PL_CHUNK)
 #define PE_PL_EMPTY 0xFFFFFFFFu
 #define PE_PL_TOUCHED 0x80000000u    // candidate flag: the node already carried a task of this batch when the chunk began (a touched
                                      // member of the best class in a tail).  Such a node can only be "taken in this chunk" by a task
@@ -97,22 +99,20 @@ struct PlSlot {
 struct PlShared {
     PlSlot slot[PE_PL_CHUNK];
     uint32_t cand[PE_PL_CHUNK * PE_PL_KS];
-    uint16_t cslot[PE_PL_CHUNK * PE_PL_KS];     // the candidate's entry of the node table (the stage phase looked it up)
     // what the resolve warp reads of every slot, as arrays (a 96-byte struct stride would put 32 lanes on 4 banks)
     uint16_t s_ncand[PE_PL_CHUNK], s_rs1[PE_PL_CHUNK], s_rs2[PE_PL_CHUNK], s_rs3[PE_PL_CHUNK];
     uint8_t s_kind[PE_PL_CHUNK];
-    uint32_t hkey[PE_PL_HASH];                 // node proposed / taken inside this chunk
-    uint32_t hold[PE_PL_HASH];                 // 0: taken (final); lane + 1: proposed by that lane of the current group; PE_PL_FREE
+    uint32_t hkey[PE_PL_HASH];                 // open addressing: nodes given a task inside this chunk
     uint32_t log_node[PE_PL_CHUNK];
     uint16_t log_task[PE_PL_CHUNK];            // task (chunk-relative = slot index)
     uint8_t log_tail[PE_PL_CHUNK];             // 1: the choice came from rank group >= 1
     uint32_t n_log, stop, cut, done;            // done: tasks of the chunk the resolve phase settled (the next chunk starts after them)
-    uint32_t first_active, badmin, again[2], leave;   // resolve: pass start, lowest special task, "somebody moved" per round parity
+    uint32_t leave;                             // resolve: the chunk ends at S.done (a task to stage again, or one the ordered sequencer takes)
     uint32_t wd;                                // watchdog: a loop of this chunk ran away (bit per loop); the chunk is handed to the ordered sequencer untouched
-    uint32_t scratch[PE_PL_WARPS][3][PE_PL_CHUNK];   // per warp: tail gather buffers, the candidate list under construction
+    uint32_t scratch[PE_PL_WARPS][3][PE_PL_SCR];   // per warp: tail gather buffers, the candidate list under construction
 };
 
-__device__ __forceinline__ uint32_t pl_hash(uint32_t node) { return (node * 2654435761u) >> 19; }   // 13 bits
+__device__ __forceinline__ uint32_t pl_hash(uint32_t node) { return (node * 2654435761u) >> 21; }   // 11 bits
 
 
 __device__ __forceinline__ unsigned long long pl_wmin64(unsigned long long v) {
@@ -245,21 +245,19 @@ __device__ __forceinline__ PlPre pl_prefetch(const PlaceParams &P, uint32_t task
     return q;
 }
 
-// The entry of the chunk's node table for a candidate node.  Every thread of CTA 0 looks up a share of the chunk's
-// candidates before the resolve phase, so that a proposal there is ONE atomicMin on a known entry instead of a hash
-// probe on the critical path.
-__device__ __forceinline__ uint32_t pl_slot_of(PlShared &S, uint32_t node) {
-    uint32_t h = pl_hash(node);
-    for (uint32_t probes = 0; probes < PE_PL_HASH; probes++, h = (h + 1u) & (PE_PL_HASH - 1u)) {
+// The set of nodes given a task inside the current chunk (CTA 0's shared memory; one warp reads and writes it).
+__device__ __forceinline__ bool pl_taken(const PlShared &S, uint32_t node) {
+    for (uint32_t h = pl_hash(node);; h = (h + 1u) & (PE_PL_HASH - 1u)) {
         const uint32_t k = S.hkey[h];
-        if (k == node) return h;
-        if (k == PE_PL_EMPTY) {
-            const uint32_t old = atomicCAS(&S.hkey[h], PE_PL_EMPTY, node);
-            if (old == PE_PL_EMPTY || old == node) return h;
-        }
+        if (k == node) return true;
+        if (k == PE_PL_EMPTY) return false;      // (at most PE_PL_CHUNK of PE_PL_HASH entries are ever used)
     }
-    atomicOr(&S.wd, 1u);          // (cannot happen: the table outnumbers a chunk's candidates; the chunk is handed over if it does)
-    return 0u;
+}
+__device__ __forceinline__ void pl_take(PlShared &S, uint32_t node) {   // (lanes of one warp may insert together)
+    for (uint32_t h = pl_hash(node);; h = (h + 1u) & (PE_PL_HASH - 1u)) {
+        const uint32_t old = atomicCAS(&S.hkey[h], PE_PL_EMPTY, node);
+        if (old == PE_PL_EMPTY || old == node) return;
+    }
 }
 
 __device__ __forceinline__ void pl_stage(const PlaceParams &P, const PlPre &pre, uint32_t *scr_a, uint32_t *scr_b, uint32_t *cand, PlShared *S0,
@@ -366,180 +364,168 @@ __device__ __forceinline__ unsigned long long pl_key_of(const PlSlot &s, uint32_
 }
 
 // ---- resolve: warp 0 of CTA 0, lanes = tasks ------------------------------------------------------------
-// Deferred acceptance with the tasks' order as every node's preference: a lane proposes its first candidate that is
-// not taken; the node keeps the LOWEST lane that proposed (one shared-memory atomicMin on the node's entry of the
-// in-chunk table) and a lane that finds a lower lane -- or a final placement (0) -- there moves on.  A lane only gives
-// a node up to a lower lane, so what the lanes hold when nobody moves any more is what the reference's
-// one-task-at-a-time loop produces.  The loop is written as warp-uniform rounds (skip / propose / re-check) so that
-// the 32 lanes stay converged: a lone warp pays ~7 cycles per instruction, divergence multiplies that.
-// BM: CTA 0 also keeps the batch's touched bitmap in shared memory (tk): candidates that were untouched when the chunk
-// began are skipped eight at a time while their bit is set (= taken inside this chunk) before anything is proposed.
-struct PlProf { unsigned long long rounds, passes, retries, attempts, masks; long long cyc_mask, cyc_attempt, cyc_check, cyc_final, cyc_work, cyc_own; };   // (cycles: this thread's view)
+// Deferred acceptance with the tasks' order as every node's preference, 32 tasks (one group) at a time: a lane
+// proposes its first candidate that no FINAL task holds; lanes proposing the same node find each other with match.any
+// and every lane but the lowest moves on to its next candidate.  A lane only gives a node up to a lower lane, and lower
+// GROUPS are final before a group starts, so what the lanes hold when nobody moves any more is what the reference's
+// one-task-at-a-time loop produces.  A round is a handful of warp-synchronous instructions: no block barrier and no
+// shared-memory atomic is on the path (the first version of this step ran all four groups together with a block
+// barrier per round: ~4200 cycles per round, ~8 rounds per chunk).
+// Final tasks are known by: the batch's touched bitmap kept in CTA 0's shared memory (tk, BM = true) for candidates that
+// were untouched when the chunk began; the chunk's own set of taken nodes (hkey) for candidates flagged PE_PL_TOUCHED
+// (their bit was set before the chunk began) and for every candidate when the node table is too big for tk.
+struct PlProf { unsigned long long passes, rounds, retries; };
 
-
-// (every thread of CTA 0 walks through the resolve phase so that its barriers are plain __syncthreads: a named barrier
-// over the four working warps measured ~2900 cycles per use here against ~100 for the block-wide one)
-__device__ __forceinline__ void pl_rbar() { __syncthreads(); }
-
-// Threads 0 .. PE_PL_CHUNK - 1 of CTA 0, thread = task of the chunk.  The priority a node's entry keeps is the task's
-// position in the chunk + 1 (0 = final), so the whole chunk settles in one pass: nothing in the argument above depends
-// on the 32 tasks of a warp being special.  Four warps on four schedulers also hide each other's latencies, which one
-// warp alone cannot (a lone warp pays ~8 cycles per instruction here).
 template <bool BM>
-__device__ __forceinline__ void pl_resolve(const PlaceParams &P, PlShared &S, uint32_t *tk, uint32_t c0_task, uint32_t nc, uint32_t tid,
+__device__ __forceinline__ void pl_resolve(const PlaceParams &P, PlShared &S, uint32_t *tk, uint32_t c0_task, uint32_t nc, uint32_t lane,
                                            uint32_t &n_amb, PlProf &prof) {
-    const uint32_t i = tid, lane = tid & 31u;
-    const bool present = i < nc;
-    const uint32_t is = present ? i : 0u;
-    const PlSlot &sl = S.slot[is];
-    const uint32_t *cd = S.cand + (size_t)is * PE_PL_KS;
-    const uint16_t *cs = S.cslot + (size_t)is * PE_PL_KS;
-    const uint32_t n_cand = present ? S.s_ncand[is] : 0u;
-    const uint32_t rs1 = S.s_rs1[is], rs2 = S.s_rs2[is], rs3 = S.s_rs3[is];
-    const bool unusable = present && S.s_kind[is] != 0u;
-    auto rank_of = [&](uint32_t j) -> uint32_t { return (j >= rs1 ? 1u : 0u) + (j >= rs2 ? 1u : 0u) + (j >= rs3 ? 1u : 0u); };
-    // Which of candidates [jb, jb + 16) may still be proposed?  The bitmap only changes when tasks are made final, so inside
-    // a pass this is computed once per 16 candidates, with all 32 shared-memory loads in flight together.  A candidate
-    // flagged PE_PL_TOUCHED carried a task before the chunk began: whether a task of THIS chunk joined it is for the node
-    // table to say when it is proposed.
-    auto load_mask = [&](uint32_t jb) -> uint32_t {
-        uint32_t x[16], w[16], mask = 0;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    if (lane == 0) { S.n_log = 0; S.leave = 0; S.cut = PE_NONE; S.done = nc; }
+    __syncwarp();
+    bool leave = false;
+    for (uint32_t g0 = 0; g0 < nc && !leave; g0 += 32u) {
+        const uint32_t i = g0 + lane;
+        const bool present = i < nc;
+        const uint32_t is = present ? i : 0u;
+        const PlSlot &sl = S.slot[is];
+        const uint32_t *cd = S.cand + (size_t)is * PE_PL_KS;
+        const uint32_t n_cand = present ? S.s_ncand[is] : 0u;
+        const uint32_t rs1 = S.s_rs1[is], rs2 = S.s_rs2[is], rs3 = S.s_rs3[is];
+        const bool unusable = present && S.s_kind[is] != 0u;
+        auto rank_of = [&](uint32_t j) -> uint32_t { return (j >= rs1 ? 1u : 0u) + (j >= rs2 ? 1u : 0u) + (j >= rs3 ? 1u : 0u); };
+        // Which of candidates [jb, jb + 16) may still be proposed as far as the bitmap knows?  It only changes when tasks
+        // are made final, i.e. between passes: computed once per 16 candidates, the 32 shared-memory loads in flight together.
+        auto load_mask = [&](uint32_t jb) -> uint32_t {
+            uint32_t x[16], w[16], mask = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) x[k] = jb + (uint32_t)k < n_cand ? cd[jb + (uint32_t)k] : 0u;     // (past the list: node 0, masked out below)
-        if (BM) {
+            for (int k = 0; k < 16; k++) x[k] = jb + (uint32_t)k < n_cand ? cd[jb + (uint32_t)k] : 0u;     // (past the list: node 0, masked out below)
+            if (BM) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) w[k] = tk[PE_PL_NODE(x[k]) >> 5];
-        }
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const bool in = jb + (uint32_t)k < n_cand;
-            const bool taken = BM && !(x[k] & PE_PL_TOUCHED) && ((w[k] >> (x[k] & 31u)) & 1u);
-            mask |= (in && !taken ? 1u : 0u) << k;
-        }
-        return mask;
-    };
-    if (tid == 0) { S.first_active = 0; S.n_log = 0; S.leave = 0; S.cut = PE_NONE; S.done = nc; }
-    pl_rbar();
-    for (uint32_t pass = 0;; pass++) {
-        if (S.wd || pass > 2u * PE_PL_CHUNK) {
-            // a loop ran away (or the node table overflowed while staging): nothing of this chunk is placed here
-            pl_rbar();
-            if (tid == 0) { S.wd |= pass > 2u * PE_PL_CHUNK ? 2u : 0u; S.n_log = 0; S.cut = c0_task; S.done = 0; }
-            pl_rbar();
-            break;
-        }
-        const uint32_t fa = S.first_active;
-        const bool act = present && i >= fa && !unusable;
-        const long long tp0 = clock64();
-        uint32_t jb = 0, mask = act ? load_mask(0u) : 0u, j = 0, myh = PE_PL_EMPTY, prop = PE_NONE;
-        bool moving = act, dead = false;
-        if (tid == 0) { S.again[0] = 0; S.again[1] = 0; S.badmin = PE_NONE; prof.passes++; }
-        pl_rbar();
-        long long tp1 = clock64();
-        prof.cyc_mask += tp1 - tp0;
-        bool ranaway = false;
-        for (uint32_t r = 0;; r++) {
-            // a moving task proposes until a node keeps it: final placements (0) and lower tasks send it on at once
-            const long long to0 = clock64();
-            while (moving) {
-                if (mask == 0u) {
-                    jb += 16u;
-                    if (jb >= n_cand) { moving = false; dead = true; myh = PE_PL_EMPTY; break; }    // out of candidates
-                    mask = load_mask(jb);
-                    prof.masks++;
-                    continue;
-                }
-                prof.attempts++;
-                const uint32_t k = (uint32_t)__ffs((int)mask) - 1u;
-                mask &= mask - 1u;
-                j = jb + k;
-                const uint32_t h = cs[j];
-                if (S.hold[h] < i + 1u) continue;                // final (0) or a lower task's (plain load: an entry only ever goes down)
-                const uint32_t prev = atomicMin(&S.hold[h], i + 1u);
-                if (prev < i + 1u) continue;
-                myh = h; moving = false;                         // (a higher task that held it finds out below)
+                for (int k = 0; k < 16; k++) w[k] = tk[PE_PL_NODE(x[k]) >> 5];
             }
-            prof.cyc_own += clock64() - to0;
-            pl_rbar();
-            { const long long tq = clock64(); prof.cyc_attempt += tq - tp1; tp1 = tq; }
-            if (tid == 0) { S.again[(r + 1u) & 1u] = 0; prof.rounds++; }        // (everybody has read it: see the barrier above)
-            if (myh != PE_PL_EMPTY && S.hold[myh] != i + 1u) { myh = PE_PL_EMPTY; moving = true; }   // a lower task took it
-            if (__any_sync(0xFFFFFFFFu, moving) && lane == 0) S.again[r & 1u] = 1;
-            prof.cyc_work += clock64() - tp1;
-            pl_rbar();
-            { const long long tq = clock64(); prof.cyc_check += tq - tp1; tp1 = tq; }
-            if (!S.again[r & 1u]) break;
-            if (r > 64u * PE_PL_CHUNK) { ranaway = true; break; }     // (uniform: r is the same in every thread)
-        }
-        if (ranaway) { if (tid == 0) S.wd |= 4u; pl_rbar(); continue; }
-        const bool valid = act && myh != PE_PL_EMPTY;
-        if (valid) prop = PE_PL_NODE(cd[j]);
-        const bool isbad = present && i >= fa && !valid;
-        // a task that ran out of a list that was cut at PE_PL_K candidates is staged again with what follows it
-        const bool isretry = isbad && !unusable && dead && n_cand == (uint32_t)PE_PL_K && i + 1u > (uint32_t)PE_PL_K;
-        const bool isamb = valid && j > 0u && rank_of(0u) < rank_of(j);
-        if (isbad || isamb) atomicMin(&S.badmin, i);
-        pl_rbar();
-        const uint32_t bad = S.badmin;
-        // tasks below the first special task are final: log them, mark their nodes taken
-        auto log_task = [&](uint32_t node, uint32_t jj) {
-            const uint32_t e = atomicAdd(&S.n_log, 1u);
-            S.log_node[e] = node; S.log_task[e] = (uint16_t)i; S.log_tail[e] = rank_of(jj) != 0u ? 1 : 0;
-            if (BM) atomicOr(&tk[node >> 5], 1u << (node & 31u));
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const bool in = jb + (uint32_t)k < n_cand;
+                const bool taken = BM && !(x[k] & PE_PL_TOUCHED) && ((w[k] >> (x[k] & 31u)) & 1u);
+                mask |= (in && !taken ? 1u : 0u) << k;
+            }
+            return mask;
         };
-        if (valid && i < bad) { log_task(prop, j); S.hold[myh] = 0u; }
-        else if (valid && i > bad) S.hold[myh] = PE_PL_FREE;       // this task proposes again after the special task is settled
-        pl_rbar();
-        if (bad == PE_NONE) { prof.cyc_final += clock64() - tp1; break; }
-        if (i == bad) {
-            if (isretry) { S.done = bad; S.leave = 1; prof.retries++; }      // the chunk ends here; the next one starts with this task
-            else if (isbad) { S.cut = c0_task + bad; S.done = bad; S.leave = 1; }   // not placeable here: the ordered sequencer takes over
-            else {
-                // ---- it skipped a candidate that ranked strictly better than its choice when the chunk began.  That node
-                // was taken inside the chunk, so its rank moved: recompute it from the chunk's log.
-                n_amb++;
-                const uint32_t n_log = S.n_log;
-                unsigned long long bk = pl_key_of(sl, rank_of(j));
-                uint32_t bn = prop, bj = j;
-                for (uint32_t q = 0; q < j; q++) {
-                    const uint32_t n = PE_PL_NODE(cd[q]);
-                    const unsigned long long k0 = pl_key_of(sl, rank_of(q));
-                    uint32_t svc = (uint32_t)(k0 >> 32) & 0xFFFFFFu, tot = (uint32_t)k0;
-                    long long dcpu = 0, dmem = 0;
-                    for (uint32_t e = 0; e < n_log; e++) {          // every placement of this chunk on that node (rare path)
-                        if (S.log_node[e] != n) continue;
-                        const PlSlot &o = S.slot[S.log_task[e]];
-                        tot++;
-                        if (o.svccol == sl.svccol) svc++;
-                        dcpu += o.cpu_res; dmem += o.mem_res;
-                    }
-                    bool ok = true;
-                    if (sl.flags & PE_SR_RES)      // (the columns still hold the chunk-start amounts: reductions come after this phase)
-                        ok = sl.cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) - dcpu &&
-                             sl.mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n)) - dmem;
-                    if (sl.flags & PE_SR_MAXREP) ok = ok && (unsigned long long)svc < sl.max_replicas;
-                    const unsigned long long k = make_pref(0u, svc, tot);
-                    if (ok && (k < bk || (k == bk && n < bn))) { bk = k; bn = n; bj = q; }
-                }
-                // the node it held goes to it for good, or back (the winner was taken before: its entry is final already)
-                S.hold[myh] = bn == prop ? 0u : PE_PL_FREE;
-                log_task(bn, bj);
-                S.first_active = bad + 1u;
+        uint32_t fa = g0;                           // tasks of the group below fa are final
+        for (uint32_t pass = 0; !leave; pass++) {
+            if (S.wd || pass > 2u * 32u + 2u) {
+                // a loop ran away: nothing more of this chunk is placed here (what is logged so far is final and stays)
+                if (lane == 0) { S.wd |= 2u; S.cut = c0_task + fa; S.done = fa; S.leave = 1; }
+                leave = true;
+                break;
             }
+            const bool act = present && i >= fa && !unusable;
+            uint32_t jb = 0, mask = act ? load_mask(0u) : 0u, j = 0, prop = 0;
+            bool moving = act, dead = false, have = false;
+            prof.passes += lane == 0 ? 1u : 0u;
+            for (uint32_t r = 0;; r++) {
+                // every moving lane walks to its next candidate that no final task holds (lock-step: one candidate per turn)
+                while (__any_sync(0xFFFFFFFFu, moving)) {
+                    if (moving) {
+                        if (mask == 0u) {
+                            jb += 16u;
+                            if (jb >= n_cand) { moving = false; dead = true; }         // out of candidates
+                            else mask = load_mask(jb);
+                        } else {
+                            const uint32_t k = (uint32_t)__ffs((int)mask) - 1u;
+                            mask &= mask - 1u;
+                            j = jb + k;
+                            const uint32_t c = cd[j];
+                            const bool ask = !BM || (c & PE_PL_TOUCHED);               // the bitmap could not tell
+                            if (!(ask && pl_taken(S, PE_PL_NODE(c)))) { prop = PE_PL_NODE(c); have = true; moving = false; }
+                        }
+                    }
+                }
+                // lanes that propose the same node: all but the lowest move on (a higher lane that held it before finds out here)
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, have ? prop : (0x80000000u | lane));
+                const bool lose = have && (same & lane_lt) != 0u;
+                prof.rounds += lane == 0 ? 1u : 0u;
+                if (!__any_sync(0xFFFFFFFFu, lose)) break;
+                if (lose) { have = false; moving = true; }
+                if (r > 64u * PE_PL_K) { if (lane == 0) S.wd |= 4u; break; }       // (uniform; the pass loop sees S.wd)
+            }
+            __syncwarp();
+            if (S.wd) continue;
+            const bool valid = act && have;
+            const bool isbad = present && i >= fa && !valid;
+            // a task that ran out of a list that was cut at PE_PL_K candidates is staged again with what follows it
+            const bool isretry = isbad && !unusable && dead && n_cand == (uint32_t)PE_PL_K && i + 1u > (uint32_t)PE_PL_K;
+            const bool isamb = valid && j > 0u && rank_of(0u) < rank_of(j);
+            const uint32_t bad = __reduce_min_sync(0xFFFFFFFFu, (isbad || isamb) ? lane : 32u);     // lowest special lane of the group
+            // tasks below the first special task are final: log them (task order), mark their nodes taken
+            const bool fin = valid && lane < bad;
+            const uint32_t finm = __ballot_sync(0xFFFFFFFFu, fin);
+            const uint32_t base = S.n_log;
+            if (fin) {
+                const uint32_t e = base + __popc(finm & lane_lt);
+                S.log_node[e] = prop; S.log_task[e] = (uint16_t)i; S.log_tail[e] = rank_of(j) != 0u ? 1 : 0;
+                if (BM) atomicOr(&tk[prop >> 5], 1u << (prop & 31u));
+                pl_take(S, prop);
+            }
+            __syncwarp();
+            if (lane == 0) S.n_log = base + __popc(finm);
+            __syncwarp();
+            if (bad == 32u) break;                  // the whole group is final
+            if (lane == bad) {
+                if (isretry) { S.done = i; S.leave = 1; prof.retries++; }          // the chunk ends here; the next one starts with this task
+                else if (isbad) { S.cut = c0_task + i; S.done = i; S.leave = 1; }    // not placeable here: the ordered sequencer takes over
+                else {
+                    // ---- it skipped a candidate that ranked strictly better than its choice when the chunk began.  That node
+                    // was taken inside the chunk, so its rank moved: recompute it from the chunk's log.
+                    n_amb++;
+                    const uint32_t n_log = S.n_log;
+                    unsigned long long bk = pl_key_of(sl, rank_of(j));
+                    uint32_t bn = prop, bj = j;
+                    for (uint32_t q = 0; q < j; q++) {
+                        const uint32_t n = PE_PL_NODE(cd[q]);
+                        const unsigned long long k0 = pl_key_of(sl, rank_of(q));
+                        uint32_t svc = (uint32_t)(k0 >> 32) & 0xFFFFFFu, tot = (uint32_t)k0;
+                        long long dcpu = 0, dmem = 0;
+                        for (uint32_t e = 0; e < n_log; e++) {          // every placement of this chunk on that node (rare path)
+                            if (S.log_node[e] != n) continue;
+                            const PlSlot &o = S.slot[S.log_task[e]];
+                            tot++;
+                            if (o.svccol == sl.svccol) svc++;
+                            dcpu += o.cpu_res; dmem += o.mem_res;
+                        }
+                        bool ok = true;
+                        if (sl.flags & PE_SR_RES)      // (the columns still hold the chunk-start amounts: reductions come after this phase)
+                            ok = sl.cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) - dcpu &&
+                                 sl.mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n)) - dmem;
+                        if (sl.flags & PE_SR_MAXREP) ok = ok && (unsigned long long)svc < sl.max_replicas;
+                        const unsigned long long k = make_pref(0u, svc, tot);
+                        if (ok && (k < bk || (k == bk && n < bn))) { bk = k; bn = n; bj = q; }
+                    }
+                    // (a winner other than its own proposal was taken before: it is in the bitmap and the set already)
+                    const uint32_t e = S.n_log;
+                    S.log_node[e] = bn; S.log_task[e] = (uint16_t)i; S.log_tail[e] = rank_of(bj) != 0u ? 1 : 0;
+                    S.n_log = e + 1u;
+                    if (BM) atomicOr(&tk[bn >> 5], 1u << (bn & 31u));
+                    pl_take(S, bn);
+                }
+            }
+            __syncwarp();
+            leave = S.leave != 0u;
+            fa = g0 + bad + 1u;                     // the tasks above the special one propose again, from their first candidate
         }
-        pl_rbar();
-        prof.cyc_final += clock64() - tp1;
-        if (S.leave) break;
     }
-    if (tid == 0) S.stop = S.cut == PE_NONE ? 0u : 1u;
+    __syncwarp();
+    if (lane == 0) S.stop = S.cut == PE_NONE ? 0u : 1u;
 }
 
 static inline size_t place_smem_bytes(uint32_t tk_words) { return sizeof(PlShared) + (size_t)tk_words * 4 + 16; }
 static_assert(sizeof(PlShared) + 18432u * 4 + 16 <= 232448, "k_place: shared memory budget");
-static_assert(PE_PL_K * (PE_PL_K + 1) / 2 + (PE_PL_CHUNK - PE_PL_K) * PE_PL_K < PE_PL_HASH, "k_place: node table too small");
+static_assert(PE_PL_SCR >= 2 * PE_PL_K, "k_place: scratch buffers hold a candidate list");
+static_assert(4 * PE_PL_CHUNK <= PE_PL_HASH, "k_place: the set of taken nodes must stay sparse");
 #define PE_PL_TK_MAX_WORDS 18432u     // 72 KB of touched bitmap next to the slots and the node table: up to ~590 k nodes
 
-__global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_THREADS, 1) k_place(const __grid_constant__ PlaceParams P) {
+// (launched with a cluster dimension attribute: gridDim.x = the cluster size = 8 or 16)
+__global__ void __launch_bounds__(PE_PL_THREADS, 1) k_place(const __grid_constant__ PlaceParams P) {
     extern __shared__ __align__(16) unsigned char pl_smem[];
     PlShared &S = *reinterpret_cast<PlShared *>(pl_smem);
     uint32_t *tk = reinterpret_cast<uint32_t *>(pl_smem + ((sizeof(PlShared) + 15) & ~(size_t)15));
@@ -548,7 +534,7 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     PlShared *S0 = cluster.map_shared_rank(&S, 0);     // CTA 0's copy: the slots every CTA stages into
 
-    for (uint32_t h = tid; h < PE_PL_HASH; h += blockDim.x) { S.hkey[h] = PE_PL_EMPTY; S.hold[h] = PE_PL_FREE; }
+    for (uint32_t h = tid; h < PE_PL_HASH; h += blockDim.x) S.hkey[h] = PE_PL_EMPTY;
     if (crank == 0) for (uint32_t w = tid; w < P.tk_words; w += blockDim.x) tk[w] = 0u;
     if (tid == 0) { S.n_log = 0; S.stop = 0; S.cut = PE_NONE; S.wd = 0; }
     uint32_t n_tail = 0, n_amb = 0, n_fast = 0, n_medium = 0, n_chunks = 0;
@@ -556,12 +542,13 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
     PlProf prof{};
     cluster.sync();
 
+    const uint32_t chunk_cap = cluster.num_blocks() * PE_PL_WARPS;     // tasks per chunk = warps in the cluster
     const uint32_t slot_i = crank * PE_PL_WARPS + warp;          // the chunk task this warp stages
     PlPre pre{};
     uint32_t pre_task = PE_NONE;
     if (slot_i < P.B) { pre = pl_prefetch(P, slot_i); pre_task = slot_i; }
     for (uint32_t c0 = 0; c0 < P.B;) {
-        const uint32_t nc = min((uint32_t)PE_PL_CHUNK, P.B - c0);
+        const uint32_t nc = min(chunk_cap, P.B - c0);
         const long long t0 = clock64();
         if (slot_i < nc) {
             if (pre_task != c0 + slot_i) pre = pl_prefetch(P, c0 + slot_i);      // (the previous chunk ended early)
@@ -572,13 +559,10 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
         pre_task = c0 + nc + slot_i;                            // the next chunk's task, if this one runs to its end: loads fly during resolve
         if (pre_task < P.B) pre = pl_prefetch(P, pre_task);
         if (crank == 0) {
-            for (uint32_t idx = tid; idx < nc * PE_PL_KS; idx += blockDim.x) {       // node-table entries of the chunk's candidates
-                const uint32_t i = idx / PE_PL_KS, e = idx - i * PE_PL_KS;
-                if (e < S.s_ncand[i]) S.cslot[idx] = (uint16_t)pl_slot_of(S, PE_PL_NODE(S.cand[idx]));
+            if (warp == 0) {
+                if (P.tk_words) pl_resolve<true>(P, S, tk, c0, nc, lane, n_amb, prof);
+                else pl_resolve<false>(P, S, tk, c0, nc, lane, n_amb, prof);
             }
-            __syncthreads();
-            if (P.tk_words) pl_resolve<true>(P, S, tk, c0, nc, tid, n_amb, prof);
-            else pl_resolve<false>(P, S, tk, c0, nc, tid, n_amb, prof);
             __syncthreads();
             const long long t2 = clock64();
             // ---- commit: NodeInfo.addTask (nodeinfo.go:125-153) for the chunk's placements, from the slots alone
@@ -610,7 +594,7 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
                 if (S.log_tail[e]) n_medium++; else n_fast++;
             }
             __syncthreads();
-            for (uint32_t h = tid; h < PE_PL_HASH; h += blockDim.x) { S.hkey[h] = PE_PL_EMPTY; S.hold[h] = PE_PL_FREE; }   // the node table is per chunk
+            for (uint32_t h = tid; h < PE_PL_HASH; h += blockDim.x) S.hkey[h] = PE_PL_EMPTY;     // the set of taken nodes is per chunk
             __threadfence();        // the chunk's reductions are performed before anyone passes the barrier
             cyc_resolve += t2 - t1; cyc_commit += clock64() - t2;
         }
@@ -624,7 +608,8 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
     cluster.sync();                                             // CTA 0's shared memory stays alive until every CTA is done with it
     // tallies: per-thread counters -> one atomic per warp
     n_tail = __reduce_add_sync(0xFFFFFFFFu, lane == 0 ? n_tail : 0u);
-    n_amb = __reduce_add_sync(0xFFFFFFFFu, n_amb);                 // (counted by whichever resolve thread of CTA 0 re-ranked)
+    n_amb = __reduce_add_sync(0xFFFFFFFFu, n_amb);                 // (counted by whichever resolve lane of CTA 0 re-ranked)
+    const uint32_t n_retry = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)prof.retries);
     n_fast = __reduce_add_sync(0xFFFFFFFFu, n_fast);
     n_medium = __reduce_add_sync(0xFFFFFFFFu, n_medium);
     if (lane == 0) {
@@ -645,13 +630,7 @@ __global__ void __cluster_dims__(PE_PL_CLUSTER, 1, 1) __launch_bounds__(PE_PL_TH
         atomicAdd(&P.ctr->place_cyc[1], (unsigned long long)cyc_resolve);
         atomicAdd(&P.ctr->place_cyc[2], (unsigned long long)cyc_commit);
         // resolve-phase diagnostics (bench.py "place.resolve"): passes over a 32-task group, proposal rounds, chunks ended early
-        atomicAdd(&P.ctr->prof[0], prof.passes); atomicAdd(&P.ctr->prof[1], prof.rounds); atomicAdd(&P.ctr->prof[2], prof.retries);
-        atomicAdd(&P.ctr->prof[3], (unsigned long long)prof.cyc_mask); atomicAdd(&P.ctr->prof[4], (unsigned long long)prof.cyc_attempt);
-        atomicAdd(&P.ctr->prof[5], (unsigned long long)prof.cyc_check); atomicAdd(&P.ctr->prof[6], (unsigned long long)prof.cyc_final);
-    }
-    if (crank == 0 && lane == 31 && warp < 4) {     // last task of each resolve warp: its attempts and the cycles it spent proposing
-        atomicAdd(&P.ctr->prof[8 + 2 * warp], prof.attempts); atomicAdd(&P.ctr->prof[9 + 2 * warp], (unsigned long long)prof.cyc_own);
-        if (warp == 3) atomicAdd(&P.ctr->prof[2], prof.masks);
+        atomicAdd(&P.ctr->prof[0], prof.passes); atomicAdd(&P.ctr->prof[1], prof.rounds); atomicAdd(&P.ctr->prof[2], (unsigned long long)n_retry);
     }
 }
 

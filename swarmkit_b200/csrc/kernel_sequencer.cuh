@@ -1169,7 +1169,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
 #pragma unroll 2
             for (uint32_t n = tid; n < N; n += nth) {
                 const uint32_t meta = T.meta[n];
-                if (!(meta & PE_NODE_VALID)) continue;
+                if (!(meta & PE_NODE_VALID) || (G.leaf_cnt && !in_leaf(T, K, G, n))) continue;
                 const uint32_t sv = svccol[n];
                 const uint32_t tot = T.total[n];
                 const uint32_t ff = eval_ctx(T, K, G, S.C, n, meta, sv);
@@ -1225,7 +1225,7 @@ __global__ void __launch_bounds__(PE_SEQ_THREADS, 1) k_sequencer(const __grid_co
         uint32_t o32 = 0, a32 = ~0u;
         for (uint32_t n = tid; n < N; n += nth) {
             const uint32_t meta = T.meta[n];
-            if (!(meta & PE_NODE_VALID)) { P.ff8[n] = 0xFF; continue; }
+            if (!(meta & PE_NODE_VALID) || (G.leaf_cnt && !in_leaf(T, K, G, n))) { P.ff8[n] = 0xFF; continue; }   // not in the node set / under another leaf
             const uint32_t sv = svccol[n];
             const uint32_t ff = eval_ctx(T, K, G, S.C, n, meta, sv);
             const uint32_t fails = G.fail_cnt ? fail_count(K, G, n) : 0u;

@@ -34,6 +34,16 @@ __device__ __forceinline__ bool gen_enough(int64_t cell, int64_t want) {
     return (cell & 3) != PE_GEN_ABSENT && want <= (cell >> 2);
 }
 
+// nodeSet.tree's branch walk (nodeset.go:59-101) seen from one leaf of the preference tree: is the node under it?
+// (pe_group.leaf_cnt terms follow the group's constraints; a group without preferences has none.)
+__device__ __forceinline__ bool in_leaf(const DevTable &T, const TickDev &K, const pe_group &g, uint32_t n) {
+    for (uint32_t i = 0; i < g.leaf_cnt; i++) {
+        const pe_constraint c = K.cons[g.con_off + g.con_cnt + i];
+        if (T.attr[c.col][n] != c.value) return false;
+    }
+    return true;
+}
+
 // Pipeline.Process (pipeline.go:56-68) for one node: 0 = every enabled filter
 // passed, else 1 + index of the first failing filter.
 __device__ __noinline__ uint32_t eval_ff(const DevTable &T, const TickDev &K, const pe_group &g, uint32_t n,

@@ -1,5 +1,5 @@
-// minijson.h -- small JSON value/parser/printer used by the host shim.s test
-// driver protocol (scheduler_host.cpp).  Not part of the hot path.
+// minijson.h -- small JSON value/parser/printer for the test-driver protocol of the host shim
+// (scheduler_host.cpp) and of the object-level oracle (oracle/sched_oracle.cpp).  Not part of the hot path.
 #pragma once
 #include <cstdint>
 #include <cstdio>

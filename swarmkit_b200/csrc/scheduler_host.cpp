@@ -21,8 +21,9 @@
 //   Encoder (rows, group descriptors) <- the SetTask methods      filter.go:35,60,118,224,259,328,369
 //
 // Not supported by the engine yet (reported as an error, never silently
-// scheduled on the CPU): Placement.Preferences (scheduler.go:772-825) and CSI
-// cluster volumes (VolumesFilter) -- SURVEY 8(f) "next".
+// scheduled on the CPU): CSI cluster volumes (VolumesFilter) -- SURVEY 8(f) "next".
+// Placement.Preferences (scheduler.go:772-825): the branch walk is host code here as in the
+// reference; the engine supplies the tree's leaves and fills one leaf per group.
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -400,6 +401,10 @@ struct Scheduler {
     // ---- dictionaries (exact interning)
     std::unordered_map<std::string, uint32_t> val_ids{{"", 0}}, exact_ids{{"", 0}}, svc_ids, kind_ids, label_cols, plugin_slots;
     std::map<std::pair<int, uint32_t>, uint32_t> port_slots;
+    // placement preferences (nodeset.go:59-101): one attribute column per spread label, holding EXACT value ids (a branch
+    // is a label value as written, not case-folded); pref_strings[id] gives the value back for the canonical branch order
+    std::unordered_map<std::string, uint32_t> pref_cols, pref_ids{{"", 0}};
+    std::vector<std::string> pref_strings{""};
     uint32_t next_label_col = PE_ATTR_FIRST_LABEL;
     bool layout_dirty = true;            // membership / dictionary change: re-upload every row
     std::set<std::string> dirty_nodes;   // rows whose NodeInfo changed on the host side
@@ -422,6 +427,20 @@ struct Scheduler {
         label_cols[prefixed] = next_label_col;
         layout_dirty = true;             // a new column has to be filled for every node
         return next_label_col++;
+    }
+    uint32_t pref_col(const std::string &prefixed) {    // "n:<key>" node label, "e:<key>" engine label (exact values)
+        auto it = pref_cols.find(prefixed);
+        if (it != pref_cols.end()) return it->second;
+        pref_cols[prefixed] = next_label_col;
+        layout_dirty = true;
+        return next_label_col++;
+    }
+    uint32_t pref_id(const std::string &v) {
+        auto it = pref_ids.find(v);
+        if (it != pref_ids.end()) return it->second;
+        uint32_t id = (uint32_t)pref_strings.size();
+        pref_ids[v] = id; pref_strings.push_back(v);
+        return id;
     }
     uint32_t plugin_slot(const std::string &type, const std::string &name) {
         std::string k = type + "\x1f" + name;
@@ -483,6 +502,15 @@ struct Scheduler {
             if (!m) continue;
             auto f = m->find(key);
             if (f != m->end()) attr(lc.second, f->second);
+        }
+        for (auto &pc : pref_cols) {                                                               // nodeset.go:69-82
+            const std::string key = pc.first.substr(2);
+            const std::map<std::string, std::string> *m = nullptr;
+            if (pc.first[0] == 'n') { if (n.has_labels) m = &n.labels; }
+            else if (n.has_desc && n.has_engine && n.has_elabels) m = &n.elabels;
+            if (!m) continue;
+            auto f = m->find(key);
+            if (f != m->end()) { uint32_t v = pref_id(f->second); if (v) b.attrs.push_back({pc.second, v}); }
         }
         r.attr_cnt = (uint32_t)b.attrs.size() - r.attr_off;
         r.gen_off = (uint32_t)b.gens.size();
@@ -689,8 +717,9 @@ struct Scheduler {
     }
     bool encode_group(const std::vector<TaskP> &tasks, TickBuf &b, bool for_fit = false) {
         const Task &t = *tasks[0];
-        // (taskFitNode checks one named node: placement preferences play no part there, scheduler.go:646-690)
-        if (!for_fit && t.has_placement && !t.preferences.empty()) { fatal = "placement preferences are not supported by the placement engine yet (task " + t.id + ")"; return false; }
+        // (placement preferences: the caller cuts the group into leaf visits, see schedulePreferenceGroup; taskFitNode
+        // checks one named node and preferences play no part there, scheduler.go:646-690)
+        (void)for_fit;
         for (auto &m : t.mounts) if (m.type == MountCluster) { fatal = "CSI cluster volumes are not supported by the placement engine (task " + t.id + ")"; return false; }
         pe_group g{};
         g.log_plugin = PE_NONE;
@@ -787,20 +816,69 @@ struct Scheduler {
     // Status.Err, exactly like tasks without a suitable node (scheduler.go:958-962), and every other group is scheduled.
     // If the engine itself fails, every task goes back to the queue and the device mirror is rebuilt from the host's
     // NodeInfo on the next call (the device rows may have moved part-way).
+    // The spread levels of a group's placement preferences (nodeset.go:59-82): attribute columns of exact label values.
+    // Descriptors that are neither node.labels.* nor engine.labels.* contribute no level.
+    std::vector<uint32_t> preference_levels(const Task &t) {
+        std::vector<uint32_t> cols;
+        if (!t.has_placement) return cols;
+        for (auto &d : t.preferences) {
+            if (d.size() > 12 && fold(d.substr(0, 12)) == "node.labels.") cols.push_back(pref_col("n:" + d.substr(12)));
+            else if (d.size() > 14 && fold(d.substr(0, 14)) == "engine.labels.") cols.push_back(pref_col("e:" + d.substr(14)));
+        }
+        return cols;
+    }
+
+    // what the engine decided for one encoded group: decisions, host mirror; tasks without a node come back in `left`
+    void apply_group(const std::vector<TaskP> &grp, const uint32_t *out_node, std::vector<TaskP> &left, std::map<std::string, Decision> &decisions) {
+        for (size_t i = 0; i < grp.size(); i++) {
+            const TaskP &t = grp[i];
+            uint32_t idx = out_node[i];
+            if (idx == PE_NONE || idx >= idx_to_id.size()) { left.push_back(t); continue; }
+            TaskP nt(new Task(*t));                                                   // scheduler.go:871-880
+            nt->node_id = idx_to_id[idx];
+            nt->state = TaskStateAssigned; nt->err.clear(); nt->message = "scheduler assigned task to node";
+            allTasks[t->id] = nt;
+            nodeSet[nt->node_id].addTask(nt);   // host mirror: counters, named generic members (the device row already moved)
+            decisions[t->id] = {t, nt};
+        }
+    }
+
+    // scheduleTaskGroup for every group of the tick (scheduler.go:464-469,694-748): maximal runs of groups without
+    // placement preferences go to the engine in ONE call; a group with preferences is walked leaf by leaf in between.
+    // A group the engine cannot take (see encode_group) does not stop the tick: its tasks stay pending with the reason in
+    // Status.Err, exactly like tasks without a suitable node (scheduler.go:958-962), and every other group is scheduled.
+    // If the engine itself fails, every task not yet decided goes back to the queue and the device mirror is rebuilt from
+    // the host's NodeInfo on the next call (the device rows may have moved part-way).
     bool scheduleTaskGroups(std::vector<std::vector<TaskP>> &all_groups, std::map<std::string, Decision> &decisions) {
+        unsupported.clear();
+        std::vector<std::vector<TaskP>> run;
+        for (size_t gi = 0; gi < all_groups.size(); gi++) {
+            auto &g = all_groups[gi];
+            const bool pref = !g.empty() && !preference_levels(*g[0]).empty();
+            if (!pref) { run.push_back(g); continue; }
+            bool ok = scheduleRun(run, decisions);
+            run.clear();
+            if (ok) ok = schedulePreferenceGroup(g, decisions);
+            if (!ok) {
+                for (size_t r = gi + 1; r < all_groups.size(); r++) for (auto &t : all_groups[r]) enqueue(t);
+                return false;
+            }
+        }
+        return scheduleRun(run, decisions);
+    }
+
+    bool scheduleRun(std::vector<std::vector<TaskP>> &all_groups, std::map<std::string, Decision> &decisions) {
         if (all_groups.empty()) return true;
         TickBuf b;
         std::vector<std::vector<TaskP>> groups;
-        std::string first_unsupported;
         for (auto &g : all_groups) {
             TickBuf probe = b;                      // (an encoder that gives up half-way must leave no side arrays behind)
             fatal.clear();
             if (encode_group(g, probe)) { b = std::move(probe); groups.push_back(g); continue; }
-            if (first_unsupported.empty()) first_unsupported = fatal;
+            if (unsupported.empty()) unsupported = fatal;
             noSuitableNode(g, "unsupported by the placement engine: " + fatal, decisions);
         }
         fatal.clear();
-        unsupported = first_unsupported;
         if (groups.empty()) return true;
         auto give_back = [&]() {
             for (auto &g : groups) for (auto &t : g) enqueue(t);
@@ -811,21 +889,117 @@ struct Scheduler {
         pe_tick tk = b.view();
         if (!check(pe_schedule(eng, &tk, out_node.data(), out_fail.data()), "pe_schedule")) { give_back(); return false; }
         for (size_t gi = 0; gi < groups.size(); gi++) {
-            auto &grp = groups[gi];
             std::vector<TaskP> left;
-            for (size_t i = 0; i < grp.size(); i++) {
-                const TaskP &t = grp[i];
-                uint32_t idx = out_node[b.groups[gi].task_off + i];
-                if (idx == PE_NONE || idx >= idx_to_id.size()) { left.push_back(t); continue; }
-                TaskP nt(new Task(*t));                                                   // scheduler.go:871-880
-                nt->node_id = idx_to_id[idx];
-                nt->state = TaskStateAssigned; nt->err.clear(); nt->message = "scheduler assigned task to node";
-                allTasks[t->id] = nt;
-                nodeSet[nt->node_id].addTask(nt);   // host mirror: counters, named generic members (the device row already moved)
-                decisions[t->id] = {t, nt};
-            }
+            apply_group(groups[gi], &out_node[b.groups[gi].task_off], left, decisions);
             if (!left.empty()) noSuitableNode(left, explain(&out_fail[gi * PE_NUM_FILTERS]), decisions);
         }
+        return true;
+    }
+
+    // ---- placement preferences: nodeSet.tree's branches (nodeset.go:59-101) + scheduleNTasksOnSubtree (scheduler.go:772-825).
+    // The engine supplies the leaves with their task sums (pe_pref_leaves) and places n tasks on one leaf per call (a group
+    // with leaf_cnt > 0: the leaf's k best feasible nodes and scheduleNTasksOnNodes over them); the walk between the
+    // branches -- integer bookkeeping on a handful of branches -- is this host code, as in the reference.
+    // Why one leaf visit = one engine group is exact: a visit assigns n' <= (tasks left) tasks and, before the fill
+    // wraps, advances at most one node per task, so only the n' best live nodes of the leaf matter; the reference's leaf
+    // heap holds the k best at tree-building time of which at least k - (tasks already placed there) >= n' are untouched and
+    // still rank ahead of every node outside it, and feasibility only shrinks inside a group: the two candidate lists agree.
+    struct PrefTree {
+        int tasks = 0;
+        std::map<std::string, std::unique_ptr<PrefTree>> next;   // canonical branch order: ascending label value, "" first
+        std::vector<pe_constraint> leaf;                          // the (column == value) path that names a leaf
+    };
+    struct PrefWalk {
+        std::vector<TaskP> pending;            // ascending task ID
+        std::vector<uint32_t> last_fail;       // failure counters of the last visit that came back short
+        bool have_fail = false, engine_failed = false;
+    };
+    int fillLeaf(int n, PrefTree &leaf, PrefWalk &w, std::map<std::string, Decision> &decisions) {
+        const size_t m = std::min<size_t>((size_t)std::max(n, 0), w.pending.size());
+        if (m == 0 || w.engine_failed) return 0;
+        std::vector<TaskP> sub(w.pending.begin(), w.pending.begin() + (long)m);
+        TickBuf b;
+        fatal.clear();
+        if (!encode_group(sub, b)) {                                   // unsupported reservation etc.: nothing is placed
+            if (unsupported.empty()) unsupported = fatal;
+            fatal.clear();
+            return 0;
+        }
+        pe_group &g = b.groups.back();
+        if (g.con_cnt == 0) g.con_off = (uint32_t)b.cons.size();       // the leaf terms follow the group's constraints
+        b.cons.insert(b.cons.end(), leaf.leaf.begin(), leaf.leaf.end());
+        g.leaf_cnt = (uint32_t)leaf.leaf.size();
+        if (!flush_rows()) { w.engine_failed = true; return 0; }
+        std::vector<uint32_t> out_node(m, PE_NONE), out_fail(PE_NUM_FILTERS, 0);
+        pe_tick tk = b.view();
+        if (!check(pe_schedule(eng, &tk, out_node.data(), out_fail.data()), "pe_schedule")) { w.engine_failed = true; return 0; }
+        std::vector<TaskP> left;
+        apply_group(sub, out_node.data(), left, decisions);
+        const size_t placed = m - left.size();
+        // (scheduleNTasksOnNodes hands out the group's tasks in order: the ones it placed are a prefix)
+        std::vector<TaskP> rest(left);
+        rest.insert(rest.end(), w.pending.begin() + (long)m, w.pending.end());
+        w.pending.swap(rest);
+        if (placed < m) { w.last_fail = out_fail; w.have_fail = true; }
+        return (int)placed;
+    }
+    int scheduleNTasksOnSubtree(int n, PrefTree &tree, PrefWalk &w, std::map<std::string, Decision> &decisions) {   // scheduler.go:772-825
+        if (tree.next.empty()) return fillLeaf(n, tree, w, decisions);
+        int tasksScheduled = 0, tasksInUsableBranches = tree.tasks;
+        std::set<PrefTree *> noRoom;
+        bool converging = true;
+        while (tasksScheduled != n && noRoom.size() != tree.next.size() && converging) {
+            const int usable = (int)(tree.next.size() - noRoom.size());
+            const int desiredTasksPerBranch = (tasksInUsableBranches + n - tasksScheduled) / usable;
+            int remainder = (tasksInUsableBranches + n - tasksScheduled) % usable;
+            converging = false;
+            for (auto &kv : tree.next) {
+                PrefTree *subtree = kv.second.get();
+                if (noRoom.count(subtree)) continue;
+                const int subtreeTasks = subtree->tasks;
+                if (subtreeTasks < desiredTasksPerBranch || (subtreeTasks == desiredTasksPerBranch && remainder > 0)) {
+                    converging = true;
+                    int tasksToAssign = desiredTasksPerBranch - subtreeTasks;
+                    if (remainder > 0) tasksToAssign++;
+                    const int res = scheduleNTasksOnSubtree(tasksToAssign, *subtree, w, decisions);
+                    if (res < tasksToAssign) { noRoom.insert(subtree); tasksInUsableBranches -= subtreeTasks; }
+                    else if (remainder > 0) remainder--;
+                    tasksScheduled += res;
+                }
+            }
+        }
+        return tasksScheduled;
+    }
+    bool schedulePreferenceGroup(std::vector<TaskP> &grp, std::map<std::string, Decision> &decisions) {
+        const Task &t = *grp[0];
+        const std::vector<uint32_t> cols = preference_levels(t);
+        auto give_back = [&](const std::vector<TaskP> &ts) { for (auto &x : ts) enqueue(x); layout_dirty = true; };
+        if (!flush_rows()) { give_back(grp); return false; }            // (a new preference column is filled for every node)
+        // ---- the leaves and their task sums, from the device mirror
+        const uint32_t cap = (uint32_t)nodeSet.size() + 1u, L = (uint32_t)cols.size();
+        std::vector<uint32_t> vals((size_t)cap * L), tasks(cap);
+        uint32_t n_leaves = 0;
+        if (!check(pe_pref_leaves(eng, svc_id(t.service), cols.data(), L, cap, vals.data(), tasks.data(), &n_leaves), "pe_pref_leaves")) { give_back(grp); return false; }
+        PrefTree root;
+        for (uint32_t i = 0; i < n_leaves; i++) {                        // nodeset.go:59-101, one leaf's worth of nodes at a time
+            PrefTree *tr = &root;
+            std::vector<pe_constraint> path;
+            for (uint32_t l = 0; l < L; l++) {
+                tr->tasks += (int)tasks[i];
+                const uint32_t v = vals[(size_t)i * L + l];
+                std::unique_ptr<PrefTree> &nx = tr->next[v < pref_strings.size() ? pref_strings[v] : std::string()];
+                if (!nx) nx.reset(new PrefTree());
+                tr = nx.get();
+                path.push_back({cols[l], v, 0});
+            }
+            tr->tasks += (int)tasks[i];
+            tr->leaf = path;
+        }
+        PrefWalk w;
+        w.pending = grp;
+        scheduleNTasksOnSubtree((int)grp.size(), root, w, decisions);
+        if (w.engine_failed) { give_back(w.pending); return false; }
+        if (!w.pending.empty()) noSuitableNode(w.pending, w.have_fail ? explain(w.last_fail.data()) : std::string(), decisions);
         return true;
     }
     void noSuitableNode(const std::vector<TaskP> &left, const std::string &explanation, std::map<std::string, Decision> &decisions) {   // scheduler.go:928-971

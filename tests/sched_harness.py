@@ -190,6 +190,22 @@ class Cluster:
         return {k: d["node_id"] for k, d in decisions.items() if d["state"] == "ASSIGNED"}
 
 
+def comparable(decisions: dict, cluster: "Cluster") -> dict:
+    """Decisions as compared between the product and the object-level oracle.  One thing is not pinned: the text in
+    parentheses of "no suitable node (...)" for the left-over tasks of a group WITH placement preferences.  In the
+    reference it is whatever the pipeline's counters hold after the last of many Process calls spread over the tree
+    building and every leaf visit -- it depends on Go's map iteration order over branches and nodes and no reference test
+    reads it.  The product reports the counters of the last leaf visit that came back short."""
+    out = {}
+    for tid, d in decisions.items():
+        t = cluster.tasks.get(tid, {})
+        pl = (t.get("spec") or {}).get("placement") or {}
+        if pl.get("preferences") and d["err"].startswith("no suitable node"):
+            d = dict(d, err="no suitable node")
+        out[tid] = d
+    return out
+
+
 def count_by_node(assign: dict, prefix: str = "") -> dict:
     out = {}
     for tid, nid in assign.items():
