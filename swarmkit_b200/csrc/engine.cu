@@ -835,7 +835,7 @@ struct pe_engine {
                 if (r != 0) { err = std::string("ncclAllReduce: ") + nc.GetErrorString(r); return PE_ERR_CUDA; }
             }
             DBG_SYNC("scan", b0, B);
-            k_merge<<<(B + 7) / 8, 256, 0, stream>>>(MP);
+            k_merge<<<std::min<uint32_t>(2u * B, (uint32_t)num_sms * 8u), 256, 0, stream>>>(MP);   // CTAs stride over (row, class) units
             ev_end(ev);
             DBG_SYNC("merge", b0, B);
             CU(cudaGetLastError());

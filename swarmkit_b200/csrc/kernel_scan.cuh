@@ -371,63 +371,66 @@ __global__ void __launch_bounds__(PE_SCAN_THREADS, 2) k_scan(const __grid_consta
     }
 }
 
-// One warp per row: the row record and the member lists from the chunks' parts (chunks are in node order, so
-// concatenating their lists keeps node order).
+// One CTA per (row, class): the class's member list from the chunks' parts (chunks are in node order, so
+// concatenating their lists keeps node order), all threads copying; the class-0 CTA also writes the row record.
+// (The first version gave a row to one warp: ~1000 warps copying up to 2 x 4096 members each, 128 us per batch.)
 __global__ void __launch_bounds__(256) k_merge(const MergeParams P) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t n_rows = *P.n_rows;
     if (P.touched != nullptr)
-        for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < P.touched_words; w += gridDim.x * blockDim.x) P.touched[w] = 0u;
-    if (row >= n_rows) return;
-    if (P.cursors != nullptr && lane < 2u) P.cursors[(size_t)row * 2u + lane] = 0u;
-    unsigned long long c0, c1;
-    merge_p1(P.p1, P.n_chunks, P.rows_cap, row, lane, c0, c1);
+        for (uint32_t w = blockIdx.x * blockDim.x + tid; w < P.touched_words; w += gridDim.x * blockDim.x) P.touched[w] = 0u;
+    for (uint32_t unit = blockIdx.x; unit < 2u * n_rows; unit += gridDim.x) {     // (the row count is on the device: the grid is fixed)
+    const uint32_t row = unit >> 1, cls = unit & 1u;
+    if (P.cursors != nullptr && tid == 0) P.cursors[(size_t)row * 2u + cls] = 0u;
     uint32_t tot[2] = {0, 0};
-    for (uint32_t cls = 0; cls < 2u; cls++) {
+    for (uint32_t g = 0; g < P.n_chunks; g++) {
+        tot[0] += P.Cc[((size_t)g * P.rows_cap + row) * 2u];
+        tot[1] += P.Cc[((size_t)g * P.rows_cap + row) * 2u + 1u];
+    }
+    uint32_t *dst = P.L + ((size_t)row * 2u + cls) * PE_LIST_CAP;
+    if (P.Lx != nullptr) {      // node sharding: the merged list of every rank's chunks (k_xpack + all-reduce)
+        const uint32_t take = min(tot[cls], P.x_cap);
+        const uint32_t *src = P.Lx + ((size_t)row * 2u + cls) * P.x_cap;
+        for (uint32_t j = tid; j < take; j += blockDim.x) dst[j] = src[j];
+    } else {
         uint32_t pos = 0;
-        uint32_t *dst = P.L + ((size_t)row * 2u + cls) * PE_LIST_CAP;
-        for (uint32_t g = 0; g < P.n_chunks; g++) {
+        for (uint32_t g = 0; g < P.n_chunks && pos < PE_LIST_CAP; g++) {
             const uint32_t n = P.Cc[((size_t)g * P.rows_cap + row) * 2u + cls];
-            tot[cls] += n;
-            if (P.Lx != nullptr) continue;
             const uint32_t take = min(min(n, (uint32_t)PE_LIST_CAP), (uint32_t)PE_LIST_CAP - pos);
             const uint32_t *src = P.Lc + (((size_t)g * P.rows_cap + row) * 2u + cls) * PE_LIST_CAP;
-            for (uint32_t j = lane; j < take; j += 32u) dst[pos + j] = src[j];
+            for (uint32_t j = tid; j < take; j += blockDim.x) dst[pos + j] = src[j];
             pos += take;
-        }
-        if (P.Lx != nullptr) {      // the merged list of every rank's chunks (k_xpack + all-reduce)
-            const uint32_t take = min(tot[cls], P.x_cap);
-            const uint32_t *src = P.Lx + ((size_t)row * 2u + cls) * P.x_cap;
-            for (uint32_t j = lane; j < take; j += 32u) dst[j] = src[j];
         }
     }
     if (P.Eall != nullptr) {
         // gathered bitmap segments -> canonical rows
-        for (uint32_t cls = 0; cls < 2u; cls++) {
-            uint32_t *dst = P.E + ((size_t)row * 2u + cls) * P.e_stride;
-            for (uint32_t r = 0; r < P.n_ranks; r++) {
-                const uint32_t *src = P.Eall + (((size_t)r * P.rows_cap + row) * 2u + cls) * P.seg_words;
-                for (uint32_t j = lane; j < P.seg_words && r * P.seg_words + j < P.e_stride; j += 32u) dst[r * P.seg_words + j] = src[j];
-            }
+        uint32_t *ed = P.E + ((size_t)row * 2u + cls) * P.e_stride;
+        for (uint32_t r = 0; r < P.n_ranks; r++) {
+            const uint32_t *src = P.Eall + (((size_t)r * P.rows_cap + row) * 2u + cls) * P.seg_words;
+            for (uint32_t j = tid; j < P.seg_words && r * P.seg_words + j < P.e_stride; j += blockDim.x) ed[r * P.seg_words + j] = src[j];
         }
     }
-    if (lane == 0) {
-        const pe_group G = P.K.groups[P.row_group[row]];
-        const uint32_t fm = G.filter_mask;
-        ScanResult r;
-        r.c0 = c0; r.c1 = c1;
-        r.n0 = c0 == PE_PREF_NONE ? 0u : tot[0];
-        r.n1 = (c0 == PE_PREF_NONE || c1 == PE_PREF_NONE) ? 0u : tot[1];
-        r.tie_start = G.tie_start;
-        r.flags = ((G.gen_cnt == 0 && G.port_cnt == 0) ? PE_SR_SIMPLE : 0u) | (G.n_tasks == 1 ? PE_SR_K1 : 0u) |
-                  ((G.n_tasks >= 1 && (P.K.task_flags[G.task_off] & PE_T_COUNTS)) ? PE_SR_COUNTS : 0u) |
-                  ((G.gen_cnt == 0 && G.port_cnt == 0 && !(fm & (1u << PE_F_HOSTPORT)) && G.fail_cnt == 0) ? PE_SR_INLINE : 0u) |
-                  ((fm & (1u << PE_F_RESOURCE)) ? PE_SR_RES : 0u) | ((fm & (1u << PE_F_MAXREPLICAS)) ? PE_SR_MAXREP : 0u);
-        r.cpu_res = G.cpu_res; r.mem_res = G.mem_res;
-        r.svccol = P.svc[G.svc_id];
-        r.max_replicas = G.max_replicas;
-        P.out[row] = r;
+    if (cls == 0u && tid < 32u) {
+        unsigned long long c0, c1;
+        merge_p1(P.p1, P.n_chunks, P.rows_cap, row, lane, c0, c1);
+        if (lane == 0) {
+            const pe_group G = P.K.groups[P.row_group[row]];
+            const uint32_t fm = G.filter_mask;
+            ScanResult r;
+            r.c0 = c0; r.c1 = c1;
+            r.n0 = c0 == PE_PREF_NONE ? 0u : tot[0];
+            r.n1 = (c0 == PE_PREF_NONE || c1 == PE_PREF_NONE) ? 0u : tot[1];
+            r.tie_start = G.tie_start;
+            r.flags = ((G.gen_cnt == 0 && G.port_cnt == 0) ? PE_SR_SIMPLE : 0u) | (G.n_tasks == 1 ? PE_SR_K1 : 0u) |
+                      ((G.n_tasks >= 1 && (P.K.task_flags[G.task_off] & PE_T_COUNTS)) ? PE_SR_COUNTS : 0u) |
+                      ((G.gen_cnt == 0 && G.port_cnt == 0 && !(fm & (1u << PE_F_HOSTPORT)) && G.fail_cnt == 0) ? PE_SR_INLINE : 0u) |
+                      ((fm & (1u << PE_F_RESOURCE)) ? PE_SR_RES : 0u) | ((fm & (1u << PE_F_MAXREPLICAS)) ? PE_SR_MAXREP : 0u);
+            r.cpu_res = G.cpu_res; r.mem_res = G.mem_res;
+            r.svccol = P.svc[G.svc_id];
+            r.max_replicas = G.max_replicas;
+            P.out[row] = r;
+        }
+    }
     }
 }
 

@@ -68,7 +68,7 @@ def random_nodes(rng: np.random.Generator, n: int, n_labels=3, n_svc=4, n_gen=3,
 
 
 def random_tick(rng: np.random.Generator, n_nodes: int, n_groups: int, n_labels=3, n_svc=4, n_gen=3, n_slots=40,
-                p_oneoff=0.6, kmax=40, feature_p=0.35, rotate=True):
+                p_oneoff=0.6, kmax=40, feature_p=0.35, rotate=True, p_leaf=0.0):
     g = np.zeros(n_groups, abi.group_dt)
     g["log_plugin"] = abi.PE_NONE
     gens, cons, ips, plats, ports, plugs, fails = [], [], [], [], [], [], []
@@ -115,6 +115,13 @@ def random_tick(rng: np.random.Generator, n_nodes: int, n_groups: int, n_labels=
                     ips.append((net, (0xFFFFFFFF,) * 4, rng.integers(0, 2), 0, 0))
             if rng.random() < 0.05:
                 g[i]["flags"] |= abi.PE_G_CONSTRAINT_NEVER
+        if p_leaf and rng.random() < p_leaf:  # one leaf visit of a placement-preference tree: the terms follow the constraints
+            if g[i]["con_cnt"] == 0:
+                g[i]["con_off"] = len(cons)
+            nl = int(rng.integers(1, 3))
+            g[i]["leaf_cnt"] = nl
+            for _ in range(nl):
+                cons.append((rng.integers(abi.PE_ATTR_FIRST_LABEL, n_cols), rng.integers(0, 4), 0))
         if rng.random() < feature_p:  # platforms
             fm |= 1 << abi.PE_F_PLATFORM
             npf = int(rng.integers(1, 6))

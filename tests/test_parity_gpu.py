@@ -111,6 +111,44 @@ def test_random_oneoff_heavy(seed):
     assert gpu.stats()["scan_launches"] > 0
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_leaf_visits(seed):
+    """Groups that are one leaf visit of a placement-preference tree (pe_group.leaf_cnt): the node set is cut down to
+    the leaf (nodeset.go:59-101) on every path a group can take (one task: one-CTA path; k > 1: k_groups)."""
+    rng = np.random.default_rng(3000 + seed)
+    n = int(rng.integers(60, 3000))
+    nodes = R.random_nodes(rng, n, tight=bool(seed % 2))
+    ticks = [R.random_tick(rng, n, int(rng.integers(20, 150)), p_leaf=0.4, p_oneoff=0.4) for _ in range(3)]
+    assert any((t.groups["leaf_cnt"] > 0).any() for t in ticks)
+    gpu, cpu, res = run_both(nodes, None, n, flags=(abi.PE_CFG_ORDERED_ONLY if seed == 5 else 0), ticks=ticks)
+    for i, (t, a, b) in enumerate(res):
+        R.compare_results(t, a, b, f"leaf visits seed {seed} tick {i}")
+    R.compare_state(gpu, cpu, n, 4, 3, 40, f"leaf visits seed {seed}")
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_pref_leaves(seed):
+    """nodeSet.tree's leaves and their task sums (pe_pref_leaves) against the oracle, before and after a tick."""
+    rng = np.random.default_rng(3100 + seed)
+    n = int(rng.integers(50, 5000))
+    nodes = R.random_nodes(rng, n)
+    tick = R.random_tick(rng, n, 60)
+    gpu, cpu, res = run_both(nodes, tick, n)
+
+    def leaves(e, svc, cols):
+        vals, tasks = e.pref_leaves(svc, cols, cap=n + 1)
+        return sorted((tuple(v.tolist()), int(t)) for v, t in zip(vals, tasks))
+
+    first = abi.PE_ATTR_FIRST_LABEL
+    for svc in range(4):
+        for cols in ([first], [first + 1, first], [first, first + 1, first + 2], [abi.PE_ATTR_ROLE, first + 2], []):
+            a, b = leaves(gpu, svc, cols), leaves(cpu, svc, cols)
+            assert a == b, f"seed {seed} service {svc} levels {cols}"
+            assert len(a) <= 4 ** max(len(cols), 1)
+    with pytest.raises(abi.EngineError):
+        gpu.pref_leaves(0, [first, first + 1], cap=2)       # more leaves than the caller's buffers hold
+
+
 def test_large_group_global_path():
     # k > 2048 candidates: the sequencer's global-memory sort / fill path
     w = W.cfg1(n_nodes=5000, n_tasks=12000)
