@@ -139,7 +139,8 @@ def golden_prefix(args, n_tasks: int, n_nodes: int):
     """Committed full-size golden placements (tests/golden/big_*.npz, CPU oracle) for this workload, if one covers it.
     The tick is sequential, so the vector of the 1M-task tick pins every shorter tick over the same nodes."""
     table = {("cfg3-oneoff", 100_000): "big_cfg3_oneoff_1m_100k", ("cfg2-oneoff", 10_000): "big_cfg2_oneoff_100k_10k",
-             ("cfg3-grouped", 100_000): "big_cfg3_grouped_1m_100k", ("cfg2-grouped", 10_000): "big_cfg2_grouped_100k_10k"}
+             ("cfg3-grouped", 100_000): "big_cfg3_grouped_1m_100k", ("cfg2-grouped", 10_000): "big_cfg2_grouped_100k_10k",
+             ("cfg5-grouped", 100_000): "big_cfg5_storm_500k_100k"}
     name = table.get((args.workload, n_nodes))
     if name is None:
         return None, None

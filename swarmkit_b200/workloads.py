@@ -316,9 +316,64 @@ def cfg4(mode: str = "oneoff", n_nodes: int = 1_000_000, n_tasks: int = 1_000_00
     return Workload(f"cfg4-{mode}", nodes, tick, dict(w.meta))
 
 
+# --------------------------------------------------------------------------- cfg5
+def cfg5(mode: str = "grouped", n_nodes: int = 100_000, n_tasks: int = 500_000, n_services: int = 5000,
+         tasks_per_node: int = 50, drain_fraction: float = 0.1, seed: int = 0x5EED0005) -> Workload:
+    """Streaming reschedule storm (BASELINE.json configs[4]): a steady state of
+    n_nodes x tasks_per_node running tasks across n_services services with cpu/memory reservations; a tenth of the
+    nodes is drained and their tasks re-enter as PENDING in ONE tick.  The reference flow is
+    replicated.handleNodeChange -> restartTasksByNodeID (manager/orchestrator/replicated/tasks.go:86-117) ->
+    restart.Supervisor.Restart -> orchestrator.NewTask: replacements keep ServiceID + SpecVersion, so the tick is
+    GROUPED (one group per service that lost tasks); the drained nodes fail ReadyFilter; the old tasks were flipped to
+    DesiredState SHUTDOWN, so they left the spread counters (nodeinfo.go:110-122) but still hold their resources.
+    n_tasks is the expected number of re-entering tasks = drain_fraction x n_nodes x tasks_per_node (it fixes
+    tasks_per_node when given); mode is accepted for symmetry (the storm is always grouped)."""
+    rng = SplitMix64(seed)
+    if n_tasks and drain_fraction > 0:
+        tasks_per_node = max(1, int(round(n_tasks / (drain_fraction * n_nodes))))
+    rows = _rows(n_nodes)
+    # capacity: every node could hold about twice its steady-state share, so the survivors absorb the storm
+    s_cpu = (1 + rng.below(n_services, 10)).astype(np.int64) * 100_000_000          # 0.1 .. 1.0 CPU
+    s_mem = (1 + rng.below(n_services, 16)).astype(np.int64) * 64 * MIB             # 64 MiB .. 1 GiB
+    # steady state: every node runs tasks_per_node tasks of distinct random services
+    svc_of = rng.below(n_nodes * tasks_per_node, n_services).reshape(n_nodes, tasks_per_node).astype(np.int64)
+    svc_of.sort(axis=1)
+    used_cpu, used_mem = s_cpu[svc_of].sum(1), s_mem[svc_of].sum(1)
+    rows["cpu_avail"] = used_cpu + (1 + rng.below(n_nodes, 4)).astype(np.int64) * int(0.55 * tasks_per_node * 100_000_000)
+    rows["mem_avail"] = used_mem + (1 + rng.below(n_nodes, 4)).astype(np.int64) * int(8.5 * tasks_per_node * 64 * MIB)
+    drained = rng.uniform(n_nodes) < drain_fraction
+    live = ~drained
+    rows["flags"] = np.where(drained, abi.PE_NODE_VALID, abi.PE_NODE_VALID | abi.PE_NODE_READY)
+    rows["cpu_avail"] -= used_cpu      # running tasks (and, on the drained nodes, the ones still shutting down) hold their share
+    rows["mem_avail"] -= used_mem
+    rows["total_tasks"] = np.where(live, tasks_per_node, 0)
+    # per-node service counters of the live nodes (duplicates of a service on one node add up)
+    li = np.flatnonzero(live)
+    keys = (li[:, None] * np.int64(n_services) + svc_of[li]).reshape(-1)
+    uniq, cnt = np.unique(keys, return_counts=True)
+    svcs = np.zeros(uniq.size, abi.kv32_dt)
+    svcs["key"], svcs["value"] = (uniq % n_services).astype(np.uint32), cnt.astype(np.uint32)
+    node_of = uniq // n_services
+    per_node = np.bincount(node_of, minlength=n_nodes)
+    rows["svc_cnt"] = per_node
+    rows["svc_off"] = np.concatenate(([0], np.cumsum(per_node)[:-1]))
+    # the storm: the drained nodes' tasks, one group per service
+    lost = np.bincount(svc_of[drained].reshape(-1), minlength=n_services)
+    sv = np.flatnonzero(lost)
+    g = _groups(sv.size)
+    g["svc_id"] = sv
+    g["n_tasks"] = lost[sv]
+    g["task_off"] = np.concatenate(([0], np.cumsum(lost[sv])[:-1]))
+    g["filter_mask"] = (1 << abi.PE_F_READY) | (1 << abi.PE_F_RESOURCE)
+    g["cpu_res"], g["mem_res"] = s_cpu[sv], s_mem[sv]
+    flags = np.full(int(lost.sum()), abi.PE_T_COUNTS, np.uint8)
+    return Workload("cfg5-grouped", NodeTable(rows, svcs=svcs), Tick(g, flags),
+                    {"mode": "grouped", "services": n_services, "drained_nodes": int(drained.sum()), "running_tasks": int(live.sum()) * tasks_per_node})
+
+
 def by_name(name: str, **kw) -> Workload:
     base, _, mode = name.partition("-")
-    fn = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4}[base]
+    fn = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[base]
     if base == "cfg1":
         return fn(**kw)
-    return fn(mode or "oneoff", **kw)
+    return fn(mode or ("grouped" if base == "cfg5" else "oneoff"), **kw)

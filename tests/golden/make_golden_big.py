@@ -32,6 +32,7 @@ CASES = {
     "big_cfg2_grouped_100k_10k": lambda: W.cfg2("grouped", n_nodes=10_000, n_tasks=100_000),
     "big_cfg3_grouped_1m_100k": lambda: W.cfg3("grouped", n_nodes=100_000, n_tasks=1_000_000),
     "big_cfg4_oneoff_60k_200k": lambda: W.cfg4("oneoff", n_nodes=200_000, n_tasks=60_000),
+    "big_cfg5_storm_500k_100k": lambda: W.cfg5(n_nodes=100_000, n_tasks=500_000, n_services=5000),
 }
 
 
