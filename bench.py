@@ -357,7 +357,7 @@ def main():
                       "tails": st["place_tails"], "chunks": st["place_chunks"],
                       "cta0_cycles": {"stage": st["place_cyc"][0], "resolve": st["place_cyc"][1], "commit": st["place_cyc"][2]},
                       "resolve": {"passes": st["seq_prof"][0], "rounds": st["seq_prof"][1], "short_chunks": st["seq_prof"][2],
-                                  "thread0_cycles": {"masks": st["seq_prof"][3], "attempts": st["seq_prof"][4], "recheck": st["seq_prof"][5], "finalize": st["seq_prof"][6]}, "task31_63_95_127_attempts_cycles": st["seq_prof"][8:16], "task127_mask_reloads": st["seq_prof"][2]}},
+                                  "thread0_cycles": {"filter": st["seq_prof"][3], "rounds": st["seq_prof"][4], "finalize": st["seq_prof"][5], "barrier": st["seq_prof"][6]}}},
             "paths": {"fast": st["fast_path"], "medium": st["medium_path"], "slow": st["slow_path"]},
             "sequencer_cycles": {"fast": st["seq_cycles_fast"], "medium": st["seq_cycles_medium"], "generic": st["seq_cycles_generic"],
                                  "fast_exits": st["seq_stops"], "ordered_warp_wait": st["seq_cons_wait"],

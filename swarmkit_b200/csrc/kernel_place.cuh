@@ -21,13 +21,16 @@
 //           Task i of a chunk gets i + 1 candidates: the i tasks before it take
 //           one node each, so the list cannot run out.  Written straight into
 //           CTA 0's shared memory (DSMEM).
-//   resolve (ordered, ONE warp of CTA 0): the chunk's tasks one after the other,
-//           each taking its first candidate that no earlier task holds -- the 32
-//           lanes test 32 candidates at once against the batch's touched bitmap in
-//           shared memory, the loads of four tasks in flight together.  A task that
-//           skipped a candidate ranked strictly better than its choice (the node was
-//           taken inside the chunk: its rank moved) recomputes those ranks from the
-//           chunk's log -- exactly.
+//   resolve (ordered, warp 0 of CTA 0, lanes = tasks, 32 tasks per group, the
+//           chunk's groups one after the other): every lane proposes its first
+//           candidate that no final task took; lanes that propose the same node find
+//           each other with match.any and all but the lowest move on.  Lanes only
+//           move forward and a node given up by one lane is held by a lower one, so
+//           the fixed point is the sequential result.  A lane that skipped a
+//           candidate ranked strictly better than its choice (the node was taken
+//           inside the chunk: its rank moved) recomputes those ranks from the
+//           chunk's log -- exactly.  (Which candidates are still free is worked
+//           out by all sixteen warps of CTA 0 before each group's rounds.)
 //   commit  (parallel, CTA 0): NodeInfo.addTask for the chunk's placements as
 //           reductions on the global columns, the batch's touched bitmap.
 //
@@ -104,7 +107,8 @@ struct PlShared {
     uint16_t log_task[PE_PL_CHUNK];            // task (chunk-relative = slot index)
     uint8_t log_tail[PE_PL_CHUNK];             // 1: the choice came from rank group >= 1
     uint32_t n_log, stop, cut, done;            // done: tasks of the chunk the resolve phase settled (the next chunk starts after them)
-    uint32_t n_pub, res_done;                   // resolve -> commit hand-over: log entries published so far; the resolve warp is done
+    uint32_t ctl_fa, ctl_leave, ctl_gdone;      // resolve: what warp 0 decided at the end of a pass, for the other warps
+    unsigned long long avail[PE_PL_CHUNK];      // resolve: per task, which of its (up to 64) candidates no final task holds
     uint32_t wd;                                // watchdog: a loop of this chunk ran away (bit per loop); the chunk is handed to the ordered sequencer untouched
     uint32_t scratch[PE_PL_WARPS][3][PE_PL_SCR];   // per warp: tail gather buffers, the candidate list under construction
 };
@@ -360,140 +364,200 @@ __device__ __forceinline__ unsigned long long pl_key_of(const PlSlot &s, uint32_
     return rank == 0u ? s.c0 : rank == 1u ? s.kv1 : rank == 2u ? s.kv2 : s.kv3;
 }
 
-// ---- resolve: warp 0 of CTA 0, the chunk's tasks ONE AFTER THE OTHER, lanes = candidates ---------------------------------
-// The reference's order, literally: task after task, each taking its first candidate that no earlier task holds.  What
-// makes it fast is that nothing is left to look up: a task's candidates sit in shared memory in preference order, so the
-// 32 lanes test 32 of them at once (one load of the candidate, one of its word of the touched bitmap, one ballot) and the
-// loads of four tasks are in flight together; a task's choice is kept from the following three in registers.
+// ---- resolve: CTA 0, 32 tasks (one group) at a time ------------------------------------------------------------------
+// Deferred acceptance with the tasks' order as every node's preference, by WARP 0 with lanes = tasks: a lane proposes its
+// first candidate that no FINAL task holds; lanes proposing the same node find each other with match.any and every lane
+// but the lowest moves on to its next candidate.  A lane only gives a node up to a lower lane, and lower GROUPS are final
+// before a group starts, so what the lanes hold when nobody moves any more is what the reference's one-task-at-a-time loop
+// produces.  A round is a few dozen warp-synchronous instructions and one shared-memory load.
+// Which candidates a final task holds is settled before the rounds by ALL SIXTEEN WARPS, two tasks each, lanes =
+// candidates (two coalesced loads of the candidates, their words of the bitmap, two ballots -> a 64-bit mask per task):
+// a lone warp pays ~8 cycles for every dependent instruction, so work that does not need the tasks' order is spread out.
 // Final tasks are known by: the batch's touched bitmap kept in CTA 0's shared memory (tk, BM = true) for candidates that
 // were untouched when the chunk began; the chunk's own set of joined nodes (hkey) for candidates flagged PE_PL_TOUCHED
 // (their bit was set before the chunk began) and for every candidate when the node table is too big for tk.
-// (Two earlier versions resolved the tasks in parallel -- lanes = tasks, deferred acceptance with the task order as the
-// nodes' preference: ~8 rounds of ~4200 cycles per chunk with block barriers, ~23 rounds of ~1100 cycles with match.any
-// in one warp.  The picks chase a frontier of low node indices, so about one round per four tasks is inherent; a lone
-// warp pays ~8 cycles per dependent instruction, so the round count, not the work, set the time.)
-struct PlProf { unsigned long long slow, rewin, retries; };
-
-#define PE_PL_UNROLL 4
+// Measured alternatives, all exact (SM cycles of the phase per 128 tasks, cfg3 one-off, B200):
+//   35k  thread = task for the whole chunk, proposals by atomicMin on a claim table in shared memory, a block barrier per
+//        round, per-thread candidate windows re-read inside the rounds (the first version)
+//   36k  the same with the masks below and no re-reads: ~8 rounds per chunk but ~3400 cycles per round -- the tasks at the
+//        frontier propose the same few nodes, and their atomics on one shared-memory word are served one after the other
+//   25k  one warp, a group at a time, per-lane candidate windows re-read inside the rounds
+//   51k  the same with the masks computed by that one warp
+//   87k  the tasks strictly one after the other, lanes = candidates
+//   23.5k this version (5.5 rounds of ~600 cycles per group; one ballot per bit of the node index instead of match.any: 28k)
+struct PlProf { unsigned long long passes, rounds, retries; long long cyc_filter, cyc_rounds, cyc_final; };   // (cycles: thread 0's view)
 
 template <bool BM>
-__device__ __forceinline__ void pl_resolve(const PlaceParams &P, PlShared &S, uint32_t *tk, uint32_t c0_task, uint32_t nc, uint32_t lane,
+__device__ __forceinline__ void pl_resolve(const PlaceParams &P, PlShared &S, uint32_t *tk, uint32_t c0_task, uint32_t nc, uint32_t tid,
                                            uint32_t &n_amb, PlProf &prof) {
-    uint32_t n_log = 0;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    uint32_t n_log = 0, cut = PE_NONE, done = nc;      // (warp 0's)
     bool leave = false;
-    uint32_t cut = PE_NONE, done = nc;
-    for (uint32_t t0 = 0; t0 < nc && !leave; t0 += PE_PL_UNROLL) {
-        uint32_t c[PE_PL_UNROLL], w[PE_PL_UNROLL], ncand[PE_PL_UNROLL], pick[PE_PL_UNROLL];
-#pragma unroll
-        for (int u = 0; u < PE_PL_UNROLL; u++) {
-            const uint32_t i = min(t0 + (uint32_t)u, nc - 1u);
-            ncand[u] = t0 + (uint32_t)u < nc ? S.s_ncand[i] : 0u;
-            c[u] = lane < ncand[u] ? S.cand[(size_t)i * PE_PL_KS + lane] : 0u;
-            pick[u] = PE_NONE;
-        }
-        if (BM) {
-#pragma unroll
-            for (int u = 0; u < PE_PL_UNROLL; u++) w[u] = tk[PE_PL_NODE(c[u]) >> 5];
-        }
-#pragma unroll
-        for (int u = 0; u < PE_PL_UNROLL; u++) {
-            const uint32_t i = t0 + (uint32_t)u;
-            if (i >= nc || leave) break;
-            if (S.s_kind[i] != 0u) { cut = c0_task + i; done = i; leave = true; break; }      // not placeable here: the ordered sequencer takes over
-            const uint32_t *cd = S.cand + (size_t)i * PE_PL_KS;
-            const uint32_t rs1 = S.s_rs1[i], rs2 = S.s_rs2[i], rs3 = S.s_rs3[i];
-            auto rank_of = [&](uint32_t j) -> uint32_t { return (j >= rs1 ? 1u : 0u) + (j >= rs2 ? 1u : 0u) + (j >= rs3 ? 1u : 0u); };
-            // is candidate x (of this task) held by an earlier task?  `word`: its word of tk as loaded before this iteration
-            auto held = [&](uint32_t x, uint32_t word) -> bool {
-                const uint32_t n = PE_PL_NODE(x);
-                bool h;
-                if (BM && !(x & PE_PL_TOUCHED)) h = (word >> (n & 31u)) & 1u;
-                else h = pl_taken(S, n);
-#pragma unroll
-                for (int v = 0; v < PE_PL_UNROLL; v++) if (v < u) h = h || n == pick[v];   // (chosen after the loads of this iteration)
-                return h;
-            };
-            uint32_t jsel = PE_NONE, node = PE_NONE;
-            {
-                const bool free = lane < ncand[u] && !held(c[u], BM ? w[u] : 0u);
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, free);
-                if (bal) { jsel = (uint32_t)__ffs((int)bal) - 1u; node = __shfl_sync(0xFFFFFFFFu, PE_PL_NODE(c[u]), (int)jsel); }
+    for (uint32_t g0 = 0; g0 < nc && !leave; g0 += 32u) {
+        const uint32_t g_end = min(g0 + 32u, nc);
+        const uint32_t i = g0 + lane;
+        const bool present = i < nc;
+        const uint32_t is = present ? i : 0u;
+        const uint32_t *cd = S.cand + (size_t)is * PE_PL_KS;
+        const uint32_t n_cand = present ? S.s_ncand[is] : 0u;
+        const uint32_t rs1 = S.s_rs1[is], rs2 = S.s_rs2[is], rs3 = S.s_rs3[is];
+        const bool unusable = present && S.s_kind[is] != 0u;
+        auto rank_of = [&](uint32_t j) -> uint32_t { return (j >= rs1 ? 1u : 0u) + (j >= rs2 ? 1u : 0u) + (j >= rs3 ? 1u : 0u); };
+        uint32_t fa = g0;                           // tasks of the group below fa are final
+        for (uint32_t pass = 0;; pass++) {
+            // ---- every warp: which candidates of tasks fa + warp, fa + warp + 16 can still be proposed (lanes = candidates)
+            const long long tq0 = clock64();
+            for (uint32_t t = fa + warp; t < g_end; t += PE_PL_WARPS) {
+                const uint32_t nn = S.s_kind[t] ? 0u : S.s_ncand[t];
+                const uint32_t *row = S.cand + (size_t)t * PE_PL_KS;
+                const uint32_t x0 = lane < nn ? row[lane] : 0u, x1 = 32u + lane < nn ? row[32u + lane] : 0u;
+                bool f0 = lane < nn, f1 = 32u + lane < nn;
+                if (BM) {
+                    const uint32_t w0 = tk[PE_PL_NODE(x0) >> 5], w1 = tk[PE_PL_NODE(x1) >> 5];
+                    if (f0) f0 = (x0 & PE_PL_TOUCHED) ? !pl_taken(S, PE_PL_NODE(x0)) : !((w0 >> (x0 & 31u)) & 1u);
+                    if (f1) f1 = (x1 & PE_PL_TOUCHED) ? !pl_taken(S, PE_PL_NODE(x1)) : !((w1 >> (x1 & 31u)) & 1u);
+                } else {
+                    if (f0) f0 = !pl_taken(S, PE_PL_NODE(x0));
+                    if (f1) f1 = !pl_taken(S, PE_PL_NODE(x1));
+                }
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, f0), b1 = __ballot_sync(0xFFFFFFFFu, f1);
+                if (lane == 0) S.avail[t] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
             }
-            for (uint32_t jb = 32u; jsel == PE_NONE && jb < ncand[u]; jb += 32u) {      // beyond the first 32 candidates (rare)
-                prof.slow += lane == 0 ? 1u : 0u;
-                const uint32_t x = jb + lane < ncand[u] ? cd[jb + lane] : 0u;
-                const uint32_t word = BM ? tk[PE_PL_NODE(x) >> 5] : 0u;
-                const bool free = jb + lane < ncand[u] && !held(x, word);
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, free);
-                if (bal) { jsel = jb + (uint32_t)__ffs((int)bal) - 1u; node = __shfl_sync(0xFFFFFFFFu, PE_PL_NODE(x), __ffs((int)bal) - 1); }
-            }
-            if (jsel == PE_NONE) {
-                // out of candidates.  A list that was cut at PE_PL_K is staged again with what follows it (the chunk ends here,
-                // the next one starts with this task); otherwise the task is not placeable here
-                if (ncand[u] == (uint32_t)PE_PL_K && i + 1u > (uint32_t)PE_PL_K) { prof.retries += lane == 0 ? 1u : 0u; }
-                else cut = c0_task + i;
-                done = i; leave = true;
-                break;
-            }
-            uint32_t jfin = jsel;
-            if (jsel > 0u && rank_of(0u) < rank_of(jsel)) {
-                // ---- it skipped a candidate that ranked strictly better than its choice when the chunk began.  That node
-                // was taken inside the chunk, so its rank moved: recompute it from the chunk's log (one lane; rare).
-                n_amb += lane == 0 ? 1u : 0u;
-                uint32_t bn = node, bj = jsel;
-                if (lane == 0) {
-                    const PlSlot &sl = S.slot[i];
-                    unsigned long long bk = pl_key_of(sl, rank_of(jsel));
-                    for (uint32_t q = 0; q < jsel; q++) {
-                        const uint32_t n = PE_PL_NODE(cd[q]);
-                        const unsigned long long k0 = pl_key_of(sl, rank_of(q));
-                        uint32_t svc = (uint32_t)(k0 >> 32) & 0xFFFFFFu, tot = (uint32_t)k0;
-                        long long dcpu = 0, dmem = 0;
-                        for (uint32_t e = 0; e < n_log; e++) {          // every placement of this chunk on that node
-                            if (S.log_node[e] != n) continue;
-                            const PlSlot &o = S.slot[S.log_task[e]];
-                            tot++;
-                            if (o.svccol == sl.svccol) svc++;
-                            dcpu += o.cpu_res; dmem += o.mem_res;
+            __syncthreads();
+            const long long tq1 = clock64();
+            long long tq2 = tq1;
+            if (warp == 0) {
+                uint32_t bad = 32u;
+                if (pass > 34u) {       // (cannot happen: every pass makes at least one more task final)
+                    if (lane == 0) S.wd |= 2u;
+                    cut = c0_task + fa; done = fa; leave = true;
+                } else {
+                    // ---- the rounds
+                    const bool act = present && i >= fa && !unusable;
+                    unsigned long long avail = act ? S.avail[is] : 0ull;
+                    uint32_t j = 0, prop = 0;
+                    bool moving = act, dead = false, have = false;
+                    prof.passes += lane == 0 ? 1u : 0u;
+                    for (uint32_t r = 0; r < 64u * PE_PL_K; r++) {
+                        if (moving) {
+                            if (avail) { j = (uint32_t)__ffsll((long long)avail) - 1u; avail &= avail - 1ull; prop = PE_PL_NODE(cd[j]); have = true; }
+                            else dead = true;                  // out of candidates
+                            moving = false;
                         }
-                        bool ok = true;
-                        if (sl.flags & PE_SR_RES)      // (the columns still hold the chunk-start amounts: reductions come after this phase)
-                            ok = sl.cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) - dcpu &&
-                                 sl.mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n)) - dmem;
-                        if (sl.flags & PE_SR_MAXREP) ok = ok && (unsigned long long)svc < sl.max_replicas;
-                        const unsigned long long k = make_pref(0u, svc, tot);
-                        if (ok && (k < bk || (k == bk && n < bn))) { bk = k; bn = n; bj = q; }
+                        // lanes that propose the same node: all but the lowest move on (a higher lane that held it before finds out here)
+                        const uint32_t same = __match_any_sync(0xFFFFFFFFu, have ? prop : (0x80000000u | lane));
+                        const bool lose = have && (same & lane_lt) != 0u;
+                        prof.rounds += lane == 0 ? 1u : 0u;
+                        if (!__any_sync(0xFFFFFFFFu, lose)) break;
+                        if (lose) { have = false; moving = true; }
+                    }
+                    tq2 = clock64();
+                    const bool valid = act && have;
+                    const bool isbad = present && i >= fa && !valid;
+                    // a task that ran out of a list that was cut at PE_PL_K candidates is staged again with what follows it
+                    const bool isretry = isbad && !unusable && dead && n_cand == (uint32_t)PE_PL_K && i + 1u > (uint32_t)PE_PL_K;
+                    const bool isamb = valid && j > 0u && rank_of(0u) < rank_of(j);
+                    bad = __reduce_min_sync(0xFFFFFFFFu, (isbad || isamb) ? lane : 32u);     // lowest special lane of the group
+                    // tasks below the first special task are final: log them (task order), mark their nodes taken
+                    const bool fin = valid && lane < bad;
+                    const uint32_t finm = __ballot_sync(0xFFFFFFFFu, fin);
+                    if (fin) {
+                        const uint32_t e = n_log + __popc(finm & lane_lt);
+                        S.log_node[e] = prop; S.log_task[e] = (uint16_t)i; S.log_tail[e] = rank_of(j) != 0u ? 1 : 0;
+                        if (BM) atomicOr(&tk[prop >> 5], 1u << (prop & 31u));
+                        if (!BM || (cd[j] & PE_PL_TOUCHED)) pl_take(S, prop);      // the set answers for what the bitmap cannot
+                    }
+                    n_log += __popc(finm);
+                    __syncwarp();
+                    if (bad != 32u) {
+                        const uint32_t ib = g0 + bad;
+                        const bool b_retry = __shfl_sync(0xFFFFFFFFu, isretry ? 1u : 0u, (int)bad) != 0u;
+                        const bool b_bad = __shfl_sync(0xFFFFFFFFu, isbad ? 1u : 0u, (int)bad) != 0u;
+                        if (b_retry) { done = ib; leave = true; prof.retries += lane == 0 ? 1u : 0u; }     // the chunk ends here; the next one starts with this task
+                        else if (b_bad) { cut = c0_task + ib; done = ib; leave = true; }                      // not placeable here: the ordered sequencer takes over
+                        else {
+                            // ---- it skipped a candidate that ranked strictly better than its choice when the chunk began.  That
+                            // node was taken inside the chunk, so its rank moved: recompute it from the chunk's log (one lane; rare).
+                            if (lane == bad) {
+                                n_amb++;
+                                const PlSlot &sl = S.slot[i];
+                                unsigned long long bk = pl_key_of(sl, rank_of(j));
+                                uint32_t bn = prop, bj = j;
+                                for (uint32_t q = 0; q < j; q++) {
+                                    const uint32_t n = PE_PL_NODE(cd[q]);
+                                    const unsigned long long k0 = pl_key_of(sl, rank_of(q));
+                                    uint32_t svc = (uint32_t)(k0 >> 32) & 0xFFFFFFu, tot = (uint32_t)k0;
+                                    long long dcpu = 0, dmem = 0;
+                                    for (uint32_t e = 0; e < n_log; e++) {          // every placement of this chunk on that node
+                                        if (S.log_node[e] != n) continue;
+                                        const PlSlot &o = S.slot[S.log_task[e]];
+                                        tot++;
+                                        if (o.svccol == sl.svccol) svc++;
+                                        dcpu += o.cpu_res; dmem += o.mem_res;
+                                    }
+                                    bool ok = true;
+                                    if (sl.flags & PE_SR_RES)      // (the columns still hold the chunk-start amounts: reductions come after this phase)
+                                        ok = sl.cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) - dcpu &&
+                                             sl.mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n)) - dmem;
+                                    if (sl.flags & PE_SR_MAXREP) ok = ok && (unsigned long long)svc < sl.max_replicas;
+                                    const unsigned long long k = make_pref(0u, svc, tot);
+                                    if (ok && (k < bk || (k == bk && n < bn))) { bk = k; bn = n; bj = q; }
+                                }
+                                // (a winner other than its own proposal was taken before: the bitmap has it already)
+                                S.log_node[n_log] = bn; S.log_task[n_log] = (uint16_t)i; S.log_tail[n_log] = rank_of(bj) != 0u ? 1 : 0;
+                                if (BM) atomicOr(&tk[bn >> 5], 1u << (bn & 31u));
+                                if (!BM || (cd[bj] & PE_PL_TOUCHED)) pl_take(S, bn);
+                            }
+                            n_log++;
+                            __syncwarp();
+                        }
+                        fa = ib + 1u;                   // the tasks above the special one propose again, from their first candidate
                     }
                 }
-                node = __shfl_sync(0xFFFFFFFFu, bn, 0); jfin = __shfl_sync(0xFFFFFFFFu, bj, 0);
+                if (lane == 0) { S.ctl_fa = fa; S.ctl_leave = leave ? 1u : 0u; S.ctl_gdone = (bad == 32u || leave) ? 1u : 0u; }
             }
-            pick[u] = node;
-            if (lane == 0) {
-                S.log_node[n_log] = node; S.log_task[n_log] = (uint16_t)i; S.log_tail[n_log] = rank_of(jfin) != 0u ? 1 : 0;
-                const bool was_touched = (cd[jfin] & PE_PL_TOUCHED) != 0u;
-                if (BM) tk[node >> 5] |= 1u << (node & 31u);      // (one warp owns tk during the phase: plain read-modify-write)
-                if (!BM || was_touched) pl_take(S, node);          // the set answers for what the bitmap cannot
-            }
-            n_log++;
-            __syncwarp();
-        }
-        if (lane == 0) {        // the committer warps take the iteration's placements from here
-            __threadfence_block();
-            *reinterpret_cast<volatile uint32_t *>(&S.n_pub) = n_log;
+            __syncthreads();
+            if (tid == 0) { prof.cyc_filter += tq1 - tq0; prof.cyc_rounds += tq2 - tq1; prof.cyc_final += clock64() - tq2; }
+            fa = S.ctl_fa; leave = S.ctl_leave != 0u;
+            if (S.ctl_gdone) break;
         }
     }
-    __syncwarp();
-    if (lane == 0) {
-        S.n_log = n_log; S.cut = cut; S.done = done; S.stop = cut == PE_NONE ? 0u : 1u;
-        __threadfence_block();
-        *reinterpret_cast<volatile uint32_t *>(&S.res_done) = 1u;
+    if (tid == 0) { S.n_log = n_log; S.cut = cut; S.done = done; S.stop = cut == PE_NONE ? 0u : 1u; }
+}
+
+// commit of one log entry: NodeInfo.addTask (nodeinfo.go:125-153) from the slot alone
+__device__ __forceinline__ void pl_commit(const PlaceParams &P, PlShared &S, uint32_t c0, uint32_t e, uint32_t &n_fast, uint32_t &n_medium) {
+    const uint32_t n = S.log_node[e];
+    const PlSlot &sl = S.slot[S.log_task[e]];
+    P.K.out_node[sl.task_off] = n;
+    const long long cpu_res = sl.cpu_res, mem_res = sl.mem_res;
+    atomicAdd(&P.T.total[n], 1u);                   // (every task placed here counts: PE_SR_COUNTS)
+    if (atomicAdd(&sl.svccol[n], 1u) + 1u >= 0xFFFFFFu) atomicOr(&P.ctr->error, PE_DEV_ERR_SVC_OVERFLOW);
+    if (cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&P.T.cpu[n]), (unsigned long long)(-cpu_res));
+    if (mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&P.T.mem[n]), (unsigned long long)(-mem_res));
+    if (!(sl.flags & PE_SR_SIMPLE)) {
+        // generic resources / host ports: such a task is the FIRST on its node in this batch and tasks that
+        // join a touched node never reserve these, so one thread owns the cells
+        const pe_group *g = &P.K.groups[P.b0 + c0 + S.log_task[e]];
+        for (uint32_t w = 0; w < g->gen_cnt; w++) {
+            if (!gen_first_occurrence(P.K, *g, w)) continue;
+            int64_t *col = P.T.gen[P.K.gens[g->gen_off + w].kind];
+            col[n] = claim_cell(P.K, *g, w, col[n]);
+        }
+        for (uint32_t w = 0; w < g->port_cnt; w++) {
+            const uint32_t s = P.K.ports[g->port_off + w];
+            P.T.ports[s >> 5][n] |= 1u << (s & 31u);
+        }
     }
+    atomicOr(&P.touched[n >> 5], 1u << (n & 31u));
+    if (S.log_tail[e]) n_medium++; else n_fast++;
 }
 
 static inline size_t place_smem_bytes(uint32_t tk_words) { return sizeof(PlShared) + (size_t)tk_words * 4 + 16; }
 static_assert(sizeof(PlShared) + 18432u * 4 + 16 <= 232448, "k_place: shared memory budget");
+static_assert(PE_PL_K <= 64, "k_place: a task's candidates fit a 64-bit mask");
 static_assert(PE_PL_SCR >= 2 * PE_PL_K, "k_place: scratch buffers hold a candidate list");
-static_assert(PE_PL_CHUNK <= 288, "k_place: one committer thread per log entry");
 static_assert(4 * PE_PL_CHUNK <= PE_PL_HASH, "k_place: the set of taken nodes must stay sparse");
 #define PE_PL_TK_MAX_WORDS 18432u     // 72 KB of touched bitmap next to the slots and the node table: up to ~590 k nodes
 
@@ -523,7 +587,6 @@ __global__ void __launch_bounds__(PE_PL_THREADS, 1) k_place(const __grid_constan
     for (uint32_t c0 = 0; c0 < P.B;) {
         const uint32_t nc = min(chunk_cap, P.B - c0);
         const long long t0 = clock64();
-        if (crank == 0 && tid == 0) { S.n_pub = 0; S.res_done = 0; }           // (the cluster barrier below comes before anyone polls them)
         if (slot_i < nc) {
             if (pre_task != c0 + slot_i) pre = pl_prefetch(P, c0 + slot_i);      // (the previous chunk ended early)
             pl_stage(P, pre, S.scratch[warp][0], S.scratch[warp][1], S.scratch[warp][2], S0, slot_i, lane, n_tail);
@@ -533,55 +596,16 @@ __global__ void __launch_bounds__(PE_PL_THREADS, 1) k_place(const __grid_constan
         pre_task = c0 + nc + slot_i;                            // the next chunk's task, if this one runs to its end: loads fly during resolve
         if (pre_task < P.B) pre = pl_prefetch(P, pre_task);
         if (crank == 0) {
-            if (warp == 0) {
-                if (P.tk_words) pl_resolve<true>(P, S, tk, c0, nc, lane, n_amb, prof);
-                else pl_resolve<false>(P, S, tk, c0, nc, lane, n_amb, prof);
-            } else if ((warp & 3u) != 0u && warp < 12u) {
-                // ---- commit, WHILE the resolve warp works: NodeInfo.addTask (nodeinfo.go:125-153) for the chunk's placements,
-                // from the slots alone.  One thread per log entry, on the three schedulers the resolve warp does not use; an
-                // entry is taken as soon as the resolve warp has published it.
-                const uint32_t e = ((warp >> 2) * 3u + (warp & 3u) - 1u) * 32u + lane;        // 0 .. 287 >= PE_PL_CHUNK
-                bool mine = false;
-                for (;;) {
-                    if (e < *reinterpret_cast<volatile uint32_t *>(&S.n_pub)) { mine = true; break; }
-                    if (*reinterpret_cast<volatile uint32_t *>(&S.res_done)) { mine = e < *reinterpret_cast<volatile uint32_t *>(&S.n_pub); break; }
-                    __nanosleep(100);
-                }
-                if (mine) {
-                    __threadfence_block();
-                    const uint32_t n = S.log_node[e];
-                    const PlSlot &sl = S.slot[S.log_task[e]];
-                    P.K.out_node[sl.task_off] = n;
-                    const long long cpu_res = sl.cpu_res, mem_res = sl.mem_res;
-                    atomicAdd(&P.T.total[n], 1u);                   // (every task placed here counts: PE_SR_COUNTS)
-                    if (atomicAdd(&sl.svccol[n], 1u) + 1u >= 0xFFFFFFu) atomicOr(&P.ctr->error, PE_DEV_ERR_SVC_OVERFLOW);
-                    if (cpu_res | mem_res) {
-                        // the resolve warp's exact re-ranking reads these two columns as they were when the chunk began
-                        // (and takes the chunk's own placements from the log): they move when it is done
-                        while (!*reinterpret_cast<volatile uint32_t *>(&S.res_done)) __nanosleep(100);
-                        if (cpu_res) atomicAdd(reinterpret_cast<unsigned long long *>(&P.T.cpu[n]), (unsigned long long)(-cpu_res));
-                        if (mem_res) atomicAdd(reinterpret_cast<unsigned long long *>(&P.T.mem[n]), (unsigned long long)(-mem_res));
-                    }
-                    if (!(sl.flags & PE_SR_SIMPLE)) {
-                        // generic resources / host ports: such a task is the FIRST on its node in this batch and tasks that
-                        // join a touched node never reserve these, so one thread owns the cells
-                        const pe_group *g = &P.K.groups[P.b0 + c0 + S.log_task[e]];
-                        for (uint32_t w = 0; w < g->gen_cnt; w++) {
-                            if (!gen_first_occurrence(P.K, *g, w)) continue;
-                            int64_t *col = P.T.gen[P.K.gens[g->gen_off + w].kind];
-                            col[n] = claim_cell(P.K, *g, w, col[n]);
-                        }
-                        for (uint32_t w = 0; w < g->port_cnt; w++) {
-                            const uint32_t s = P.K.ports[g->port_off + w];
-                            P.T.ports[s >> 5][n] |= 1u << (s & 31u);
-                        }
-                    }
-                    atomicOr(&P.touched[n >> 5], 1u << (n & 31u));
-                    if (S.log_tail[e]) n_medium++; else n_fast++;
-                }
-            }
-            const long long t2 = clock64();
+            if (P.tk_words) pl_resolve<true>(P, S, tk, c0, nc, tid, n_amb, prof);
+            else pl_resolve<false>(P, S, tk, c0, nc, tid, n_amb, prof);
             __syncthreads();
+            const long long t2 = clock64();
+            // ---- commit: NodeInfo.addTask (nodeinfo.go:125-153) for the chunk's placements, from the slots alone
+            {
+                const uint32_t n_log = S.n_log;
+                for (uint32_t e = tid; e < n_log; e += blockDim.x) pl_commit(P, S, c0, e, n_fast, n_medium);
+                __syncthreads();
+            }
             for (uint32_t h = tid; h < PE_PL_HASH; h += blockDim.x) S.hkey[h] = PE_PL_EMPTY;     // the set of taken nodes is per chunk
             __threadfence();        // the chunk's reductions are performed before anyone passes the barrier
             cyc_resolve += t2 - t1; cyc_commit += clock64() - t2;
@@ -597,7 +621,7 @@ __global__ void __launch_bounds__(PE_PL_THREADS, 1) k_place(const __grid_constan
     // tallies: per-thread counters -> one atomic per warp
     n_tail = __reduce_add_sync(0xFFFFFFFFu, lane == 0 ? n_tail : 0u);
     n_amb = __reduce_add_sync(0xFFFFFFFFu, n_amb);                 // (counted by whichever resolve lane of CTA 0 re-ranked)
-    const uint32_t n_retry = (uint32_t)prof.retries, n_slow = (uint32_t)prof.slow;      // (lane 0 of the resolve warp counts)
+    const uint32_t n_retry = (uint32_t)prof.retries;      // (lane 0 of the resolve warp counts)
     n_fast = __reduce_add_sync(0xFFFFFFFFu, n_fast);
     n_medium = __reduce_add_sync(0xFFFFFFFFu, n_medium);
     if (lane == 0) {
@@ -618,7 +642,9 @@ __global__ void __launch_bounds__(PE_PL_THREADS, 1) k_place(const __grid_constan
         atomicAdd(&P.ctr->place_cyc[1], (unsigned long long)cyc_resolve);
         atomicAdd(&P.ctr->place_cyc[2], (unsigned long long)cyc_commit);
         // resolve-phase diagnostics (bench.py "place.resolve"): passes over a 32-task group, proposal rounds, chunks ended early
-        atomicAdd(&P.ctr->prof[0], (unsigned long long)n_slow); atomicAdd(&P.ctr->prof[2], (unsigned long long)n_retry);
+        atomicAdd(&P.ctr->prof[0], prof.passes); atomicAdd(&P.ctr->prof[1], prof.rounds); atomicAdd(&P.ctr->prof[2], (unsigned long long)n_retry);
+        atomicAdd(&P.ctr->prof[3], (unsigned long long)prof.cyc_filter); atomicAdd(&P.ctr->prof[4], (unsigned long long)prof.cyc_rounds);
+        atomicAdd(&P.ctr->prof[5], (unsigned long long)prof.cyc_final);
     }
 }
 
