@@ -274,8 +274,9 @@ int32_t pe_node_task_delta(pe_engine *h, const pe_task_delta *d, uint32_t n,
 /* Mirrors the group loop of tick + scheduleTaskGroup, applying reservations as
  * it goes.  out_node[n_tasks]: chosen node_idx or PE_NONE.  out_fail[n_groups*8]:
  * Pipeline failure counters (pipeline.go:56-68,84-103) as they stand when the
- * group finishes -- meaningful when the group has unplaced tasks.  Host
- * buffers in, host buffers out. */
+ * group finishes -- meaningful when the group has unplaced tasks, and WRITTEN
+ * only when some task of the tick went unplaced (the reference reads Explain()
+ * only then, scheduler.go:744-746).  Host buffers in, host buffers out. */
 int32_t pe_schedule(pe_engine *h, const pe_tick *tick, uint32_t *out_node, uint32_t *out_fail);
 
 /* Same pass split so the copy and the compute can be timed apart. */

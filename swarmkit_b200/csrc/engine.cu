@@ -498,8 +498,8 @@ struct pe_engine {
 
     // sync = false: pe_schedule keeps the caller's buffers alive itself and waits once, at the end of the whole call
     int32_t tick_upload(const pe_tick *tk, bool sync = true) {
-        int32_t rc = validate_and_prepare(tk);
-        if (rc) return rc;
+        if (!tk) { err = "null tick"; return PE_ERR_INVALID; }
+        int32_t rc;
         n_groups = tk->n_groups; n_tasks = tk->n_tasks;
         size_t off[10]; size_t o = 0;
         auto place = [&](int i, size_t bytes) { off[i] = o; o += (bytes + 15) / 16 * 16; };
@@ -529,6 +529,9 @@ struct pe_engine {
         CU(up(7, tk->plugs, (size_t)tk->n_plugs * 4));
         CU(up(8, tk->fails, (size_t)tk->n_fails * sizeof(pe_node_fail)));
         ev_end(ev);
+        // the host's pass over the groups (bounds, which columns the scan needs, missing service columns) runs while the
+        // copies above are in flight; nothing reads the device copy before it is through
+        if ((rc = validate_and_prepare(tk))) { n_groups = 0; n_tasks = 0; runs.clear(); return rc; }
         K.groups = reinterpret_cast<pe_group *>(b + off[0]);
         K.task_flags = reinterpret_cast<uint8_t *>(b + off[1]);
         K.gens = reinterpret_cast<pe_generic_want *>(b + off[2]);
@@ -965,7 +968,13 @@ struct pe_engine {
     int32_t tick_download(uint32_t *out_node, uint32_t *out_fail, bool sync = true) {
         EvPair *ev = ev_begin(3);
         if (out_node && n_tasks) { CU(cudaMemcpyAsync(out_node, d_out_node, (size_t)n_tasks * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (size_t)n_tasks * 4; }
-        if (out_fail && n_groups) { CU(cudaMemcpyAsync(out_fail, d_out_fail, (size_t)n_groups * PE_NUM_FILTERS * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (size_t)n_groups * PE_NUM_FILTERS * 4; }
+        // (pe_schedule: the failure counters are wanted only if some task went unplaced, which the tick's own counters say
+        // once the stream has drained -- finish_schedule() fetches them then; 32 bytes per group otherwise cross PCIe for nothing)
+        pending_fail = nullptr;
+        if (out_fail && n_groups) {
+            if (sync) { CU(cudaMemcpyAsync(out_fail, d_out_fail, (size_t)n_groups * PE_NUM_FILTERS * 4, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += (size_t)n_groups * PE_NUM_FILTERS * 4; }
+            else pending_fail = out_fail;
+        }
         ev_end(ev);
         if (!sync) return PE_OK;
         CU(cudaStreamSynchronize(stream));
@@ -990,9 +999,18 @@ struct pe_engine {
         return collect_counters();
     }
 
+    uint32_t *pending_fail = nullptr;
     int32_t finish_schedule() {
         CU(cudaStreamSynchronize(stream));
-        return counters_finish();      // (also collects the event timings)
+        const bool all_placed = h_ctr && h_ctr->placements == (unsigned long long)n_tasks;
+        int32_t rc = counters_finish();      // (also collects the event timings)
+        if (rc == PE_OK && pending_fail && !all_placed) {
+            CU(cudaMemcpyAsync(pending_fail, d_out_fail, (size_t)n_groups * PE_NUM_FILTERS * 4, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += (size_t)n_groups * PE_NUM_FILTERS * 4;
+        }
+        pending_fail = nullptr;
+        return rc;
     }
 
     // nodeSet.tree's leaves and their task sums for one service (nodeset.go:59-101); see kernel_misc.cuh

@@ -478,36 +478,46 @@ __device__ __forceinline__ void pl_resolve(const PlaceParams &P, PlShared &S, ui
                         else if (b_bad) { cut = c0_task + ib; done = ib; leave = true; }                      // not placeable here: the ordered sequencer takes over
                         else {
                             // ---- it skipped a candidate that ranked strictly better than its choice when the chunk began.  That
-                            // node was taken inside the chunk, so its rank moved: recompute it from the chunk's log (one lane; rare).
-                            if (lane == bad) {
-                                n_amb++;
-                                const PlSlot &sl = S.slot[i];
-                                unsigned long long bk = pl_key_of(sl, rank_of(j));
-                                uint32_t bn = prop, bj = j;
-                                for (uint32_t q = 0; q < j; q++) {
-                                    const uint32_t n = PE_PL_NODE(cd[q]);
-                                    const unsigned long long k0 = pl_key_of(sl, rank_of(q));
-                                    uint32_t svc = (uint32_t)(k0 >> 32) & 0xFFFFFFu, tot = (uint32_t)k0;
-                                    long long dcpu = 0, dmem = 0;
-                                    for (uint32_t e = 0; e < n_log; e++) {          // every placement of this chunk on that node
-                                        if (S.log_node[e] != n) continue;
-                                        const PlSlot &o = S.slot[S.log_task[e]];
-                                        tot++;
-                                        if (o.svccol == sl.svccol) svc++;
-                                        dcpu += o.cpu_res; dmem += o.mem_res;
-                                    }
-                                    bool ok = true;
-                                    if (sl.flags & PE_SR_RES)      // (the columns still hold the chunk-start amounts: reductions come after this phase)
-                                        ok = sl.cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) - dcpu &&
-                                             sl.mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n)) - dmem;
-                                    if (sl.flags & PE_SR_MAXREP) ok = ok && (unsigned long long)svc < sl.max_replicas;
-                                    const unsigned long long k = make_pref(0u, svc, tot);
-                                    if (ok && (k < bk || (k == bk && n < bn))) { bk = k; bn = n; bj = q; }
+                            // node was taken inside the chunk, so its rank moved: recompute the skipped candidates' ranks from the
+                            // chunk's log -- the warp's lanes take one skipped candidate each (rare).
+                            n_amb += lane == 0 ? 1u : 0u;
+                            const uint32_t jb = __shfl_sync(0xFFFFFFFFu, j, (int)bad), pb = __shfl_sync(0xFFFFFFFFu, prop, (int)bad);
+                            const PlSlot &sl = S.slot[ib];
+                            const uint32_t *cdb = S.cand + (size_t)ib * PE_PL_KS;
+                            const uint32_t q1 = S.s_rs1[ib], q2 = S.s_rs2[ib], q3 = S.s_rs3[ib];
+                            auto rank_b = [&](uint32_t x) -> uint32_t { return (x >= q1 ? 1u : 0u) + (x >= q2 ? 1u : 0u) + (x >= q3 ? 1u : 0u); };
+                            unsigned long long bk = pl_key_of(sl, rank_b(jb));     // the choice itself: every lane starts from it
+                            uint32_t bn = pb, bj = jb;
+                            for (uint32_t q = lane; q < jb; q += 32u) {
+                                const uint32_t n = PE_PL_NODE(cdb[q]);
+                                const unsigned long long k0 = pl_key_of(sl, rank_b(q));
+                                uint32_t svc = (uint32_t)(k0 >> 32) & 0xFFFFFFu, tot = (uint32_t)k0;
+                                long long dcpu = 0, dmem = 0;
+                                for (uint32_t e = 0; e < n_log; e++) {          // every placement of this chunk on that node
+                                    if (S.log_node[e] != n) continue;
+                                    const PlSlot &o = S.slot[S.log_task[e]];
+                                    tot++;
+                                    if (o.svccol == sl.svccol) svc++;
+                                    dcpu += o.cpu_res; dmem += o.mem_res;
                                 }
+                                bool ok = true;
+                                if (sl.flags & PE_SR_RES)      // (the columns still hold the chunk-start amounts: reductions come after this phase)
+                                    ok = sl.cpu_res <= __ldcg(reinterpret_cast<const long long *>(P.T.cpu + n)) - dcpu &&
+                                         sl.mem_res <= __ldcg(reinterpret_cast<const long long *>(P.T.mem + n)) - dmem;
+                                if (sl.flags & PE_SR_MAXREP) ok = ok && (unsigned long long)svc < sl.max_replicas;
+                                const unsigned long long k = make_pref(0u, svc, tot);
+                                if (ok && (k < bk || (k == bk && n < bn))) { bk = k; bn = n; bj = q; }
+                            }
+                            // the warp's best: smallest (rank key, node)
+                            const unsigned long long kmin = pl_wmin64(bk);
+                            const uint32_t nmin = __reduce_min_sync(0xFFFFFFFFu, bk == kmin ? bn : 0xFFFFFFFFu);
+                            const uint32_t who = (uint32_t)__ffs((int)__ballot_sync(0xFFFFFFFFu, bk == kmin && bn == nmin)) - 1u;
+                            bn = nmin; bj = __shfl_sync(0xFFFFFFFFu, bj, (int)who);
+                            if (lane == 0) {
                                 // (a winner other than its own proposal was taken before: the bitmap has it already)
-                                S.log_node[n_log] = bn; S.log_task[n_log] = (uint16_t)i; S.log_tail[n_log] = rank_of(bj) != 0u ? 1 : 0;
+                                S.log_node[n_log] = bn; S.log_task[n_log] = (uint16_t)ib; S.log_tail[n_log] = rank_b(bj) != 0u ? 1 : 0;
                                 if (BM) atomicOr(&tk[bn >> 5], 1u << (bn & 31u));
-                                if (!BM || (cd[bj] & PE_PL_TOUCHED)) pl_take(S, bn);
+                                if (!BM || (cdb[bj] & PE_PL_TOUCHED)) pl_take(S, bn);
                             }
                             n_log++;
                             __syncwarp();
