@@ -531,7 +531,7 @@ struct pe_engine {
         ev_end(ev);
         // the host's pass over the groups (bounds, which columns the scan needs, missing service columns) runs while the
         // copies above are in flight; nothing reads the device copy before it is through
-        if ((rc = validate_and_prepare(tk))) { n_groups = 0; n_tasks = 0; runs.clear(); return rc; }
+        if ((rc = validate_and_prepare(tk))) { cudaStreamSynchronize(stream); n_groups = 0; n_tasks = 0; runs.clear(); return rc; }   // (the caller's buffers are free again)
         K.groups = reinterpret_cast<pe_group *>(b + off[0]);
         K.task_flags = reinterpret_cast<uint8_t *>(b + off[1]);
         K.gens = reinterpret_cast<pe_generic_want *>(b + off[2]);
