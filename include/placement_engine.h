@@ -304,6 +304,16 @@ int32_t pe_fit(pe_engine *h, const pe_tick *tick, const uint32_t *node_idx,
 int32_t pe_pref_leaves(pe_engine *h, uint32_t svc_id, const uint32_t *cols, uint32_t n_levels, uint32_t cap,
                        uint32_t *out_vals, uint32_t *out_tasks, uint32_t *out_n_leaves);
 
+/* ---- the predicate matrix in the other direction ------------ */
+/* constraint.NodeMatches per (service, node) is also what the constraint enforcer
+ * (manager/orchestrator/constraintenforcer/constraint_enforcer.go:65-226) and the global orchestrator's node
+ * eligibility (manager/orchestrator/global/global.go:306,440,513) evaluate, one pair at a time.  This call
+ * evaluates the node-attribute filters a group ENABLES in filter_mask -- Ready, Plugin, Constraint, Platform; for
+ * NodeMatches alone set only 1 << PE_F_CONSTRAINT -- for every group of the tick against every row of the node
+ * set, with the kernel the scheduler's own batches use (one bit per pair): out_bits[n_groups * words],
+ * words = (node count + 31) / 32, bit n of row g = node n passes group g.  No state is read or changed. */
+int32_t pe_match_matrix(pe_engine *h, const pe_tick *tick, uint32_t *out_bits);
+
 /* ---- introspection (parity checker) -------------------------------------- */
 typedef struct pe_node_state {
     uint32_t flags;

@@ -493,6 +493,32 @@ int32_t ope_pref_leaves(pe_engine *h, uint32_t svc_id, const uint32_t *cols, uin
     return PE_OK;
 }
 
+// The node-attribute filters of every group against every node (constraint.NodeMatches per (service, node) when only the
+// constraint filter is enabled): constraint_enforcer.go:65-226, global.go:306,440,513
+int32_t ope_match_matrix(pe_engine *h, const pe_tick *tk, uint32_t *out_bits) {
+    Oracle &o = h->o;
+    int32_t rc = validate(o, tk);
+    if (rc) return rc;
+    Tick t = view(tk);
+    const size_t words = (o.n_nodes + 31) / 32;
+    std::memset(out_bits, 0, words * 4 * tk->n_groups);
+    for (uint32_t g = 0; g < tk->n_groups; g++) {
+        Sched s(o, t, t.groups[g]);
+        const uint32_t fm = t.groups[g].filter_mask;
+        for (uint32_t n = 0; n < o.n_nodes; n++) {
+            if (!(o.nodes[n].flags & PE_NODE_VALID)) continue;
+            if (t.groups[g].leaf_cnt && !s.in_leaf(n)) continue;
+            bool ok = true;
+            if ((fm >> PE_F_READY) & 1) ok = ok && s.check_ready(n);
+            if ((fm >> PE_F_PLUGIN) & 1) ok = ok && s.check_plugin(n);
+            if ((fm >> PE_F_CONSTRAINT) & 1) ok = ok && s.check_constraint(n);
+            if ((fm >> PE_F_PLATFORM) & 1) ok = ok && s.check_platform(n);
+            if (ok) out_bits[g * words + (n >> 5)] |= 1u << (n & 31);
+        }
+    }
+    return PE_OK;
+}
+
 int32_t ope_schedule(pe_engine *h, const pe_tick *tk, uint32_t *out_node, uint32_t *out_fail) {
     Oracle &o = h->o;
     int32_t rc = validate(o, tk);

@@ -40,6 +40,7 @@
 #define ope_fold_value mpe_fold_value
 #define ope_nccl_unique_id mpe_nccl_unique_id
 #define ope_pref_leaves mpe_pref_leaves
+#define ope_match_matrix mpe_match_matrix
 #include "flat_oracle.cpp"
 
 #include <cstdlib>

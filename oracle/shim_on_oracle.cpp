@@ -26,6 +26,7 @@
 #define pe_fold_value ope_fold_value
 #define pe_nccl_unique_id ope_nccl_unique_id
 #define pe_pref_leaves ope_pref_leaves
+#define pe_match_matrix ope_match_matrix
 #define ss_create sso_create
 #define ss_destroy sso_destroy
 #define ss_apply sso_apply

@@ -112,7 +112,7 @@ ABI_SYMBOLS = [
     "abi_version", "create", "destroy", "last_error", "node_upsert", "node_remove", "set_node_count",
     "node_task_delta", "schedule", "tick_upload", "tick_run", "tick_download", "fit", "snapshot",
     "snapshot_service", "snapshot_generic", "snapshot_ports", "get_stats", "stats_reset", "fold_value",
-    "nccl_unique_id", "pref_leaves",
+    "nccl_unique_id", "pref_leaves", "match_matrix",
 ]
 
 
@@ -220,6 +220,7 @@ class FlatABI:
         self.f["stats_reset"].argtypes = [C.c_void_p]
         self.f["fold_value"].argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
         self.f["nccl_unique_id"].argtypes = [C.c_void_p]
+        self.f["match_matrix"].argtypes = [C.c_void_p, C.POINTER(pe_tick), C.c_void_p]
         self.f["pref_leaves"].argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         if self.f["abi_version"]() != PE_ABI_VERSION:
             raise RuntimeError("ABI version mismatch")
@@ -314,6 +315,15 @@ class FlatABI:
         ts = tick.c_struct()
         self._check(self.f["fit"](self.h, C.byref(ts), _ptr(node_idx), _ptr(ok), _ptr(out_fail)))
         return ok[:tick.n_groups], out_fail[:tick.n_groups * PE_NUM_FILTERS].reshape(-1, PE_NUM_FILTERS)
+
+    def match_matrix(self, tick: Tick, n_nodes: int):
+        """[n_groups, n_nodes] bool: the node-attribute filters each group enables, for every (group, node) pair."""
+        words = (n_nodes + 31) // 32
+        out = np.zeros(max(tick.n_groups * words, 1), np.uint32)
+        ts = tick.c_struct()
+        self._check(self.f["match_matrix"](self.h, C.byref(ts), _ptr(out)))
+        bits = np.unpackbits(out[:tick.n_groups * words].view(np.uint8), bitorder="little").reshape(tick.n_groups, words * 32)
+        return bits[:, :n_nodes].astype(bool)
 
     def pref_leaves(self, svc: int, cols, cap: int = 4096):
         """Leaves of the placement-preference tree of one service: (value tuples [n, levels], task sums [n])."""

@@ -1057,6 +1057,40 @@ struct pe_engine {
         return PE_OK;
     }
 
+    // (service, node) predicate matrix for the enforcer / global orchestrator: k_static over every group
+    int32_t match_matrix(const pe_tick *tk, uint32_t *out_bits) {
+        int32_t rc;
+        if (!out_bits) { err = "match_matrix: null output"; return PE_ERR_INVALID; }
+        if ((rc = tick_upload(tk, true))) return rc;
+        if (!n_groups || !n_nodes) return PE_OK;
+        if ((rc = ensure_scratch())) return rc;
+        const size_t stride = e_stride();
+        if ((size_t)n_groups * stride > S_words) {
+            void *p = Sbuf; size_t c = S_words * 4;
+            if ((rc = ensure_buf(p, c, (size_t)n_groups * stride * 4))) return rc;
+            Sbuf = reinterpret_cast<uint32_t *>(p); S_words = c / 4;
+        }
+        if ((rc = ensure_buf(cls_buf, cls_cap, ((size_t)n_groups + 1) * 4 + 64))) return rc;
+        uint32_t *reps = reinterpret_cast<uint32_t *>(cls_buf);
+        std::vector<uint32_t> iota((size_t)n_groups + 1);
+        for (uint32_t i = 0; i < n_groups; i++) iota[i] = i;
+        iota[n_groups] = n_groups;                                  // the row count k_static reads from the device
+        CU(cudaMemcpyAsync(reps, iota.data(), iota.size() * 4, cudaMemcpyHostToDevice, stream));
+        StaticParams XP;
+        XP.T = table(); XP.K = K; XP.S = Sbuf; XP.s_stride = (uint32_t)stride; XP.lo = 0; XP.hi = n_nodes; XP.ctr = d_ctr;
+        XP.reps = reps; XP.n_reps = reps + n_groups;
+        const unsigned long long units = (unsigned long long)n_groups * (stride / 32u);
+        const uint32_t grid = (uint32_t)std::min<unsigned long long>((units + 7) / 8, (unsigned long long)num_sms * 16ull);
+        k_static<<<std::max(grid, 1u), 256, 0, stream>>>(XP);
+        stats.kernel_launches++;
+        CU(cudaGetLastError());
+        const size_t words = (n_nodes + 31) / 32;
+        CU(cudaMemcpy2DAsync(out_bits, words * 4, Sbuf, stride * 4, words * 4, n_groups, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));                          // (also: `iota` may go now)
+        stats.d2h_bytes += words * 4 * n_groups;
+        return PE_OK;
+    }
+
     template <class T> int32_t snap_col(const T *col, uint32_t first, uint32_t n, T *out) {
         if ((uint64_t)first + n > cap) { err = "snapshot range out of bounds"; return PE_ERR_INVALID; }
         if (!col) { std::memset(out, 0, (size_t)n * sizeof(T)); return PE_OK; }
@@ -1151,6 +1185,8 @@ int32_t pe_pref_leaves(pe_engine *h, uint32_t svc_id, const uint32_t *cols, uint
                        uint32_t *out_tasks, uint32_t *out_n_leaves) {
     return h->pref_leaves(svc_id, cols, n_levels, cap, out_vals, out_tasks, out_n_leaves);
 }
+
+int32_t pe_match_matrix(pe_engine *h, const pe_tick *tick, uint32_t *out_bits) { return h->match_matrix(tick, out_bits); }
 
 int32_t pe_get_stats(pe_engine *h, pe_stats *out) { *out = h->stats; return PE_OK; }
 int32_t pe_stats_reset(pe_engine *h) { h->stats = pe_stats{}; return PE_OK; }

@@ -149,6 +149,29 @@ def test_pref_leaves(seed):
         gpu.pref_leaves(0, [first, first + 1], cap=2)       # more leaves than the caller's buffers hold
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_match_matrix(seed):
+    """The (service, node) predicate matrix for the constraint enforcer / global orchestrator (pe_match_matrix):
+    constraint.NodeMatches alone, and all four node-attribute filters, against the oracle."""
+    rng = np.random.default_rng(3200 + seed)
+    n = int(rng.integers(40, 4000))
+    nodes = R.random_nodes(rng, n)
+    tick = R.random_tick(rng, n, 80, feature_p=0.6)
+    gpu, cpu = PlacementEngine(node_capacity=n), OracleEngine(node_capacity=n)
+    for e in (gpu, cpu):
+        e.node_upsert(nodes)
+        e.set_node_count(n)
+    for only_constraints in (True, False):
+        t = tick.slice_groups(0, tick.n_groups)
+        g = t.groups.copy()
+        if only_constraints:
+            g["filter_mask"] &= 1 << abi.PE_F_CONSTRAINT
+        t.groups = g
+        a, b = gpu.match_matrix(t, n), cpu.match_matrix(t, n)
+        assert a.shape == (tick.n_groups, n) and (a == b).all(), f"seed {seed} only_constraints={only_constraints}: {(a != b).sum()} pairs differ"
+        assert 0 < a.sum() < a.size
+
+
 def test_large_group_global_path():
     # k > 2048 candidates: the sequencer's global-memory sort / fill path
     w = W.cfg1(n_nodes=5000, n_tasks=12000)
