@@ -406,6 +406,7 @@ struct Scheduler {
     std::unordered_map<std::string, uint32_t> pref_cols, pref_ids{{"", 0}};
     std::vector<std::string> pref_strings{""};
     uint32_t next_label_col = PE_ATTR_FIRST_LABEL;
+    uint64_t rows_uploaded = 0, full_uploads = 0;   // node rows sent with pe_node_upsert; how often the whole table went
     bool layout_dirty = true;            // membership / dictionary change: re-upload every row
     std::set<std::string> dirty_nodes;   // rows whose NodeInfo changed on the host side
     std::vector<std::string> idx_to_id;
@@ -560,6 +561,8 @@ struct Scheduler {
                 if (idx != PE_NONE && it != nodeSet.end()) encode_row(idx, it->second, b);
             }
         }
+        if (layout_dirty) full_uploads++;
+        rows_uploaded += b.rows.size();
         layout_dirty = false;
         dirty_nodes.clear();
         if (b.rows.empty()) return true;
@@ -1167,6 +1170,8 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         }
         out.set("nodes", arr);
         if (op == "device_check") out.set("mismatch", bad);
+        out.set("rows_uploaded", mj::Value::integer((int64_t)S.rows_uploaded));      // event ingestion: only rows
+        out.set("full_uploads", mj::Value::integer((int64_t)S.full_uploads));        // store events touched cross the ABI
         mj::Value un = mj::Value::array();
         for (auto &kv : S.unassignedTasks) un.push(mj::Value::string(kv.first));
         out.set("unassigned", un);

@@ -212,3 +212,29 @@ def count_by_node(assign: dict, prefix: str = "") -> dict:
         if tid.startswith(prefix):
             out[nid] = out.get(nid, 0) + 1
     return out
+
+
+def drain_storm_scenario(make):
+    """Event ingestion (SURVEY 8f-4, cfg5's flow): a drain storm reaches the device mirror as row upserts of the drained
+    nodes alone -- createOrUpdateNode (scheduler.go:368-396) marks a row dirty, membership changes rebuild the table."""
+    nodes = [node(f"n{i:03d}", description=description(resources=resources(8 * 10**9, 2**34))) for i in range(200)]
+    tasks = [task(f"t{i:04d}", service_id=f"s{i % 7}", spec_version=1, reservations=resources(10**8, 2**26)) for i in range(600)]
+    c = Cluster(make(), nodes=nodes, tasks=tasks, services=[(f"s{i}", 1) for i in range(7)])
+    d = c.tick()
+    assert len(c.assignments(d)) == 600
+    s0 = c.s.apply({"op": "device_check"})
+    assert s0["mismatch"] == [] and s0["full_uploads"] == 1 and s0["rows_uploaded"] == 200
+    # drain 20 nodes; their tasks come back as new pending tasks of the same services (tasks.go:86-117)
+    drained = [f"n{i:03d}" for i in range(0, 200, 10)]
+    moved = [t for t in c.tasks.values() if t["node_id"] in drained]
+    for nid in drained:
+        c.update_node(dict(c.nodes[nid], availability="DRAIN") if "availability" in c.nodes[nid] else node(nid, availability="DRAIN", description=c.nodes[nid]["description"]))
+    for j, t in enumerate(moved):
+        c.update_task(dict(t, desired_state="SHUTDOWN"))
+        c.create_task(task(f"r{j:04d}", service_id=t["service_id"], spec_version=1, reservations=resources(10**8, 2**26)))
+    d = c.tick()
+    placed = c.assignments(d)
+    assert len(placed) == len(moved) and not set(placed.values()) & set(drained)
+    s1 = c.s.apply({"op": "device_check"})
+    assert s1["mismatch"] == [] and s1["full_uploads"] == 1
+    assert s1["rows_uploaded"] - s0["rows_uploaded"] == len(drained), s1["rows_uploaded"]

@@ -133,3 +133,9 @@ def test_commit_failure_rolls_back():
     c = Cluster(make_mirror(), nodes=nodes, tasks=tasks, services=[("s", 1)])
     c.tick(fail_commit=["t1"])
     assert c.s.apply({"op": "device_check"})["mismatch"] == []
+
+
+def test_drain_storm_uploads_only_the_changed_rows():
+    """cfg5's flow through the shim on the GPU: the drained nodes' rows are the only ones that cross the ABI again."""
+    from tests.sched_harness import drain_storm_scenario
+    drain_storm_scenario(make_mirror)

@@ -69,3 +69,8 @@ def test_random_event_stream_flat_vs_object(seed):
                 c.delete_node(r2.choice(sorted(c.nodes)))
             c.advance(r2.choice([1, 30, 200]))
         next_task += 25
+
+
+def test_drain_storm_uploads_only_the_changed_rows():
+    from tests.sched_harness import drain_storm_scenario
+    drain_storm_scenario(make_shim)
