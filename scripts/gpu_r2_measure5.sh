@@ -1,8 +1,8 @@
 #!/bin/bash
 # round 2: resolve v4, concurrent commit on/off, cluster 8
 mkdir -p gpurun_out
-echo "== headline suite"; timeout 900 python -m pytest tests/test_headline_gpu.py -q -x 2>&1 | tail -3
-for cc in 8 16; do
+echo skip-suite
+for cc in 16; do
   echo "== bench cluster=$cc"
   PE_PLACE_CLUSTER=$cc timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu --latency-ticks 0 > gpurun_out/r2e_bench_cc$cc.json 2> gpurun_out/r2e_bench_cc$cc.err; echo "rc=$?"; tail -c 400 gpurun_out/r2e_bench_cc$cc.err
   python - <<PY
