@@ -384,7 +384,10 @@ __device__ __forceinline__ unsigned long long pl_key_of(const PlSlot &s, uint32_
 //   25k  one warp, a group at a time, per-lane candidate windows re-read inside the rounds
 //   51k  the same with the masks computed by that one warp
 //   87k  the tasks strictly one after the other, lanes = candidates
-//   23.5k this version (5.5 rounds of ~600 cycles per group; one ballot per bit of the node index instead of match.any: 28k)
+//   23.5k this version (5.5 rounds of ~560 cycles per group; one ballot per bit of the node index instead of match.any: 28k)
+//   33k  this version with the NEXT group's masks worked out by the other warps while warp 0 runs the rounds (and every
+//        popped candidate looked up once more): anything else that runs on the SM slows the lone warp down -- its rounds
+//        took 2.1x as long -- which is also why the commit phase does not run next to the resolve phase
 struct PlProf { unsigned long long passes, rounds, retries; long long cyc_filter, cyc_rounds, cyc_final; };   // (cycles: thread 0's view)
 
 template <bool BM>
