@@ -115,6 +115,7 @@ struct pe_engine {
                                                      //     parallel placement step stopped in the current batch
     uint32_t *cursors = nullptr; size_t cursors_cap = 0;   // [rows][2] class-list cursors of the placement step
     uint32_t place_cluster = PE_PL_CLUSTER;                // CTAs per cluster of k_place (8 or 16)
+    uint32_t batch_shift = 0;                              // batches of this tick are 2^-batch_shift of the usual size (hand-over feedback)
     void *groups_buf = nullptr;                            // scratch of k_groups: class table | GroupSel | per-CTA class counts
     int groups_grid = 0;                                   // CTAs of the cooperative launch (0: not available)
     DevCounters *d_ctr = nullptr;
@@ -892,7 +893,13 @@ struct pe_engine {
         // batch x the row's node density) hands the rest to the ordered sequencer, so they must not be too long: a sixth of
         // the nodes, at most 16384 (measured on cfg3: 4736 -> 16384 takes the scan from 115 to 34 ms per million tasks).
         // (a multiple of 8, at least 8: the multi-rank exchange strides its arrays by the batch's row count rounded up to 8)
-        const uint32_t Bmax = max_batch ? std::max(8u, round_up(max_batch, 8u)) : std::min(16384u, std::max(256u, round_up(n_nodes / 6u, 16u)));
+        // Feedback from the previous tick (its counters are on the host by now): a batch the placement step had to hand to
+        // the ordered sequencer -- a task found both recorded classes of its row consumed, which is what happens when the
+        // nodes carry many tasks and every (service count, total) class is small -- costs milliseconds on one SM.  Such
+        // ticks are followed by ticks with shorter batches (every batch starts from a fresh scan); clean ticks grow them
+        // back.  The batch size never changes a placement (tests/test_headline_gpu.py::test_cfg3_oneoff_batch_sizes).
+        uint32_t Bmax = max_batch ? std::max(8u, round_up(max_batch, 8u)) : std::min(16384u, std::max(256u, round_up(n_nodes / 6u, 16u)));
+        if (!max_batch && batch_shift) Bmax = std::max(std::min(Bmax, 1024u), round_up(Bmax >> batch_shift, 16u));
         const bool spec = !(cfg_flags & PE_CFG_NO_SPECULATION) && n_nodes > 0;
         if (spec) {
             size_t need = (size_t)Bmax * 2u * e_stride();   // two class rows per scan row
@@ -953,6 +960,8 @@ struct pe_engine {
         for (int r = 0; r < 16; r++) stats.seq_prof[r] += c.prof[r];
         stats.seq_cons_wait += c.cyc_cons_wait; stats.seq_cons_work += c.cyc_cons_work; stats.seq_rewalks += c.iters;
         stats.evals += c.scan_evals; stats.scan_bytes += c.scan_bytes; stats.static_evals += c.static_evals; stats.scan_rows += c.scan_rows;
+        if (c.place_cuts) batch_shift = std::min(batch_shift + 1u, 4u);          // (see tick_enqueue)
+        else if (c.place_tasks && batch_shift) batch_shift--;
         stats.place_tasks += c.place_tasks; stats.place_cuts += c.place_cuts; stats.place_amb += c.place_amb; stats.place_tails += c.place_tails;
         stats.place_chunks += c.place_chunks;
         for (int r = 0; r < 3; r++) stats.place_cyc[r] += c.place_cyc[r];
