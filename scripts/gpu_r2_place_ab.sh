@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2: resolve v4, concurrent commit on/off, cluster 8
+# round 2: A-B runs of k_place variants (PE_PLACE_CLUSTER = 8 / 16): headline parity tests, then the bench line with the per-phase counters
 mkdir -p gpurun_out
 echo skip-suite
 for cc in 16; do
