@@ -420,7 +420,35 @@ struct Scheduler {
     }
     uint32_t value_id(const std::string &s) { return intern(val_ids, fold(s)); }
     uint32_t exact_id(const std::string &s) { return intern(exact_ids, s); }
-    uint32_t svc_id(const std::string &s) { return intern(svc_ids, s); }
+    // Service ids name the engine's per-service counter columns (one dense column per id, never freed by the engine): ids of
+    // services nobody counts or references any more are handed out again, so the columns are bounded by the services alive
+    // at one time, not by the services ever seen.  (A recycled id's column is all zeros: the device counts mirror the host's.)
+    std::vector<uint32_t> free_svc_ids;
+    uint32_t next_svc_id = 0;
+    size_t svc_recycle_min = 4096, svc_recycle_at = 4096;   // look for dead services once this many ids are in use
+    uint32_t svc_id(const std::string &s) {
+        auto it = svc_ids.find(s);
+        if (it != svc_ids.end()) return it->second;
+        uint32_t id;
+        if (!free_svc_ids.empty()) { id = free_svc_ids.back(); free_svc_ids.pop_back(); }
+        else id = next_svc_id++;
+        svc_ids[s] = id;
+        return id;
+    }
+    void recycle_service_ids() {
+        if (svc_ids.size() < svc_recycle_at) return;
+        std::set<std::string> live;
+        for (auto &kv : nodeSet) for (auto &c : kv.second.by_service) if (c.second != 0) live.insert(c.first);
+        for (auto &kv : allTasks) if (kv.second) live.insert(kv.second->service);
+        for (auto &kv : unassignedTasks) if (kv.second) live.insert(kv.second->service);
+        for (auto &kv : pendingPreassignedTasks) if (kv.second) live.insert(kv.second->service);
+        for (auto it = svc_ids.begin(); it != svc_ids.end();) {
+            if (live.count(it->first)) { ++it; continue; }
+            free_svc_ids.push_back(it->second);
+            it = svc_ids.erase(it);
+        }
+        svc_recycle_at = std::max<size_t>(svc_recycle_min, 2 * svc_ids.size());      // (amortised: the sweep is O(nodes + tasks))
+    }
     uint32_t kind_id(const std::string &s) { return intern(kind_ids, s); }
     uint32_t label_col(const std::string &prefixed) {   // "n:<key>" node label, "e:<key>" engine label
         auto it = label_cols.find(prefixed);
@@ -1028,6 +1056,7 @@ struct Scheduler {
     }
     // tick, scheduler.go:429-488
     bool tick(const std::set<std::string> &failCommit, std::map<std::string, Decision> &decisions) {
+        recycle_service_ids();
         std::map<std::pair<std::string, uint64_t>, std::vector<TaskP>> bySpec;
         std::vector<TaskP> oneOff;
         for (auto it = unassignedTasks.begin(); it != unassignedTasks.end(); it = unassignedTasks.erase(it)) {
@@ -1099,6 +1128,7 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         for (auto &n : ev.at("nodes").a) nodes.push_back(parse_node(n));
         for (auto &t : ev.at("tasks").a) tasks.push_back(parse_task(t));
         for (auto &s : ev.at("services").a) S.services[s.at("id").as_str()] = {!s.at("spec_version").is_null(), (uint64_t)s.at("spec_version").as_int()};
+        if (!ev.at("svc_recycle_at").is_null()) S.svc_recycle_min = S.svc_recycle_at = (size_t)ev.at("svc_recycle_at").as_int();
         S.setupTasksList(nodes, tasks);
     } else if (op == "set_service") S.services[ev.at("id").as_str()] = {!ev.at("spec_version").is_null(), (uint64_t)ev.at("spec_version").as_int()};
     else if (op == "delete_service") S.services.erase(ev.at("id").as_str());
@@ -1130,8 +1160,17 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
                 bool same = dev[idx].cpu_avail == ni.avail.cpu && dev[idx].mem_avail == ni.avail.mem && dev[idx].total_tasks == (uint32_t)ni.active;
                 for (auto &s : ni.by_service) {
                     uint32_t v = 0;
-                    if (!S.check(pe_snapshot_service(S.eng, S.svc_id(s.first), idx, 1, &v), "pe_snapshot_service")) { out.set("error", mj::Value::string(S.fatal)); return out; }
+                    auto known = S.svc_ids.find(s.first);        // (a service whose id was recycled counts nowhere)
+                    if (known == S.svc_ids.end()) { same = same && s.second == 0; continue; }
+                    if (!S.check(pe_snapshot_service(S.eng, known->second, idx, 1, &v), "pe_snapshot_service")) { out.set("error", mj::Value::string(S.fatal)); return out; }
                     same = same && v == (uint32_t)s.second;
+                }
+                // ... and no column counts anything for this node beyond what NodeInfo knows
+                for (auto &kv : S.svc_ids) {
+                    if (ni.by_service.count(kv.first)) continue;
+                    uint32_t v = 0;
+                    if (!S.check(pe_snapshot_service(S.eng, kv.second, idx, 1, &v), "pe_snapshot_service")) { out.set("error", mj::Value::string(S.fatal)); return out; }
+                    same = same && v == 0u;
                 }
                 std::set<std::string> kinds; for (auto &g : ni.avail.generic) kinds.insert(g.kind);
                 for (auto &kd : S.kind_ids) {
@@ -1172,6 +1211,8 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         if (op == "device_check") out.set("mismatch", bad);
         out.set("rows_uploaded", mj::Value::integer((int64_t)S.rows_uploaded));      // event ingestion: only rows
         out.set("full_uploads", mj::Value::integer((int64_t)S.full_uploads));        // store events touched cross the ABI
+        out.set("service_ids", mj::Value::integer((int64_t)S.svc_ids.size()));       // ids in use / ever handed out (recycling)
+        out.set("service_id_high_water", mj::Value::integer((int64_t)S.next_svc_id));
         mj::Value un = mj::Value::array();
         for (auto &kv : S.unassignedTasks) un.push(mj::Value::string(kv.first));
         out.set("unassigned", un);

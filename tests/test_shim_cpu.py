@@ -74,3 +74,32 @@ def test_random_event_stream_flat_vs_object(seed):
 def test_drain_storm_uploads_only_the_changed_rows():
     from tests.sched_harness import drain_storm_scenario
     drain_storm_scenario(make_shim)
+
+
+def test_service_ids_are_recycled_under_churn():
+    """The engine keeps one dense counter column per service id and never frees one: the shim hands the ids of services
+    nobody counts or references any more out again, so the columns are bounded by the services alive at one time."""
+    from tests.sched_harness import description, node, resources, task
+    nodes = [node(f"n{i:02d}", description=description(resources=resources(64 * 10**9, 2**36))) for i in range(12)]
+    cm, co = Cluster(make_shim(), nodes=nodes), Cluster(make_oracle(), nodes=nodes)
+    cm.s.apply({"op": "init", "now_ns": cm.now, "nodes": nodes, "tasks": [], "services": [], "svc_recycle_at": 8})
+    high = 0
+    for rnd in range(40):
+        live = [f"svc{rnd}-{j}" for j in range(3)]
+        for c in (cm, co):
+            for sid in live:
+                c.set_service(sid, 1)
+                for r in range(4):
+                    c.create_task(task(f"t{rnd:02d}-{sid}-{r}", service_id=sid, spec_version=1, reservations=resources(10**8, 2**20)))
+        dm, do = cm.run(), co.run()
+        assert comparable(dm, cm) == comparable(do, co), f"round {rnd}: decisions differ"
+        sm = cm.s.apply({"op": "device_check"})
+        assert sm["mismatch"] == [], f"round {rnd}: {sm['mismatch']}"
+        assert sm["nodes"] == co.snapshot()["nodes"]
+        high = max(high, sm["service_id_high_water"])
+        # the services of this round go away: their tasks are shut down and deleted
+        for c in (cm, co):
+            for t in [t for t in c.tasks.values() if t["service_id"] in live]:
+                c.update_task(dict(t, status=dict(t["status"], state="SHUTDOWN")))
+                c.delete_task(t["id"])
+    assert high <= 16, high          # 120 services came and went; at most a handful of ids were ever alive together
