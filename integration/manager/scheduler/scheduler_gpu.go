@@ -49,7 +49,10 @@ type gpuEngine struct {
 	h         *C.pe_engine
 	values    map[string]uint32 // folded constraint operands / attribute values; "" = 0 (strings.EqualFold -> ==)
 	exact     map[string]uint32 // Platform.OS / normalised Platform.Architecture (filter.go:291-312)
-	services  map[string]uint32
+	services  map[string]uint32      // service ID -> id of its dense counter column in the engine (ids are recycled, see serviceID)
+	freeSvc   []uint32
+	nextSvc   uint32
+	recycleAt int
 	kinds     map[string]uint32      // generic resource kinds
 	labelCols map[string]uint32      // "n:<key>" / "e:<key>" -> attribute column of FOLDED values (constraints)
 	prefCols  map[string]uint32      // same keys -> attribute column of EXACT values (placement preferences)
@@ -74,7 +77,53 @@ func mustNewGPUEngine() *gpuEngine {
 	return &gpuEngine{h: h, values: map[string]uint32{"": 0}, exact: map[string]uint32{"": 0}, services: map[string]uint32{},
 		kinds: map[string]uint32{}, labelCols: map[string]uint32{}, prefCols: map[string]uint32{}, prefIDs: map[string]uint32{"": 0},
 		prefStr: []string{""}, ports: map[hostPortSpec]uint32{}, plugins: map[[2]string]uint32{}, nextCol: C.PE_ATTR_FIRST_LABEL,
-		index: map[string]uint32{}, dirty: map[string]struct{}{}, layout: true}
+		index: map[string]uint32{}, dirty: map[string]struct{}{}, layout: true, recycleAt: 4096}
+}
+
+// serviceID names the engine's per-service counter column.  The engine never frees a column, so the ids of services that
+// no node counts and no task references any more are handed out again (recycleServiceIDs, called at the top of a tick):
+// the columns are bounded by the services alive at one time.  A recycled column is all zeros: the device counts mirror
+// NodeInfo.ActiveTasksCountByService.
+func (e *gpuEngine) serviceID(s string) uint32 {
+	if id, ok := e.services[s]; ok {
+		return id
+	}
+	var id uint32
+	if n := len(e.freeSvc); n > 0 {
+		id, e.freeSvc = e.freeSvc[n-1], e.freeSvc[:n-1]
+	} else {
+		id = e.nextSvc
+		e.nextSvc++
+	}
+	e.services[s] = id
+	return id
+}
+
+func (s *Scheduler) recycleServiceIDs() {
+	e := s.gpu
+	if len(e.services) < e.recycleAt {
+		return
+	}
+	live := map[string]struct{}{}
+	for _, ni := range s.nodeSet.nodes {
+		for svc, c := range ni.ActiveTasksCountByService {
+			if c != 0 {
+				live[svc] = struct{}{}
+			}
+		}
+	}
+	for _, t := range s.allTasks {
+		live[t.ServiceID] = struct{}{}
+	}
+	for svc, id := range e.services {
+		if _, ok := live[svc]; !ok {
+			e.freeSvc = append(e.freeSvc, id)
+			delete(e.services, svc)
+		}
+	}
+	if e.recycleAt = 2 * len(e.services); e.recycleAt < 4096 {
+		e.recycleAt = 4096
+	}
 }
 
 func (e *gpuEngine) err(what string) error { return fmt.Errorf("%s: %s", what, C.GoString(C.pe_last_error(e.h))) }
@@ -245,7 +294,7 @@ func (e *gpuEngine) encodeRow(idx uint32, ni *NodeInfo, b *rowBatch) {
 	r.svc_off = C.uint32_t(len(b.svcs))
 	for svc, c := range ni.ActiveTasksCountByService {
 		if c != 0 {
-			b.svcs = append(b.svcs, C.pe_kv32{key: C.uint32_t(intern(e.services, svc)), value: C.uint32_t(c)})
+			b.svcs = append(b.svcs, C.pe_kv32{key: C.uint32_t(e.serviceID(svc)), value: C.uint32_t(c)})
 		}
 	}
 	r.svc_cnt = C.uint32_t(len(b.svcs)) - r.svc_off
@@ -451,7 +500,7 @@ func fillIP(ic *C.pe_ip_constraint, ip16 net.IP, mask net.IPMask, cidr, v4 bool)
 // encodeGroup: one pe_group for tasks that share a spec (the SetTask methods: filter.go:35,60,118,224,259,328,369).
 func (s *Scheduler) encodeGroup(tasks []*api.Task, b *tickBuf, now time.Time) error {
 	e, t := s.gpu, tasks[0]
-	g := C.pe_group{log_plugin: C.PE_NONE, svc_id: C.uint32_t(intern(e.services, t.ServiceID)), n_tasks: C.uint32_t(len(tasks)),
+	g := C.pe_group{log_plugin: C.PE_NONE, svc_id: C.uint32_t(e.serviceID(t.ServiceID)), n_tasks: C.uint32_t(len(tasks)),
 		task_off: C.uint32_t(len(b.flags)), filter_mask: 1 << C.PE_F_READY}
 	for _, x := range tasks {
 		f := C.uint8_t(0)
@@ -590,6 +639,7 @@ func (s *Scheduler) assign(t *api.Task, nodeID string, group map[string]*api.Tas
 // in ONE pe_schedule call, a group with preferences is walked leaf by leaf in between.
 func (s *Scheduler) scheduleTickGPU(ctx context.Context, groups []map[string]*api.Task, decisions map[string]schedulingDecision) {
 	now := time.Now() // sampled once per tick (the reference samples it once per group, scheduler.go:706)
+	s.recycleServiceIDs()
 	var run []map[string]*api.Task
 	flush := func() {
 		if len(run) != 0 {
@@ -810,7 +860,7 @@ func (s *Scheduler) schedulePreferenceGroup(ctx context.Context, group map[strin
 		ccols[i] = C.uint32_t(c)
 	}
 	var nLeaves C.uint32_t
-	if rc := C.pe_pref_leaves(s.gpu.h, C.uint32_t(intern(s.gpu.services, ts[0].ServiceID)), ptr(ccols), C.uint32_t(len(cols)),
+	if rc := C.pe_pref_leaves(s.gpu.h, C.uint32_t(s.gpu.serviceID(ts[0].ServiceID)), ptr(ccols), C.uint32_t(len(cols)),
 		C.uint32_t(leafCap), ptr(vals), ptr(tasks), &nLeaves); rc != C.PE_OK {
 		requeue(s.gpu.err("pe_pref_leaves"))
 		return
