@@ -25,6 +25,7 @@
 // Placement.Preferences (scheduler.go:772-825): the branch walk is host code here as in the
 // reference; the engine supplies the tree's leaves and fills one leaf per group.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -407,6 +408,7 @@ struct Scheduler {
     std::vector<std::string> pref_strings{""};
     uint32_t next_label_col = PE_ATTR_FIRST_LABEL;
     uint64_t rows_uploaded = 0, full_uploads = 0;   // node rows sent with pe_node_upsert; how often the whole table went
+    double host_encode_ms = 0, host_engine_ms = 0, host_apply_ms = 0;   // where a tick's host time went (last tick)
     bool layout_dirty = true;            // membership / dictionary change: re-upload every row
     std::set<std::string> dirty_nodes;   // rows whose NodeInfo changed on the host side
     std::vector<std::string> idx_to_id;
@@ -678,6 +680,14 @@ struct Scheduler {
         // shared by every group of the same (service, spec version): (offset, count) into `fails`
         bool fails_built = false;
         std::map<SvcVer, std::pair<uint32_t, uint32_t>> fail_range;
+        // an encoder that gives up half-way must leave no side arrays behind: remember the sizes, cut back to them
+        // (the failure lists are built once per tick and stay)
+        struct Mark { size_t groups, flags, gens, cons, ips, plats, ports, plugs; };
+        Mark mark() const { return {groups.size(), flags.size(), gens.size(), cons.size(), ips.size(), plats.size(), ports.size(), plugs.size()}; }
+        void rollback(const Mark &m) {
+            groups.resize(m.groups); flags.resize(m.flags); gens.resize(m.gens); cons.resize(m.cons); ips.resize(m.ips);
+            plats.resize(m.plats); ports.resize(m.ports); plugs.resize(m.plugs);
+        }
         pe_tick view() const {
             pe_tick t{};
             t.groups = groups.data(); t.n_groups = (uint32_t)groups.size();
@@ -693,7 +703,30 @@ struct Scheduler {
         }
     };
     // constraint.Parse (constraint.go:40-81) + key dispatch of NodeMatches (:107-207), compiled to integer programs
+    // (one-off tasks of one service carry the same expressions: a tick of 1M tasks parses ~1000 distinct lists, not 1M.
+    // The compiled form only holds ids that never change once handed out -- columns, value ids -- so it stays valid.)
+    struct Compiled { bool ok = false, never = false; std::vector<pe_constraint> cons; std::vector<pe_ip_constraint> ips; };
+    std::unordered_map<std::string, Compiled> compiled_cache;
     bool compile_constraints(const std::vector<std::string> &env, pe_group &g, TickBuf &b) {
+        std::string key;
+        for (auto &e : env) { key += e; key += '\x1f'; }
+        auto hit = compiled_cache.find(key);
+        if (hit == compiled_cache.end()) {
+            if (compiled_cache.size() > (1u << 16)) compiled_cache.clear();      // (bounded; a miss only costs the parse)
+            Compiled c;
+            c.ok = parse_constraints(env, c);
+            hit = compiled_cache.emplace(std::move(key), std::move(c)).first;
+        }
+        const Compiled &c = hit->second;
+        if (!c.ok) return false;
+        g.con_off = (uint32_t)b.cons.size(); g.con_cnt = (uint32_t)c.cons.size();
+        b.cons.insert(b.cons.end(), c.cons.begin(), c.cons.end());
+        g.ip_off = (uint32_t)b.ips.size(); g.ip_cnt = (uint32_t)c.ips.size();
+        b.ips.insert(b.ips.end(), c.ips.begin(), c.ips.end());
+        if (c.never) g.flags |= PE_G_CONSTRAINT_NEVER;
+        return true;
+    }
+    bool parse_constraints(const std::vector<std::string> &env, Compiled &out) {
         auto alpha = [](unsigned char c) { return c >= 'a' && c <= 'z'; };
         std::vector<pe_constraint> cons; std::vector<pe_ip_constraint> ips; bool never = false;
         for (auto &e : env) {
@@ -739,11 +772,7 @@ struct Scheduler {
             else { never = true; continue; }                                                            // constraint.go:200-203
             cons.push_back({col, value_id(val), (uint32_t)op});
         }
-        g.con_off = (uint32_t)b.cons.size(); g.con_cnt = (uint32_t)cons.size();
-        b.cons.insert(b.cons.end(), cons.begin(), cons.end());
-        g.ip_off = (uint32_t)b.ips.size(); g.ip_cnt = (uint32_t)ips.size();
-        b.ips.insert(b.ips.end(), ips.begin(), ips.end());
-        if (never) g.flags |= PE_G_CONSTRAINT_NEVER;
+        out.cons = std::move(cons); out.ips = std::move(ips); out.never = never;
         return true;
     }
     bool encode_group(const std::vector<TaskP> &tasks, TickBuf &b, bool for_fit = false) {
@@ -900,12 +929,15 @@ struct Scheduler {
 
     bool scheduleRun(std::vector<std::vector<TaskP>> &all_groups, std::map<std::string, Decision> &decisions) {
         if (all_groups.empty()) return true;
+        const auto tp0 = std::chrono::steady_clock::now();
+        auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
         TickBuf b;
         std::vector<std::vector<TaskP>> groups;
         for (auto &g : all_groups) {
-            TickBuf probe = b;                      // (an encoder that gives up half-way must leave no side arrays behind)
+            const TickBuf::Mark m = b.mark();       // (copying the buffer per group, as round 1 did, is quadratic in the tick)
             fatal.clear();
-            if (encode_group(g, probe)) { b = std::move(probe); groups.push_back(g); continue; }
+            if (encode_group(g, b)) { groups.push_back(g); continue; }
+            b.rollback(m);
             if (unsupported.empty()) unsupported = fatal;
             noSuitableNode(g, "unsupported by the placement engine: " + fatal, decisions);
         }
@@ -918,12 +950,17 @@ struct Scheduler {
         if (!flush_rows()) { give_back(); return false; }     // after encoding: new label columns / plugin slots force a re-upload
         std::vector<uint32_t> out_node(b.flags.size(), PE_NONE), out_fail(b.groups.size() * PE_NUM_FILTERS, 0);
         pe_tick tk = b.view();
+        host_encode_ms += since(tp0);
+        const auto tp1 = std::chrono::steady_clock::now();
         if (!check(pe_schedule(eng, &tk, out_node.data(), out_fail.data()), "pe_schedule")) { give_back(); return false; }
+        host_engine_ms += since(tp1);
+        const auto tp2 = std::chrono::steady_clock::now();
         for (size_t gi = 0; gi < groups.size(); gi++) {
             std::vector<TaskP> left;
             apply_group(groups[gi], &out_node[b.groups[gi].task_off], left, decisions);
             if (!left.empty()) noSuitableNode(left, explain(&out_fail[gi * PE_NUM_FILTERS]), decisions);
         }
+        host_apply_ms += since(tp2);
         return true;
     }
 
@@ -1056,6 +1093,7 @@ struct Scheduler {
     }
     // tick, scheduler.go:429-488
     bool tick(const std::set<std::string> &failCommit, std::map<std::string, Decision> &decisions) {
+        host_encode_ms = host_engine_ms = host_apply_ms = 0;
         recycle_service_ids();
         std::map<std::pair<std::string, uint64_t>, std::vector<TaskP>> bySpec;
         std::vector<TaskP> oneOff;
@@ -1146,6 +1184,12 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         bool ok = op == "tick" ? S.tick(strset(ev.at("fail_commit")), ds) : S.processPreassignedTasks(strset(ev.at("fail_commit")), ds);
         if (!ok) { out.set("error", mj::Value::string(S.fatal)); return out; }
         out.set("decisions", decisions_json(ds));
+        if (op == "tick") {      // where the host time of the tick went (encode groups / engine call / apply decisions)
+            mj::Value hm = mj::Value::object();
+            hm.set("encode", mj::Value::integer((int64_t)(S.host_encode_ms * 1000))); hm.set("engine", mj::Value::integer((int64_t)(S.host_engine_ms * 1000)));
+            hm.set("apply", mj::Value::integer((int64_t)(S.host_apply_ms * 1000)));
+            out.set("host_us", hm);
+        }
         if (!S.unsupported.empty()) out.set("unsupported", mj::Value::string(S.unsupported));   // those tasks stayed pending
     } else if (op == "snapshot" || op == "device_check") {
         if (!S.flush_rows()) { out.set("error", mj::Value::string(S.fatal)); return out; }
