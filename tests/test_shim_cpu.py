@@ -36,7 +36,7 @@ def test_known_answer_through_shim(name, fn):
         fn(make_shim)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(24))
 def test_random_event_stream_flat_vs_object(seed):
     rng = random.Random(seed)
     n_nodes, n_services = rng.randint(5, 60), rng.randint(2, 8)
