@@ -36,3 +36,40 @@ class OracleEngine(FlatABI):
 
     def __init__(self, node_capacity: int = 0):
         super().__init__(build_flat(), "ope_", node_capacity=node_capacity)
+
+
+def build_volumes() -> str:
+    return _make("liboracle_volumes.so")
+
+
+class VolumesOracle:
+    """JSON-op driver of oracle/volumes_oracle.cpp (volumeSet / IsInTopology / VolumesFilter restatement)."""
+
+    def __init__(self):
+        import ctypes as C
+        import json
+        self._json = json
+        self.lib = C.CDLL(build_volumes())
+        self.lib.vo_create.restype = C.c_void_p
+        self.lib.vo_apply.restype = C.c_void_p
+        self.lib.vo_apply.argtypes = [C.c_void_p, C.c_char_p]
+        self.lib.vo_free.argtypes = [C.c_void_p]
+        self.lib.vo_destroy.argtypes = [C.c_void_p]
+        self.h = self.lib.vo_create()
+        self._C = C
+
+    def __call__(self, **ev):
+        p = self.lib.vo_apply(self.h, self._json.dumps(ev).encode())
+        try:
+            out = self._json.loads(self._C.string_at(p).decode())
+        finally:
+            self.lib.vo_free(p)
+        if "error" in out and out["error"] and ev.get("op") != "choose":
+            raise RuntimeError(out["error"])
+        return out
+
+    def __del__(self):
+        try:
+            self.lib.vo_destroy(self.h)
+        except Exception:
+            pass
