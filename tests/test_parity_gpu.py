@@ -233,3 +233,14 @@ def test_cfg3_many_nodes_touched_bitmap_in_global_memory():
         R.compare_results(t, a, b, "cfg3-450k-nodes")
     st = gpu.stats()
     assert st["scan_launches"] > 0 and st["fast_path"] > 0
+
+
+def test_cfg3_more_nodes_than_the_placement_steps_shared_bitmap_holds():
+    # more than 18432 bitmap words (~590k nodes): k_place keeps no copy of the touched bitmap in shared memory and asks the
+    # chunk's set of taken nodes for every candidate (the BM = false instantiation of its resolve phase)
+    w = W.cfg3("oneoff", n_nodes=620_000, n_tasks=2500, n_services=25)
+    gpu, cpu, res = run_both(w.nodes, w.tick, w.n_nodes)
+    for t, a, b in res:
+        R.compare_results(t, a, b, "cfg3-620k-nodes")
+    st = gpu.stats()
+    assert st["scan_launches"] > 0 and st["place_tasks"] > 0
