@@ -1,7 +1,8 @@
 """Rank plumbing for the N>1 benchmark arm (one process per GPU, launched by torchrun).
 
-The placement path's own collectives (NCCL all-gathers of the per-chunk scan results of a
-node-sharded engine group) live inside libplacement.so; what crosses
+The placement path's own collectives (per batch two small NCCL all-gathers and one all-reduce of the merged
+class member lists of a node-sharded engine group) and the split of the node axis over
+the ranks live inside libplacement.so; what crosses
 ranks HERE is the timing reduction the bench contract asks for: MAX over ranks of the device
 time, SUM over ranks of the work done (the ranks of a group hold replicas of the same
 decisions, so bench.py lets only rank 0 contribute work)."""
@@ -27,13 +28,3 @@ def reduce_step(times, counts, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     return t.tolist(), c.tolist()
-
-
-def shard_range(n_items: int, rank: int, world: int, align: int = 1):
-    """Contiguous [lo, hi) range of `n_items` owned by `rank` (node-index sharding),
-    boundaries aligned to `align` items (scan tiles)."""
-    per = -(-n_items // world)
-    per = -(-per // align) * align
-    lo = min(n_items, rank * per)
-    hi = min(n_items, lo + per)
-    return lo, hi

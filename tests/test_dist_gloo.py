@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from swarmkit_b200.dist import reduce_step, shard_range
+from swarmkit_b200.dist import reduce_step
 
 
 def _free_port():
@@ -40,19 +40,6 @@ def test_reduce_step_world2():
         assert p.exitcode == 0
     for _, t, c in res:
         assert t == [11.0, 5.0] and c == [300.0]      # MAX of times, SUM of work
-
-
-def test_shard_range_covers_everything_once():
-    for n, world, align in ((100_000, 8, 1024), (1_000_000, 8, 2048), (5, 2, 1), (4096, 3, 1024)):
-        seen = 0
-        prev_hi = 0
-        for r in range(world):
-            lo, hi = shard_range(n, r, world, align)
-            assert lo == prev_hi or lo == hi == n
-            assert lo % align == 0 or lo == n
-            seen += hi - lo
-            prev_hi = hi
-        assert seen == n and prev_hi == n
 
 
 def _id_worker(rank, world, port, out):
