@@ -26,8 +26,11 @@
 //     createOrUpdateNode, processPreassignedTasks, tick, taskFitNode,
 //     scheduleTaskGroup, scheduleNTasksOnSubtree, scheduleNTasksOnNodes,
 //     noSuitableNode, buildNodeSet}           manager/scheduler/scheduler.go:68-990
-// Out of scope: VolumesFilter / volumeSet (CSI); a task with
-// cluster mounts is scheduled as if the filter were disabled.
+//   volumeSet, IsInTopology, VolumesFilter      manager/scheduler/{volumes.go:45-327,
+//                                             topology.go:22-47, filter.go:388-447}
+//     (unit-level twin with the reference's tables: oracle/volumes_oracle.cpp; here
+//     they are wired into the scheduler as scheduler.go:68-125,205-217,350-366,
+//     398-487,646-690,844-924 wire them)
 //
 // Driver protocol: so_create() / so_apply(handle, json) -> json / so_free().
 #include <algorithm>
@@ -70,12 +73,25 @@ struct EngineDescription {
     std::map<std::string, std::string> Labels;
     std::vector<PluginDescription> Plugins;
 };
+struct Topology { bool present = false; std::map<std::string, std::string> Segments; };   // *api.Topology
+struct NodeCSIInfo { std::string PluginName, NodeID; Topology AccessibleTopology; };
 struct NodeDescription {
     std::string Hostname;
     bool has_platform = false; Platform platform;
     bool has_resources = false; Resources resources;
     bool has_engine = false; EngineDescription engine;
+    std::vector<NodeCSIInfo> CSIInfo;
 };
+enum { VolumeScopeSingleNode = 0, VolumeScopeMultiNode = 1 };
+enum { VolumeSharingNone = 0, VolumeSharingReadOnly = 1, VolumeSharingOneWriter = 2, VolumeSharingAll = 3 };
+enum { VolumeAvailabilityActive = 0, VolumeAvailabilityPause = 1, VolumeAvailabilityDrain = 2 };
+struct Volume {
+    std::string ID, Name, Group, Driver;          // Spec.Annotations.Name, Spec.Group, Spec.Driver.Name
+    int Availability = VolumeAvailabilityActive, Scope = VolumeScopeSingleNode, Sharing = VolumeSharingNone;
+    bool has_info = false; std::string VolumeID;  // VolumeInfo, VolumeInfo.VolumeID
+    std::vector<std::map<std::string, std::string>> AccessibleTopology;
+};
+struct VolumeAttachment { std::string ID, Source, Target; };
 struct Node {
     std::string ID;
     bool has_description = false; NodeDescription Description;
@@ -86,7 +102,7 @@ struct Node {
     uint64_t version = 0;  // Meta.Version.Index
 };
 struct PortConfig { int protocol = ProtocolTCP; uint32_t PublishedPort = 0; int publish_mode = PublishModeIngress; };
-struct Mount { int type = MountTypeBind; bool has_driver = false; std::string driver_name; };
+struct Mount { int type = MountTypeBind; bool has_driver = false; std::string driver_name; std::string Source, Target; bool ReadOnly = false; };
 struct Placement {
     std::vector<std::string> Constraints;
     std::vector<std::string> Preferences;  // spread descriptors
@@ -107,6 +123,7 @@ struct Task {
     std::vector<Net> Networks;
     bool has_endpoint = false; std::vector<PortConfig> Ports;
     std::vector<GenericResource> AssignedGenericResources;
+    std::vector<VolumeAttachment> Volumes;
 };
 }  // namespace api
 
@@ -678,6 +695,123 @@ struct MaxReplicasFilter : Filter {  // filter.go:364-386
     std::string Explain(int) override { return "max replicas per node limit exceed"; }
 };
 
+// volumeSet, volumes.go:45-327; IsInTopology, topology.go:22-47.  Canonicalisation: the volumes of a group are visited in
+// ascending volume ID (the reference ranges over a Go map, volumes.go:233).
+struct VolumeSet {
+    struct Usage { std::string nodeID; bool readOnly = false; };
+    struct Info { api::Volume volume; std::map<std::string, Usage> tasks; std::map<std::string, int> nodes; };
+    std::map<std::string, Info> volumes;
+    std::map<std::string, std::set<std::string>> byGroup;
+    std::map<std::string, std::string> byName;
+
+    static bool IsInTopology(const api::Topology &top, const std::vector<std::map<std::string, std::string>> &accessible) {
+        if (!top.present || accessible.empty()) return true;
+        for (auto &topology : accessible) {
+            bool all = true;
+            for (auto &kv : topology) {
+                auto f = top.Segments.find(kv.first);
+                if ((f == top.Segments.end() ? std::string() : f->second) != kv.second) { all = false; break; }
+            }
+            if (all) return true;
+        }
+        return false;
+    }
+    void addOrUpdateVolume(const api::Volume &v) {                       // :61-81 (an update does not replace the stored spec: :69-70)
+        if (!volumes.count(v.ID)) { Info i; i.volume = v; volumes[v.ID] = i; }
+        byGroup[v.Group].insert(v.ID);
+        byName[v.Name] = v.ID;
+    }
+    void removeVolume(const std::string &id) {                           // :83-96
+        auto it = volumes.find(id);
+        if (it == volumes.end()) return;
+        byGroup[it->second.volume.Group].erase(id);
+        byName.erase(it->second.volume.Name);
+        volumes.erase(it);
+    }
+    void reserveVolume(const std::string &vid, const std::string &taskID, const std::string &nodeID, bool readOnly) {   // :150-160
+        auto it = volumes.find(vid);
+        if (it == volumes.end()) return;
+        it->second.tasks[taskID] = Usage{nodeID, readOnly};
+        it->second.nodes[nodeID] += 1;
+    }
+    void releaseVolume(const std::string &vid, const std::string &taskID) {                                           // :162-184
+        auto it = volumes.find(vid);
+        if (it == volumes.end()) return;
+        auto u = it->second.tasks.find(taskID);
+        if (u == it->second.tasks.end()) return;
+        int &c = it->second.nodes[u->second.nodeID];
+        if (c > 0) c -= 1;
+        it->second.tasks.erase(u);
+    }
+    bool checkVolume(const std::string &id, const NodeInfo &info, bool readOnly) const {                              // :257-318
+        auto it = volumes.find(id);
+        if (it == volumes.end()) return false;
+        const Info &vi = it->second;
+        if (vi.volume.Availability != api::VolumeAvailabilityActive) return false;
+        api::Topology top;
+        if (info.Node->has_description)
+            for (auto &c : info.Node->Description.CSIInfo) if (c.PluginName == vi.volume.Driver) { top = c.AccessibleTopology; break; }
+        if (vi.volume.Scope == api::VolumeScopeSingleNode)
+            for (auto &kv : vi.tasks) if (kv.second.nodeID != info.Node->ID) return false;
+        switch (vi.volume.Sharing) {
+            case api::VolumeSharingNone: if (!vi.tasks.empty()) return false; break;
+            case api::VolumeSharingOneWriter: { bool writer = false; for (auto &kv : vi.tasks) writer |= !kv.second.readOnly; if (!readOnly && writer) return false; break; }
+            case api::VolumeSharingReadOnly: if (!readOnly) return false; break;
+            default: break;
+        }
+        return IsInTopology(top, vi.volume.has_info ? vi.volume.AccessibleTopology : std::vector<std::map<std::string, std::string>>());
+    }
+    std::string isVolumeAvailableOnNode(const api::Mount &mount, const NodeInfo &node) const {                        // :223-255
+        const std::string &source = mount.Source;
+        if (source.compare(0, 6, "group:") == 0) {
+            auto g = byGroup.find(source.substr(6));
+            if (g == byGroup.end()) return "";
+            for (auto &id : g->second) if (checkVolume(id, node, mount.ReadOnly)) return id;
+            return "";
+        }
+        auto n = byName.find(source);
+        if (n == byName.end() || !checkVolume(n->second, node, mount.ReadOnly)) return "";
+        return n->second;
+    }
+    // chooseTaskVolumes, :98-136 (what it reserves while choosing is released again before it returns)
+    bool chooseTaskVolumes(const api::Task &task, const NodeInfo &node, std::vector<api::VolumeAttachment> &out, std::string &err) {
+        std::vector<api::VolumeAttachment> chosen;
+        bool ok = true;
+        if (task.has_container)
+            for (auto &m : task.Mounts) {
+                if (m.type != api::MountTypeCluster) continue;
+                std::string cand = isVolumeAvailableOnNode(m, node);
+                if (cand.empty()) { err = "cannot find volume to satisfy mount with source " + m.Source; ok = false; break; }
+                reserveVolume(cand, task.ID, node.Node->ID, m.ReadOnly);
+                chosen.push_back({cand, m.Source, m.Target});
+            }
+        for (auto &a : chosen) releaseVolume(a.ID, task.ID);
+        if (ok) out = chosen; else out.clear();
+        return ok;
+    }
+    void reserveTaskVolumes(const api::Task &task) {                                                                  // :138-148
+        for (auto &va : task.Volumes)
+            for (auto &m : task.Mounts)
+                if (m.Source == va.Source && m.Target == va.Target) reserveVolume(va.ID, task.ID, task.NodeID, m.ReadOnly);
+    }
+};
+struct VolumesFilter : Filter {  // filter.go:388-447 (appended to the pipeline at scheduler.go:132)
+    const VolumeSet *vs = nullptr;
+    std::vector<api::Mount> requestedVolumes;
+    bool SetTask(const api::Task &t) override {
+        requestedVolumes.clear();
+        if (!vs || !t.has_container) return false;
+        bool hasCSI = false;
+        for (auto &m : t.Mounts) if (m.type == api::MountTypeCluster) { hasCSI = true; requestedVolumes.push_back(m); }
+        return hasCSI;
+    }
+    bool Check(const NodeInfo &n) override {       // true as soon as ONE requested mount can be met (:432-440)
+        for (auto &m : requestedVolumes) if (vs->isVolumeAvailableOnNode(m, n) != "") return true;
+        return false;
+    }
+    std::string Explain(int nodes) override { return plural(nodes, "cannot fulfill requested CSI volume mounts on 1 node", "cannot fulfill requested CSI volume mounts on %d nodes"); }
+};
+
 // Pipeline, pipeline.go:38-103
 struct Pipeline {
     struct Entry { std::unique_ptr<Filter> f; bool enabled = false; int failureCount = 0; };
@@ -687,6 +821,7 @@ struct Pipeline {
         add(new ReadyFilter()); add(new ResourceFilter()); add(new PluginFilter()); add(new ConstraintFilter());
         add(new PlatformFilter()); add(new HostPortFilter()); add(new MaxReplicasFilter());
     }
+    void AddFilter(Filter *f) { Entry e; e.f.reset(f); checklist.push_back(std::move(e)); }   // pipeline.go:70-72
     bool Process(const NodeInfo &n) {
         for (auto &e : checklist)
             if (e.enabled && !e.f->Check(n)) { e.failureCount++; return false; }
@@ -695,7 +830,7 @@ struct Pipeline {
     }
     void SetTask(const api::Task &t) { for (auto &e : checklist) { e.enabled = e.f->SetTask(t); e.failureCount = 0; } }
     std::string Explain() {
-        // sort.Sort(sort.Reverse(byFailures)) on 7 entries = insertion sort: stable, most failures first
+        // sort.Sort(sort.Reverse(byFailures)) on 8 entries (< 12) = insertion sort: stable, most failures first
         std::vector<const Entry *> s;
         for (auto &e : checklist) s.push_back(&e);
         for (size_t i = 1; i < s.size(); i++)
@@ -727,7 +862,10 @@ struct Scheduler {
     std::map<std::string, NodeInfo> nodeSet;  // canonical node order = ascending ID
     std::map<std::string, std::pair<bool, uint64_t>> services;  // store view: id -> (has SpecVersion, index)
     Pipeline pipeline;
+    VolumeSet volumes;
     int64_t now = 0;
+    Scheduler() { VolumesFilter *vf = new VolumesFilter(); vf->vs = &volumes; pipeline.AddFilter(vf); }   // scheduler.go:126-134
+    Scheduler(const Scheduler &) = delete;
 
     // canonical total order: nodeLess (scheduler.go:708-735) + node ID
     static bool lessWithTie(const NodeLess &nodeLess, const NodeInfo &a, const NodeInfo &b) {
@@ -739,7 +877,9 @@ struct Scheduler {
     void enqueue(const TaskP &t) { unassignedTasks[t->ID] = t; }
 
     // setupTasksList + buildNodeSet, scheduler.go:68-125,973-990
-    void setup(const std::vector<NodeP> &nodes, const std::vector<TaskP> &tasks) {
+    void setup(const std::vector<NodeP> &nodes, const std::vector<TaskP> &tasks, const std::vector<api::Volume> &vols = {}) {
+        // only volumes that have been created with their plugin, i.e. carry a VolumeID (scheduler.go:75-81)
+        for (auto &v : vols) if (v.has_info && v.VolumeID != "") volumes.addOrUpdateVolume(v);
         std::map<std::string, std::vector<TaskP>> tasksByNode;
         for (auto &t : tasks) {
             if (t->state < api::TaskStatePending || t->state > api::TaskStateRunning) continue;
@@ -747,6 +887,7 @@ struct Scheduler {
             allTasks[t->ID] = t;
             if (t->NodeID == "") { enqueue(t); continue; }
             if (t->state == api::TaskStatePending) { preassignedTasks.insert(t->ID); pendingPreassignedTasks[t->ID] = t; continue; }
+            volumes.reserveTaskVolumes(*t);          // track the volumes in use by the task (scheduler.go:115-116)
             tasksByNode[t->NodeID].push_back(t);
         }
         for (auto &n : nodes) {
@@ -755,6 +896,8 @@ struct Scheduler {
             nodeSet[n->ID] = newNodeInfo(n, tasksByNode[n->ID], r, now);
         }
     }
+    // EventUpdateVolume, scheduler.go:205-217 (there is no create case: a volume is usable once its plugin created it)
+    void updateVolume(const api::Volume &v) { if (v.has_info && v.VolumeID != "") volumes.addOrUpdateVolume(v); }
     // createTask, scheduler.go:254-281
     void createTask(const TaskP &t) {
         if (t->state < api::TaskStatePending || t->state > api::TaskStateRunning) return;
@@ -767,6 +910,7 @@ struct Scheduler {
     // deleteTask, scheduler.go:350-366
     void deleteTask(const api::Task &t) {
         allTasks.erase(t.ID); preassignedTasks.erase(t.ID); pendingPreassignedTasks.erase(t.ID);
+        for (auto &va : t.Volumes) volumes.releaseVolume(va.ID, t.ID);      // the task's volume reservations, if any (:355-358)
         auto it = nodeSet.find(t.NodeID);
         if (it != nodeSet.end()) it->second.removeTask(t);
     }
@@ -881,8 +1025,13 @@ struct Scheduler {
             TaskP t = taskGroup[taskID];
             if (decisions.count(taskID)) continue;
             NodeInfo &node = nodes[nodeIter % nodeCount];
+            // the volume attachments of the task on this node (:857-867; an error is only logged there)
+            std::vector<api::VolumeAttachment> attachments; std::string verr;
+            volumes.chooseTaskVolumes(*t, node, attachments, verr);
             TaskP newT(new api::Task(*t));
+            newT->Volumes = attachments;
             newT->NodeID = node.Node->ID;
+            volumes.reserveTaskVolumes(*newT);
             newT->state = api::TaskStateAssigned; newT->Err = ""; newT->Message = "scheduler assigned task to node";
             allTasks[t->ID] = newT;
             auto ns = nodeSet.find(node.Node->ID);
@@ -988,6 +1137,10 @@ struct Scheduler {
         TaskP newT(new api::Task(*t));
         pipeline.SetTask(*t);
         if (!pipeline.Process(it->second)) { newT->Err = pipeline.Explain(); allTasks[t->ID] = newT; return newT; }
+        // :664-675: the attachments are chosen here (and NOT reserved: the reference does not call reserveTaskVolumes on this path)
+        std::vector<api::VolumeAttachment> attachments; std::string verr;
+        if (!volumes.chooseTaskVolumes(*t, it->second, attachments, verr)) { newT->Err = verr; allTasks[t->ID] = newT; return newT; }
+        newT->Volumes = attachments;
         newT->state = api::TaskStateAssigned; newT->Err = ""; newT->Message = "scheduler confirmed task can run on preassigned node";
         allTasks[t->ID] = newT;
         it->second.addTask(newT);
@@ -1009,6 +1162,7 @@ struct Scheduler {
                 allTasks[d.old_->ID] = d.old_;
                 auto it = nodeSet.find(d.new_->NodeID);
                 if (it != nodeSet.end()) it->second.removeTask(*d.new_);
+                for (auto &va : d.new_->Volumes) volumes.releaseVolume(va.ID, d.new_->ID);       // :422-424
             } else if (d.new_->state == api::TaskStateAssigned) pendingPreassignedTasks.erase(d.old_->ID);
         }
         return decisions;
@@ -1034,6 +1188,7 @@ struct Scheduler {
             allTasks[d.old_->ID] = d.old_;
             auto it = nodeSet.find(d.new_->NodeID);
             if (it != nodeSet.end()) it->second.removeTask(*d.new_);
+            for (auto &va : d.new_->Volumes) volumes.releaseVolume(va.ID, d.new_->ID);           // release the volumes we tried to use (:480-483)
             enqueue(d.old_);
         }
         return decisions;
@@ -1093,6 +1248,12 @@ static NodeP node(const mj::Value &v) {
         n->Description.Hostname = d.at("hostname").as_str();
         if (!d.at("platform").is_null()) { n->Description.has_platform = true; n->Description.platform.OS = d.at("platform").at("os").as_str(); n->Description.platform.Architecture = d.at("platform").at("arch").as_str(); }
         if (!d.at("resources").is_null()) { n->Description.has_resources = true; n->Description.resources = resources(d.at("resources")); }
+        if (d.find("csi_info") && !d.at("csi_info").is_null())
+            for (auto &c : d.at("csi_info").a) {
+                api::NodeCSIInfo ci; ci.PluginName = c.at("plugin").as_str(); ci.NodeID = c.at("node_id").as_str();
+                if (!c.at("topology").is_null()) { ci.AccessibleTopology.present = true; ci.AccessibleTopology.Segments = strmap(c.at("topology")); }
+                n->Description.CSIInfo.push_back(ci);
+            }
         const mj::Value &e = d.at("engine");
         if (!e.is_null()) {
             n->Description.has_engine = true;
@@ -1127,6 +1288,7 @@ static TaskP task(const mj::Value &v) {
         for (auto &m : ct.at("mounts").a) {
             api::Mount mm; mm.type = enum_of(m.at("type"), {{"BIND", 0}, {"VOLUME", 1}, {"TMPFS", 2}, {"NPIPE", 3}, {"CLUSTER", 4}}, 0);
             if (!m.at("driver").is_null()) { mm.has_driver = true; mm.driver_name = m.at("driver").as_str(); }
+            mm.Source = m.at("source").as_str(); mm.Target = m.at("target").as_str(); mm.ReadOnly = !m.at("read_only").is_null() && m.at("read_only").as_bool();
             t->Mounts.push_back(mm);
         }
     }
@@ -1146,7 +1308,22 @@ static TaskP task(const mj::Value &v) {
         if (g.find("named")) { gr.named = true; gr.value = g.at("named").as_str(); } else gr.amount = g.at("value").as_int();
         t->AssignedGenericResources.push_back(gr);
     }
+    if (v.find("volumes") && !v.at("volumes").is_null())
+        for (auto &a : v.at("volumes").a) t->Volumes.push_back({a.at("id").as_str(), a.at("source").as_str(), a.at("target").as_str()});
     return t;
+}
+static api::Volume volume(const mj::Value &v) {
+    api::Volume x;
+    x.ID = v.at("id").as_str(); x.Name = v.at("name").as_str(); x.Group = v.at("group").as_str(); x.Driver = v.at("driver").as_str();
+    x.Availability = enum_of(v.at("availability"), {{"ACTIVE", 0}, {"PAUSE", 1}, {"DRAIN", 2}}, 0);
+    x.Scope = enum_of(v.at("scope"), {{"SINGLE_NODE", 0}, {"MULTI_NODE", 1}}, 0);
+    x.Sharing = enum_of(v.at("sharing"), {{"NONE", 0}, {"READ_ONLY", 1}, {"ONE_WRITER", 2}, {"ALL", 3}}, 0);
+    if (!v.at("volume_info").is_null()) {
+        x.has_info = true; x.VolumeID = v.at("volume_info").at("volume_id").as_str();
+        if (!v.at("volume_info").at("accessible_topology").is_null())
+            for (auto &t : v.at("volume_info").at("accessible_topology").a) x.AccessibleTopology.push_back(strmap(t));
+    }
+    return x;
 }
 static mj::Value decisions_json(const std::map<std::string, Decision> &ds) {
     mj::Value arr = mj::Value::array();
@@ -1164,6 +1341,12 @@ static mj::Value decisions_json(const std::map<std::string, Decision> &ds) {
             ag.push(e);
         }
         d.set("assigned_generic", ag);
+        mj::Value vols = mj::Value::array();
+        for (auto &a : kv.second.new_->Volumes) {
+            mj::Value e = mj::Value::object(); e.set("id", mj::Value::string(a.ID)); e.set("source", mj::Value::string(a.Source)); e.set("target", mj::Value::string(a.Target));
+            vols.push(e);
+        }
+        if (!kv.second.new_->Volumes.empty()) d.set("volumes", vols);      // (only tasks with cluster mounts carry the key)
         arr.push(d);
     }
     return arr;
@@ -1179,7 +1362,21 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         for (auto &n : ev.at("nodes").a) nodes.push_back(node(n));
         for (auto &t : ev.at("tasks").a) tasks.push_back(task(t));
         for (auto &s : ev.at("services").a) S.services[s.at("id").as_str()] = {!s.at("spec_version").is_null(), (uint64_t)s.at("spec_version").as_int()};
-        S.setup(nodes, tasks);
+        std::vector<api::Volume> vols;
+        if (ev.find("volumes") && !ev.at("volumes").is_null()) for (auto &v : ev.at("volumes").a) vols.push_back(volume(v));
+        S.setup(nodes, tasks, vols);
+    } else if (op == "update_volume") {
+        S.updateVolume(volume(ev.at("volume")));
+    } else if (op == "delete_volume") {
+        S.volumes.removeVolume(ev.at("id").as_str());
+    } else if (op == "volume_usage") {
+        mj::Value vols = mj::Value::object();
+        for (auto &kv : S.volumes.volumes) {
+            mj::Value tasks = mj::Value::object();
+            for (auto &t : kv.second.tasks) { mj::Value u = mj::Value::object(); u.set("node", mj::Value::string(t.second.nodeID)); u.set("read_only", mj::Value::boolean(t.second.readOnly)); tasks.set(t.first, u); }
+            vols.set(kv.first, tasks);
+        }
+        out.set("volumes", vols);
     } else if (op == "set_service") {
         S.services[ev.at("id").as_str()] = {!ev.at("spec_version").is_null(), (uint64_t)ev.at("spec_version").as_int()};
     } else if (op == "delete_service") {

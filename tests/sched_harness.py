@@ -59,8 +59,21 @@ def node(id, state="READY", availability="ACTIVE", labels=None, role="WORKER", a
             "status": {"state": state, "addr": addr}, "description": description}
 
 
-def description(hostname="", platform=None, resources=None, engine=None):
-    return {"hostname": hostname, "platform": platform, "resources": resources, "engine": engine}
+def description(hostname="", platform=None, resources=None, engine=None, csi_info=None):
+    d = {"hostname": hostname, "platform": platform, "resources": resources, "engine": engine}
+    if csi_info is not None:
+        d["csi_info"] = [{"plugin": c[0], "node_id": c[1], "topology": (c[2] if len(c) > 2 else None)} for c in csi_info]
+    return d
+
+
+def csi_volume(vid, name, group="", driver="", scope="SINGLE_NODE", sharing="NONE", volume_id="", accessible_topology=None, availability="ACTIVE"):
+    """An api.Volume as the scheduler sees it (volume_id "" = not created with its plugin yet)."""
+    return {"id": vid, "name": name, "group": group, "driver": driver, "scope": scope, "sharing": sharing, "availability": availability,
+            "volume_info": {"volume_id": volume_id, "accessible_topology": accessible_topology} if volume_id is not None else None}
+
+
+def cluster_mount(source, target, read_only=False):
+    return {"type": "CLUSTER", "driver": None, "source": source, "target": target, "read_only": read_only}
 
 
 def resources(nano_cpus=0, memory_bytes=0, generic=()):
@@ -101,7 +114,7 @@ def host_port(port, protocol="TCP"):
 class Cluster:
     """A dict 'store' plus one scheduler under test."""
 
-    def __init__(self, sched: JsonScheduler, nodes=(), tasks=(), services=(), now_ns=10**18):
+    def __init__(self, sched: JsonScheduler, nodes=(), tasks=(), services=(), now_ns=10**18, volumes=()):
         self.s = sched
         self.now = now_ns
         self.nodes = {n["id"]: copy.deepcopy(n) for n in nodes}
@@ -110,8 +123,11 @@ class Cluster:
         for sv in services:
             sid, ver = (sv, None) if isinstance(sv, str) else sv
             self.services[sid] = ver
-        self.s.apply({"op": "init", "now_ns": self.now, "nodes": list(self.nodes.values()), "tasks": list(self.tasks.values()),
-                      "services": [{"id": k, "spec_version": v} for k, v in self.services.items()]})
+        ev = {"op": "init", "now_ns": self.now, "nodes": list(self.nodes.values()), "tasks": list(self.tasks.values()),
+              "services": [{"id": k, "spec_version": v} for k, v in self.services.items()]}
+        if volumes:
+            ev["volumes"] = list(volumes)
+        self.s.apply(ev)
 
     # --- store mutations (each echoes the event the MemoryStore would publish)
     def set_service(self, sid, spec_version=None):
@@ -129,6 +145,9 @@ class Cluster:
     def delete_node(self, nid):
         self.nodes.pop(nid, None)
         self.s.apply({"op": "delete_node", "id": nid})
+
+    def update_volume(self, v):
+        self.s.apply({"op": "update_volume", "volume": v})
 
     def create_task(self, t):
         self.tasks[t["id"]] = copy.deepcopy(t)
@@ -159,6 +178,8 @@ class Cluster:
             t["node_id"] = d["node_id"]
             t["status"] = {"state": d["state"], "err": d["err"], "message": d["message"]}
             t["assigned_generic"] = d.get("assigned_generic", [])
+            if d.get("volumes"):
+                t["volumes"] = d["volumes"]
             self.tasks[t["id"]] = t
             out[d["id"]] = d
         for d in decisions:
