@@ -20,8 +20,9 @@
 //   NodeInfo::addTask/removeTask/taskFailed/countRecentFailures   nodeinfo.go:66-221
 //   Encoder (rows, group descriptors) <- the SetTask methods      filter.go:35,60,118,224,259,328,369
 //
-// Not supported by the engine yet (reported as an error, never silently
-// scheduled on the CPU): CSI cluster volumes (VolumesFilter) -- SURVEY 8(f) "next".
+// CSI cluster volumes (VolumesFilter): the volume bookkeeping and the filter stay on the host as in the
+// reference; the shim hands the engine the node set the filter allows (scheduleVolumeGroup).  Groups whose volume
+// availability changes with every placement are answered as unsupported (never scheduled on the CPU).
 // Placement.Preferences (scheduler.go:772-825): the branch walk is host code here as in the
 // reference; the engine supplies the tree's leaves and fills one leaf per group.
 #include <algorithm>
@@ -49,7 +50,9 @@ enum { NodeReady = 2, AvailActive = 0, PublishHost = 1, MountVolume = 1, MountCl
 struct Generic { bool named = false; std::string kind, value; int64_t amount = 0; };
 struct Resources { int64_t cpu = 0, mem = 0; std::vector<Generic> generic; };
 struct Plugin { std::string type, name; };
+struct CsiInfo { std::string plugin, node_id; bool has_top = false; std::map<std::string, std::string> segments; };   // api.NodeCSIInfo
 struct Node {
+    std::vector<CsiInfo> csi;
     std::string id, hostname, addr, os, arch;
     bool has_desc = false, has_platform = false, has_resources = false, has_engine = false, has_labels = false, has_elabels = false;
     Resources resources;
@@ -59,7 +62,15 @@ struct Node {
     uint64_t version = 0;
 };
 struct Port { int protocol = 0; uint32_t port = 0; int mode = 0; };
-struct Mount { int type = 0; bool has_driver = false; std::string driver; };
+struct Mount { int type = 0; bool has_driver = false; std::string driver; std::string source, target; bool read_only = false; };
+struct Attachment { std::string id, source, target; };                     // api.VolumeAttachment
+struct Volume {                                                             // api.Volume, what the scheduler reads of it
+    std::string id, name, group, driver;
+    int availability = 0, scope = 0, sharing = 0;                           // ACTIVE / SINGLE_NODE / NONE = 0
+    bool has_info = false; std::string volume_id;
+    std::vector<std::map<std::string, std::string>> accessible;
+};
+enum { VolScopeSingle = 0, VolScopeMulti = 1, VolShareNone = 0, VolShareReadOnly = 1, VolShareOneWriter = 2, VolShareAll = 3 };
 struct Task {
     std::string id, service, node_id, err, message;
     int desired = TaskStateRunning, state = 0;
@@ -74,6 +85,7 @@ struct Task {
     std::vector<std::pair<bool, std::string>> networks;
     bool has_endpoint = false; std::vector<Port> ports;
     std::vector<Generic> assigned;
+    std::vector<Attachment> volumes;
     mj::Value raw;  // echoed back in snapshots of decisions
 };
 using TaskP = std::shared_ptr<Task>;
@@ -137,8 +149,27 @@ static NodeP parse_node(const mj::Value &v) {
             if (!e.at("labels").is_null()) { n->has_elabels = true; for (auto &kv : e.at("labels").o) n->elabels[kv.first] = kv.second.as_str(); }
             for (auto &p : e.at("plugins").a) n->plugins.push_back({p.at("type").as_str(), p.at("name").as_str()});
         }
+        if (!d.at("csi_info").is_null())
+            for (auto &c : d.at("csi_info").a) {
+                CsiInfo ci; ci.plugin = c.at("plugin").as_str(); ci.node_id = c.at("node_id").as_str();
+                if (!c.at("topology").is_null()) { ci.has_top = true; for (auto &kv : c.at("topology").o) ci.segments[kv.first] = kv.second.as_str(); }
+                n->csi.push_back(ci);
+            }
     }
     return n;
+}
+static Volume parse_volume(const mj::Value &v) {
+    Volume x;
+    x.id = v.at("id").as_str(); x.name = v.at("name").as_str(); x.group = v.at("group").as_str(); x.driver = v.at("driver").as_str();
+    x.availability = enum_of(v.at("availability"), {{"ACTIVE", 0}, {"PAUSE", 1}, {"DRAIN", 2}}, 0);
+    x.scope = enum_of(v.at("scope"), {{"SINGLE_NODE", 0}, {"MULTI_NODE", 1}}, 0);
+    x.sharing = enum_of(v.at("sharing"), {{"NONE", 0}, {"READ_ONLY", 1}, {"ONE_WRITER", 2}, {"ALL", 3}}, 0);
+    if (!v.at("volume_info").is_null()) {
+        x.has_info = true; x.volume_id = v.at("volume_info").at("volume_id").as_str();
+        if (!v.at("volume_info").at("accessible_topology").is_null())
+            for (auto &t : v.at("volume_info").at("accessible_topology").a) { std::map<std::string, std::string> sg; for (auto &kv : t.o) sg[kv.first] = kv.second.as_str(); x.accessible.push_back(sg); }
+    }
+    return x;
 }
 static TaskP parse_task(const mj::Value &v) {
     TaskP t(new Task());
@@ -162,6 +193,7 @@ static TaskP parse_task(const mj::Value &v) {
         for (auto &m : spec.at("container").at("mounts").a) {
             Mount mm; mm.type = enum_of(m.at("type"), {{"BIND", 0}, {"VOLUME", 1}, {"TMPFS", 2}, {"NPIPE", 3}, {"CLUSTER", 4}}, 0);
             if (!m.at("driver").is_null()) { mm.has_driver = true; mm.driver = m.at("driver").as_str(); }
+            mm.source = m.at("source").as_str(); mm.target = m.at("target").as_str(); mm.read_only = !m.at("read_only").is_null() && m.at("read_only").as_bool();
             t->mounts.push_back(mm);
         }
     }
@@ -181,6 +213,7 @@ static TaskP parse_task(const mj::Value &v) {
         if (g.find("named")) { x.named = true; x.value = g.at("named").as_str(); } else x.amount = g.at("value").as_int();
         t->assigned.push_back(x);
     }
+    if (!v.at("volumes").is_null()) for (auto &a : v.at("volumes").a) t->volumes.push_back({a.at("id").as_str(), a.at("source").as_str(), a.at("target").as_str()});
     return t;
 }
 
@@ -387,6 +420,119 @@ static Addr parse_ip(const std::string &s) {  // net.ParseIP
 }
 
 // ------------------------------------------------------------------ the scheduler
+// ------------------------------------------------------------------ CSI cluster volumes (host side)
+// The reference keeps this bookkeeping in the scheduler and evaluates VolumesFilter per node (filter.go:388-447,
+// volumes.go:45-327, topology.go:22-47); it "stays on host" here too: the shim decides which nodes can satisfy a task's
+// cluster mounts and hands the engine that node set (see Scheduler::scheduleVolumeGroup).
+struct VolumeBook {
+    struct Use { std::string node; bool read_only = false; };
+    struct Entry { Volume v; std::map<std::string, Use> tasks; std::map<std::string, int> nodes; };
+    std::map<std::string, Entry> vols;
+    std::map<std::string, std::set<std::string>> by_group;     // a group's volumes in ascending ID (canonical order)
+    std::map<std::string, std::string> by_name;
+
+    void addOrUpdate(const Volume &v) {                         // volumes.go:61-81 (an update keeps the stored spec: :69-70)
+        if (!vols.count(v.id)) { Entry e; e.v = v; vols[v.id] = e; }
+        by_group[v.group].insert(v.id);
+        by_name[v.name] = v.id;
+    }
+    void remove(const std::string &id) {                        // :83-96
+        auto it = vols.find(id);
+        if (it == vols.end()) return;
+        by_group[it->second.v.group].erase(id);
+        by_name.erase(it->second.v.name);
+        vols.erase(it);
+    }
+    void reserve(const std::string &vid, const std::string &task, const std::string &node, bool ro) {   // :150-160
+        auto it = vols.find(vid);
+        if (it == vols.end()) return;
+        it->second.tasks[task] = Use{node, ro};
+        it->second.nodes[node]++;
+    }
+    void release(const std::string &vid, const std::string &task) {                                     // :162-184
+        auto it = vols.find(vid);
+        if (it == vols.end()) return;
+        auto u = it->second.tasks.find(task);
+        if (u == it->second.tasks.end()) return;
+        int &c = it->second.nodes[u->second.node];
+        if (c > 0) c--;
+        it->second.tasks.erase(u);
+    }
+    static bool inTopology(const CsiInfo *ci, const std::vector<std::map<std::string, std::string>> &accessible) {   // topology.go:22-47
+        if (!ci || !ci->has_top || accessible.empty()) return true;
+        for (auto &want : accessible) {
+            bool all = true;
+            for (auto &kv : want) { auto f = ci->segments.find(kv.first); if (f == ci->segments.end() ? !kv.second.empty() : f->second != kv.second) { all = false; break; } }
+            if (all) return true;
+        }
+        return false;
+    }
+    bool check(const std::string &id, const Node &n, bool ro) const {                                    // :257-318
+        auto it = vols.find(id);
+        if (it == vols.end()) return false;
+        const Entry &e = it->second;
+        if (e.v.availability != 0) return false;
+        const CsiInfo *ci = nullptr;
+        if (n.has_desc) for (auto &c : n.csi) if (c.plugin == e.v.driver) { ci = &c; break; }
+        if (e.v.scope == VolScopeSingle) for (auto &u : e.tasks) if (u.second.node != n.id) return false;
+        if (e.v.sharing == VolShareNone && !e.tasks.empty()) return false;
+        if (e.v.sharing == VolShareReadOnly && !ro) return false;
+        if (e.v.sharing == VolShareOneWriter && !ro) for (auto &u : e.tasks) if (!u.second.read_only) return false;
+        return inTopology(ci, e.v.has_info ? e.v.accessible : std::vector<std::map<std::string, std::string>>());
+    }
+    std::string availableOn(const Mount &m, const Node &n) const {                                        // :223-255
+        if (m.source.compare(0, 6, "group:") == 0) {
+            auto g = by_group.find(m.source.substr(6));
+            if (g == by_group.end()) return "";
+            for (auto &id : g->second) if (check(id, n, m.read_only)) return id;
+            return "";
+        }
+        auto f = by_name.find(m.source);
+        return (f != by_name.end() && check(f->second, n, m.read_only)) ? f->second : std::string();
+    }
+    // VolumesFilter.Check, filter.go:432-440: ONE satisfiable cluster mount is enough
+    bool filterCheck(const Task &t, const Node &n) const {
+        for (auto &m : t.mounts) if (m.type == MountCluster && !availableOn(m, n).empty()) return true;
+        return false;
+    }
+    // chooseTaskVolumes, :98-136
+    bool choose(const Task &t, const Node &n, std::vector<Attachment> &out, std::string &err) {
+        std::vector<Attachment> got; bool ok = true;
+        if (t.has_container)
+            for (auto &m : t.mounts) {
+                if (m.type != MountCluster) continue;
+                std::string id = availableOn(m, n);
+                if (id.empty()) { err = "cannot find volume to satisfy mount with source " + m.source; ok = false; break; }
+                reserve(id, t.id, n.id, m.read_only);
+                got.push_back({id, m.source, m.target});
+            }
+        for (auto &a : got) release(a.id, t.id);
+        out = ok ? got : std::vector<Attachment>();
+        return ok;
+    }
+    void reserveTask(const Task &t) {                                                                     // :138-148
+        for (auto &va : t.volumes) for (auto &m : t.mounts) if (m.source == va.source && m.target == va.target) reserve(va.id, t.id, t.node_id, m.read_only);
+    }
+    // Can a placement of one task of this spec change what VolumesFilter answers for the next task of the same group?
+    // (scope SINGLE_NODE pins the volume to the first node that uses it; sharing NONE / ONE_WRITER count users.)
+    bool staticFor(const Task &t) const {
+        for (auto &m : t.mounts) {
+            if (m.type != MountCluster) continue;
+            std::vector<std::string> ids;
+            if (m.source.compare(0, 6, "group:") == 0) { auto g = by_group.find(m.source.substr(6)); if (g != by_group.end()) ids.assign(g->second.begin(), g->second.end()); }
+            else { auto f = by_name.find(m.source); if (f != by_name.end()) ids.push_back(f->second); }
+            for (auto &id : ids) {
+                const Volume &v = vols.at(id).v;
+                if (v.scope != VolScopeMulti) return false;
+                if (v.sharing == VolShareNone) return false;
+                if (v.sharing == VolShareOneWriter && !m.read_only) return false;
+            }
+        }
+        return true;
+    }
+};
+static bool has_cluster_mounts(const Task &t) { if (!t.has_container) return false; for (auto &m : t.mounts) if (m.type == MountCluster) return true; return false; }
+
 struct Decision { TaskP old_, new_; };
 
 struct Scheduler {
@@ -397,6 +543,11 @@ struct Scheduler {
     std::set<std::string> preassignedTasks;
     std::map<std::string, NodeInfo> nodeSet;   // ordered: row index = rank of the node ID
     std::map<std::string, std::pair<bool, uint64_t>> services;
+    VolumeBook volumes;                  // CSI cluster volumes: host-side bookkeeping (volumes.go)
+    uint32_t vol_col = PE_NONE;          // attribute column that names the node set of a group with cluster mounts
+    uint32_t vol_gen = 0;                // value of that column for the set marked last
+    std::vector<uint32_t> vol_marked;    // the rows that carry it
+    std::map<std::string, uint32_t> vol_mark_of;   // node ID -> its current mark (0 = none), written into the row by encode_row
     int64_t now = 0;
 
     // ---- dictionaries (exact interning)
@@ -534,6 +685,7 @@ struct Scheduler {
             auto f = m->find(key);
             if (f != m->end()) attr(lc.second, f->second);
         }
+        if (vol_col != PE_NONE) { auto vm = vol_mark_of.find(n.id); if (vm != vol_mark_of.end() && vm->second) b.attrs.push_back({vol_col, vm->second}); }
         for (auto &pc : pref_cols) {                                                               // nodeset.go:69-82
             const std::string key = pc.first.substr(2);
             const std::map<std::string, std::string> *m = nullptr;
@@ -603,7 +755,8 @@ struct Scheduler {
 
     // ---- store events -----------------------------------------------------------
     void enqueue(const TaskP &t) { unassignedTasks[t->id] = t; }
-    void setupTasksList(const std::vector<NodeP> &nodes, const std::vector<TaskP> &tasks) {   // scheduler.go:68-125 + buildNodeSet :973-990
+    void setupTasksList(const std::vector<NodeP> &nodes, const std::vector<TaskP> &tasks, const std::vector<Volume> &vols = {}) {   // scheduler.go:68-125 + buildNodeSet :973-990
+        for (auto &v : vols) if (v.has_info && !v.volume_id.empty()) volumes.addOrUpdate(v);      // only volumes created with their plugin (:75-81)
         std::map<std::string, std::vector<TaskP>> byNode;
         for (auto &t : tasks) {
             if (t->state < TaskStatePending || t->state > TaskStateRunning) continue;
@@ -611,6 +764,7 @@ struct Scheduler {
             allTasks[t->id] = t;
             if (t->node_id.empty()) { enqueue(t); continue; }
             if (t->state == TaskStatePending) { preassignedTasks.insert(t->id); pendingPreassignedTasks[t->id] = t; continue; }
+            volumes.reserveTask(*t);                 // track the volumes in use by the task (:115-116)
             byNode[t->node_id].push_back(t);
         }
         for (auto &n : nodes) {
@@ -629,8 +783,10 @@ struct Scheduler {
         auto it = nodeSet.find(t->node_id);
         if (it != nodeSet.end() && it->second.addTask(t)) touch(t->node_id);
     }
+    void updateVolume(const Volume &v) { if (v.has_info && !v.volume_id.empty()) volumes.addOrUpdate(v); }   // scheduler.go:205-217
     void deleteTask(const Task &t) {   // scheduler.go:350-366
         allTasks.erase(t.id); preassignedTasks.erase(t.id); pendingPreassignedTasks.erase(t.id);
+        for (auto &va : t.volumes) volumes.release(va.id, t.id);
         auto it = nodeSet.find(t.node_id);
         if (it != nodeSet.end() && it->second.removeTask(t)) touch(t.node_id);
     }
@@ -780,7 +936,7 @@ struct Scheduler {
         // (placement preferences: the caller cuts the group into leaf visits, see schedulePreferenceGroup; taskFitNode
         // checks one named node and preferences play no part there, scheduler.go:646-690)
         (void)for_fit;
-        for (auto &m : t.mounts) if (m.type == MountCluster) { fatal = "CSI cluster volumes are not supported by the placement engine (task " + t.id + ")"; return false; }
+        // (cluster mounts: VolumesFilter is evaluated by the shim, which hands the engine the node set: scheduleVolumeGroup)
         pe_group g{};
         g.log_plugin = PE_NONE;
         g.svc_id = svc_id(t.service);
@@ -915,10 +1071,11 @@ struct Scheduler {
         for (size_t gi = 0; gi < all_groups.size(); gi++) {
             auto &g = all_groups[gi];
             const bool pref = !g.empty() && !preference_levels(*g[0]).empty();
-            if (!pref) { run.push_back(g); continue; }
+            const bool csi = !g.empty() && has_cluster_mounts(*g[0]);
+            if (!pref && !csi) { run.push_back(g); continue; }
             bool ok = scheduleRun(run, decisions);
             run.clear();
-            if (ok) ok = schedulePreferenceGroup(g, decisions);
+            if (ok) ok = csi ? scheduleVolumeGroup(g, decisions) : schedulePreferenceGroup(g, decisions);
             if (!ok) {
                 for (size_t r = gi + 1; r < all_groups.size(); r++) for (auto &t : all_groups[r]) enqueue(t);
                 return false;
@@ -961,6 +1118,109 @@ struct Scheduler {
             if (!left.empty()) noSuitableNode(left, explain(&out_fail[gi * PE_NUM_FILTERS]), decisions);
         }
         host_apply_ms += since(tp2);
+        return true;
+    }
+
+    // ---- cluster (CSI) volumes: VolumesFilter (filter.go:388-447) is evaluated HERE, on the host, against the shim's own
+    // volume bookkeeping; the engine gets the answer as the group's node set -- the rows marked in one attribute column,
+    // named by a leaf term (the mechanism of the preference leaves) -- and does everything else.  Exact for a single task and
+    // for groups whose volumes cannot change availability while the group is placed (VolumeBook::staticFor); a group whose
+    // volume availability moves with every placement (scope SINGLE_NODE, sharing NONE / ONE_WRITER writers) is answered
+    // like an unsupported group: the reference re-evaluates the filter inside its fill loop (scheduler.go:912-920) and the
+    // engine cannot.  Left-over single tasks get the reference's exact explanation (every node's first failing filter).
+    void mark_volume_nodes(const std::vector<std::string> &ids) {
+        if (vol_col == PE_NONE) { vol_col = next_label_col++; layout_dirty = true; }
+        vol_gen++;                                    // marks of older sets never equal the new value: nothing to clear
+        for (auto &id : ids) { vol_mark_of[id] = vol_gen; touch(id); }
+    }
+    // first failing filter of one task of this spec on each of `ids` (taskFitNode's question, in batches of pe_fit requests);
+    // a node that passes every device filter is counted for VolumesFilter and the reservation pe_fit made on it is taken back
+    bool count_excluded(const TaskP &t, const std::vector<std::string> &ids, std::vector<uint32_t> &cnt) {
+        const size_t kBatch = 4096;
+        for (size_t lo = 0; lo < ids.size(); lo += kBatch) {
+            const size_t n = std::min(kBatch, ids.size() - lo);
+            TickBuf b;
+            std::vector<TaskP> one{t};
+            for (size_t i = 0; i < n; i++) if (!encode_group(one, b, true)) return false;
+            if (!flush_rows()) return false;
+            std::vector<uint32_t> idx(n);
+            for (size_t i = 0; i < n; i++) idx[i] = node_index(ids[lo + i]);
+            std::vector<uint8_t> ok(n, 0); std::vector<uint32_t> fail(n * PE_NUM_FILTERS, 0);
+            pe_tick tk = b.view();
+            if (!check(pe_fit(eng, &tk, idx.data(), ok.data(), fail.data()), "pe_fit")) return false;
+            for (size_t i = 0; i < n; i++) {
+                if (ok[i] == 1) { cnt[PE_F_VOLUMES]++; touch(ids[lo + i]); }
+                else if (ok[i] == 0) for (int f = 0; f < PE_NUM_FILTERS; f++) cnt[f] += fail[i * PE_NUM_FILTERS + f];
+            }
+        }
+        return true;
+    }
+    bool scheduleVolumeGroup(std::vector<TaskP> &grp, std::map<std::string, Decision> &decisions) {
+        const Task &t = *grp[0];
+        auto refuse = [&](const std::string &why) {
+            if (unsupported.empty()) unsupported = why;
+            noSuitableNode(grp, "unsupported by the placement engine: " + why, decisions);
+            return true;
+        };
+        if (!preference_levels(t).empty()) return refuse("placement preferences together with cluster volumes (task " + t.id + ")");
+        if (grp.size() > 1 && !volumes.staticFor(t)) return refuse("the availability of the group's cluster volumes changes with every placement (task " + t.id + ")");
+        auto give_back = [&](const std::vector<TaskP> &ts) { for (auto &x : ts) enqueue(x); layout_dirty = true; };
+        std::vector<std::string> allowed, excluded;
+        for (auto &kv : nodeSet) (volumes.filterCheck(t, *kv.second.node) ? allowed : excluded).push_back(kv.first);
+        mark_volume_nodes(allowed);
+        TickBuf b;
+        fatal.clear();
+        if (!encode_group(grp, b)) { std::string why = fatal; fatal.clear(); return refuse(why); }
+        const TickBuf::Mark after_group = b.mark();
+        auto restrict_to = [&](uint32_t gen) {
+            b.rollback(after_group);
+            pe_group &g = b.groups.back();
+            if (g.con_cnt == 0) g.con_off = (uint32_t)b.cons.size();
+            b.cons.resize(g.con_off + g.con_cnt);
+            b.cons.push_back({vol_col, gen, 0});
+            g.leaf_cnt = 1;
+        };
+        restrict_to(vol_gen);
+        if (!flush_rows()) { give_back(grp); return false; }
+        std::vector<uint32_t> out_node(grp.size(), PE_NONE), out_fail(PE_NUM_FILTERS, 0);
+        pe_tick tk = b.view();
+        if (!check(pe_schedule(eng, &tk, out_node.data(), out_fail.data()), "pe_schedule")) { give_back(grp); return false; }
+        std::vector<TaskP> left;
+        std::string first_placed;
+        for (size_t i = 0; i < grp.size(); i++) {
+            const TaskP &ti = grp[i];
+            const uint32_t idx = out_node[i];
+            if (idx == PE_NONE || idx >= idx_to_id.size()) { left.push_back(ti); continue; }
+            NodeInfo &ni = nodeSet[idx_to_id[idx]];
+            if (first_placed.empty()) first_placed = idx_to_id[idx];
+            TaskP nt(new Task(*ti));                                                  // scheduler.go:857-880
+            std::string verr;
+            volumes.choose(*ti, *ni.node, nt->volumes, verr);                         // (a failure is only logged there)
+            nt->node_id = idx_to_id[idx];
+            volumes.reserveTask(*nt);
+            nt->state = TaskStateAssigned; nt->err.clear(); nt->message = "scheduler assigned task to node";
+            allTasks[ti->id] = nt;
+            ni.addTask(nt);
+            decisions[ti->id] = {ti, nt};
+        }
+        if (left.empty()) return true;
+        std::vector<uint32_t> cnt(out_fail);
+        // The reference ran its pipeline over EVERY node while it built the tree (scheduler.go:722-731), in this model's
+        // canonical order (ascending node ID); a node outside the volume set fails there on its first failing filter -- a
+        // device filter if one fails, VolumesFilter (the last of the pipeline) otherwise -- and is in no heap afterwards.
+        // Process() clears the counters whenever a node passes (pipeline.go:55-68), so what Explain() reports is what failed
+        // AFTER the last pass: with no task placed nothing ever passed and every excluded node counts; with one task placed
+        // exactly one node passed the tree building (two would both be in the heap, and the second, untouched, would have
+        // passed its re-check and taken the second task) and the excluded nodes after it count; with two or more placed a
+        // re-check inside the fill loop passed (scheduler.go:912-920) and wiped everything from the tree building -- the
+        // engine's counters, which cover the nodes of the set, are complete.  The group placed nothing on excluded nodes,
+        // so asking about them now gives the answer of that moment.
+        const size_t placed = grp.size() - left.size();
+        std::vector<std::string> counted;
+        if (placed == 0) counted = excluded;
+        else if (placed == 1) for (auto &id : excluded) if (id > first_placed) counted.push_back(id);
+        if (!counted.empty() && !count_excluded(left[0], counted, cnt)) { give_back(left); return false; }
+        noSuitableNode(left, explain(cnt.data()), decisions);
         return true;
     }
 
@@ -1089,6 +1349,7 @@ struct Scheduler {
         allTasks[d.old_->id] = d.old_;
         auto it = nodeSet.find(d.new_->node_id);
         if (it != nodeSet.end() && it->second.removeTask(*d.new_)) touch(d.new_->node_id);
+        for (auto &va : d.new_->volumes) volumes.release(va.id, d.new_->id);        // release the volumes we tried to use (:422-424, :480-483)
         if (requeue) enqueue(d.old_);
     }
     // tick, scheduler.go:429-488
@@ -1111,9 +1372,10 @@ struct Scheduler {
         return true;
     }
     // processPreassignedTasks + taskFitNode, scheduler.go:398-426,646-690
-    bool processPreassignedTasks(const std::set<std::string> &failCommit, std::map<std::string, Decision> &decisions) {
-        std::vector<TaskP> pend;
-        for (auto &kv : pendingPreassignedTasks) if (nodeSet.count(kv.second->node_id)) pend.push_back(kv.second);
+    // one pe_fit call for a run of preassigned tasks.  vol_fail: the (single) task of the run has cluster mounts that this
+    // node cannot satisfy -- VolumesFilter is the LAST filter of the pipeline, so a device filter that fails still names
+    // the error; if none does, the engine's reservation is taken back (the row is uploaded again from NodeInfo).
+    bool fit_run(const std::vector<TaskP> &pend, bool vol_fail, std::map<std::string, Decision> &decisions) {
         if (pend.empty()) return true;
         TickBuf b;
         for (auto &t : pend) { std::vector<TaskP> one{t}; if (!encode_group(one, b, true)) return false; }
@@ -1127,11 +1389,39 @@ struct Scheduler {
             if (ok[i] == 2) continue;
             TaskP nt(new Task(*t));
             if (ok[i] == 0) { nt->err = explain(&fail[i * PE_NUM_FILTERS]); allTasks[t->id] = nt; decisions[t->id] = {t, nt}; continue; }
+            if (vol_fail) {
+                touch(t->node_id);
+                nt->err = "cannot fulfill requested CSI volume mounts on 1 node";                 // filter.go:442-447
+                allTasks[t->id] = nt; decisions[t->id] = {t, nt};
+                continue;
+            }
+            if (has_cluster_mounts(*t)) {      // scheduler.go:664-675: the attachments are chosen (and, on this path, not reserved)
+                std::string verr;
+                if (!volumes.choose(*t, *nodeSet[t->node_id].node, nt->volumes, verr)) { touch(t->node_id); nt->err = verr; allTasks[t->id] = nt; decisions[t->id] = {t, nt}; continue; }
+            }
             nt->state = TaskStateAssigned; nt->err.clear(); nt->message = "scheduler confirmed task can run on preassigned node";
             allTasks[t->id] = nt;
             nodeSet[t->node_id].addTask(nt);
             decisions[t->id] = {t, nt};
         }
+        return true;
+    }
+    bool processPreassignedTasks(const std::set<std::string> &failCommit, std::map<std::string, Decision> &decisions) {
+        std::vector<TaskP> run;
+        for (auto &kv : pendingPreassignedTasks) {
+            const TaskP &t = kv.second;
+            auto ns = nodeSet.find(t->node_id);
+            if (ns == nodeSet.end()) continue;
+            if (has_cluster_mounts(*t) && !volumes.filterCheck(*t, *ns->second.node)) {
+                // (its own call, so that a reservation the engine makes for it is undone before the next task is checked)
+                if (!fit_run(run, false, decisions)) return false;
+                run.clear();
+                if (!fit_run({t}, true, decisions)) return false;
+                continue;
+            }
+            run.push_back(t);
+        }
+        if (!fit_run(run, false, decisions)) return false;
         for (auto &kv : decisions) {
             if (failCommit.count(kv.first)) { if (kv.second.new_->state == TaskStateAssigned) rollback(kv.second, false); }
             else if (kv.second.new_->state == TaskStateAssigned) pendingPreassignedTasks.erase(kv.first);
@@ -1152,6 +1442,11 @@ static mj::Value decisions_json(const std::map<std::string, Decision> &ds) {
         d.set("err", mj::Value::string(kv.second.new_->err));
         d.set("message", mj::Value::string(kv.second.new_->message));
         d.set("assigned_generic", generic_json(kv.second.new_->assigned));
+        if (!kv.second.new_->volumes.empty()) {      // (only tasks with cluster mounts carry the key)
+            mj::Value vols = mj::Value::array();
+            for (auto &a : kv.second.new_->volumes) { mj::Value e = mj::Value::object(); e.set("id", mj::Value::string(a.id)); e.set("source", mj::Value::string(a.source)); e.set("target", mj::Value::string(a.target)); vols.push(e); }
+            d.set("volumes", vols);
+        }
         arr.push(d);
     }
     return arr;
@@ -1167,7 +1462,19 @@ static mj::Value apply(Scheduler &S, const mj::Value &ev) {
         for (auto &t : ev.at("tasks").a) tasks.push_back(parse_task(t));
         for (auto &s : ev.at("services").a) S.services[s.at("id").as_str()] = {!s.at("spec_version").is_null(), (uint64_t)s.at("spec_version").as_int()};
         if (!ev.at("svc_recycle_at").is_null()) S.svc_recycle_min = S.svc_recycle_at = (size_t)ev.at("svc_recycle_at").as_int();
-        S.setupTasksList(nodes, tasks);
+        std::vector<Volume> vols;
+        if (!ev.at("volumes").is_null()) for (auto &v : ev.at("volumes").a) vols.push_back(parse_volume(v));
+        S.setupTasksList(nodes, tasks, vols);
+    } else if (op == "update_volume") S.updateVolume(parse_volume(ev.at("volume")));
+    else if (op == "delete_volume") S.volumes.remove(ev.at("id").as_str());
+    else if (op == "volume_usage") {
+        mj::Value vols = mj::Value::object();
+        for (auto &kv : S.volumes.vols) {
+            mj::Value tasks = mj::Value::object();
+            for (auto &t : kv.second.tasks) { mj::Value u = mj::Value::object(); u.set("node", mj::Value::string(t.second.node)); u.set("read_only", mj::Value::boolean(t.second.read_only)); tasks.set(t.first, u); }
+            vols.set(kv.first, tasks);
+        }
+        out.set("volumes", vols);
     } else if (op == "set_service") S.services[ev.at("id").as_str()] = {!ev.at("spec_version").is_null(), (uint64_t)ev.at("spec_version").as_int()};
     else if (op == "delete_service") S.services.erase(ev.at("id").as_str());
     else if (op == "create_node" || op == "update_node") S.createOrUpdateNode(parse_node(ev.at("node")));
