@@ -15,7 +15,9 @@
 // tests (there is no Go toolchain in its build image): same dictionaries, same encoders, same call sequence.  Function
 // by function:   encodeRow <- Scheduler::encode_row   encodeGroup <- encode_group   compileConstraints <-
 // compile_constraints   scheduleTickGPU <- scheduleTaskGroups/scheduleRun   schedulePreferenceGroup/fillLeaf/
-// scheduleNTasksOnSubtreeGPU <- the functions of the same names   taskFitNodeGPU <- processPreassignedTasks.
+// scheduleNTasksOnSubtreeGPU <- the functions of the same names   taskFitNodeGPU <- processPreassignedTasks / fit_run
+// scheduleVolumeGroup / countExcluded / volumesStaticFor <- scheduleVolumeGroup / count_excluded / VolumeBook::staticFor
+// (the volume bookkeeping itself is the reference's own volumeSet, volumes.go).
 package scheduler
 
 /*
@@ -65,6 +67,10 @@ type gpuEngine struct {
 	index     map[string]uint32   // node ID -> row index
 	dirty     map[string]struct{} // rows whose NodeInfo changed since the last upload
 	layout    bool                // membership or a dictionary grew: every row is uploaded again
+	// CSI cluster volumes: the node set VolumesFilter allows for the group being scheduled, as one attribute column
+	volCol    uint32            // C.PE_NONE until the first group with cluster mounts
+	volGen    uint32            // the value that marks the current set (older marks never equal it: nothing to clear)
+	volMarkOf map[string]uint32 // node ID -> its mark
 }
 
 func mustNewGPUEngine() *gpuEngine {
@@ -77,7 +83,8 @@ func mustNewGPUEngine() *gpuEngine {
 	return &gpuEngine{h: h, values: map[string]uint32{"": 0}, exact: map[string]uint32{"": 0}, services: map[string]uint32{},
 		kinds: map[string]uint32{}, labelCols: map[string]uint32{}, prefCols: map[string]uint32{}, prefIDs: map[string]uint32{"": 0},
 		prefStr: []string{""}, ports: map[hostPortSpec]uint32{}, plugins: map[[2]string]uint32{}, nextCol: C.PE_ATTR_FIRST_LABEL,
-		index: map[string]uint32{}, dirty: map[string]struct{}{}, layout: true, recycleAt: 4096}
+		index: map[string]uint32{}, dirty: map[string]struct{}{}, layout: true, recycleAt: 4096, volCol: C.PE_NONE,
+		volMarkOf: map[string]uint32{}}
 }
 
 // serviceID names the engine's per-service counter column.  The engine never frees a column, so the ids of services that
@@ -270,6 +277,9 @@ func (e *gpuEngine) encodeRow(idx uint32, ni *NodeInfo, b *rowBatch) {
 		if v, ok := label(key); ok {
 			attr(col, e.prefID(v))
 		}
+	}
+	if m := e.volMarkOf[n.ID]; e.volCol != C.PE_NONE && m != 0 {
+		attr(e.volCol, m)
 	}
 	r.attr_cnt = C.uint32_t(len(b.attrs)) - r.attr_off
 	r.gen_off = C.uint32_t(len(b.gens))
@@ -509,13 +519,7 @@ func (s *Scheduler) encodeGroup(tasks []*api.Task, b *tickBuf, now time.Time) er
 		}
 		b.flags = append(b.flags, f)
 	}
-	if c := t.Spec.GetContainer(); c != nil {
-		for _, m := range c.Mounts {
-			if m.Type == api.MountTypeCluster {
-				return errors.New("CSI cluster volumes are evaluated by VolumesFilter on the host: not handed to the placement engine")
-			}
-		}
-	}
+	// (cluster mounts: VolumesFilter is evaluated by the shim, which hands the engine the node set: scheduleVolumeGroup)
 	res := taskReservations(t.Spec) // nodeinfo.go:156-161
 	g.cpu_res, g.mem_res = C.int64_t(res.NanoCPUs), C.int64_t(res.MemoryBytes)
 	g.gen_off = C.uint32_t(len(b.gens))
@@ -623,7 +627,13 @@ func sortedTasks(group map[string]*api.Task) []*api.Task {
 // assign is the body of scheduleNTasksOnNodes that stays on the host (scheduler.go:871-893).
 func (s *Scheduler) assign(t *api.Task, nodeID string, group map[string]*api.Task, decisions map[string]schedulingDecision) {
 	newT := *t
+	if hasClusterMounts(t) { // scheduler.go:857-874 (an error is only logged there)
+		if ni, err := s.nodeSet.nodeInfo(nodeID); err == nil {
+			newT.Volumes, _ = s.volumes.chooseTaskVolumes(t, &ni)
+		}
+	}
 	newT.NodeID = nodeID
+	s.volumes.reserveTaskVolumes(&newT)
 	newT.Status = api.TaskStatus{State: api.TaskStateAssigned, Timestamp: ptypes.MustTimestampProto(time.Now()),
 		Message: "scheduler assigned task to node"}
 	s.allTasks[t.ID] = &newT
@@ -636,7 +646,8 @@ func (s *Scheduler) assign(t *api.Task, nodeID string, group map[string]*api.Tas
 
 // scheduleTickGPU replaces the two loops over scheduleTaskGroup: groups in canonical order (ascending (ServiceID,
 // SpecVersion.Index), then one-offs by task ID); maximal runs of groups without placement preferences go to the engine
-// in ONE pe_schedule call, a group with preferences is walked leaf by leaf in between.
+// in ONE pe_schedule call, a group with preferences is walked leaf by leaf in between, a group with cluster mounts is
+// restricted to the nodes VolumesFilter allows.
 func (s *Scheduler) scheduleTickGPU(ctx context.Context, groups []map[string]*api.Task, decisions map[string]schedulingDecision) {
 	now := time.Now() // sampled once per tick (the reference samples it once per group, scheduler.go:706)
 	s.recycleServiceIDs()
@@ -652,6 +663,11 @@ func (s *Scheduler) scheduleTickGPU(ctx context.Context, groups []map[string]*ap
 		for _, t := range g {
 			any = t
 			break
+		}
+		if any != nil && hasClusterMounts(any) {
+			flush()
+			s.scheduleVolumeGroup(ctx, g, decisions, now)
+			continue
 		}
 		if any != nil && len(s.preferenceLevels(any)) != 0 {
 			flush()
@@ -711,6 +727,192 @@ func (s *Scheduler) scheduleRunGPU(ctx context.Context, groups []map[string]*api
 			s.noSuitableNodeWith(ctx, of[gi], decisions, explainCounters(outFail[gi*C.PE_NUM_FILTERS:]))
 		}
 	}
+}
+
+// ---- cluster (CSI) volumes: VolumesFilter (filter.go:388-447) is evaluated HERE against s.volumes; the engine gets the
+// answer as the group's node set -- the rows marked in one attribute column, named by a leaf term -- and does the rest
+// (DESIGN.md 4.7).  Exact for one task and for groups whose volumes cannot change availability while the group is placed.
+
+func hasClusterMounts(t *api.Task) bool {
+	if c := t.Spec.GetContainer(); c != nil {
+		for _, m := range c.Mounts {
+			if m.Type == api.MountTypeCluster {
+				return true
+			}
+		}
+	}
+	return false
+}
+
+// volumesStaticFor: can a placement of one task of this spec change what VolumesFilter answers for the next one?
+// (scope SINGLE_NODE pins the volume to its first node; sharing NONE and ONE_WRITER writers count users: volumes.go:257-318)
+func (s *Scheduler) volumesStaticFor(t *api.Task) bool {
+	for _, m := range t.Spec.GetContainer().Mounts {
+		if m.Type != api.MountTypeCluster {
+			continue
+		}
+		var ids []string
+		if group := strings.TrimPrefix(m.Source, "group:"); group != m.Source {
+			for id := range s.volumes.byGroup[group] {
+				ids = append(ids, id)
+			}
+		} else if id, ok := s.volumes.byName[m.Source]; ok {
+			ids = append(ids, id)
+		}
+		for _, id := range ids {
+			am := s.volumes.volumes[id].volume.Spec.AccessMode
+			if am.Scope != api.VolumeScopeMultiNode || am.Sharing == api.VolumeSharingNone ||
+				(am.Sharing == api.VolumeSharingOneWriter && !m.ReadOnly) {
+				return false
+			}
+		}
+	}
+	return true
+}
+
+func (e *gpuEngine) markVolumeNodes(ids []string) {
+	if e.volCol == C.PE_NONE {
+		e.volCol = e.nextCol // a column of its own, filled for every node on the next upload
+		e.nextCol++
+		e.nodeSetChanged()
+	}
+	e.volGen++
+	for _, id := range ids {
+		e.volMarkOf[id] = e.volGen
+		e.nodeChanged(id)
+	}
+}
+
+// countExcluded: the first failing filter of one task of this spec on each of ids (taskFitNode's question, batched); a node
+// that passes every device filter counts for VolumesFilter, and the reservation pe_fit made on it is taken back.
+func (s *Scheduler) countExcluded(t *api.Task, ids []string, cnt []C.uint32_t, now time.Time) error {
+	const batch = 4096
+	for lo := 0; lo < len(ids); lo += batch {
+		part := ids[lo:min(lo+batch, len(ids))]
+		var b tickBuf
+		idx := make([]C.uint32_t, len(part))
+		for i, id := range part {
+			if err := s.encodeGroup([]*api.Task{t}, &b, now); err != nil {
+				return err
+			}
+			idx[i] = C.uint32_t(s.gpu.index[id])
+		}
+		if err := s.gpu.flushRows(&s.nodeSet); err != nil {
+			return err
+		}
+		ok := make([]C.uint8_t, len(part))
+		fail := make([]C.uint32_t, len(part)*C.PE_NUM_FILTERS)
+		tick := b.view()
+		if rc := C.pe_fit(s.gpu.h, &tick, ptr(idx), ptr(ok), ptr(fail)); rc != C.PE_OK {
+			return s.gpu.err("pe_fit")
+		}
+		for i, id := range part {
+			switch ok[i] {
+			case 1:
+				cnt[C.PE_F_VOLUMES]++
+				s.gpu.nodeChanged(id)
+			case 0:
+				for f := 0; f < C.PE_NUM_FILTERS; f++ {
+					cnt[f] += fail[i*C.PE_NUM_FILTERS+f]
+				}
+			}
+		}
+	}
+	return nil
+}
+
+func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*api.Task, decisions map[string]schedulingDecision, now time.Time) {
+	ts := sortedTasks(group)
+	t := ts[0]
+	refuse := func(why string) {
+		s.noSuitableNodeWith(ctx, group, decisions, "unsupported by the placement engine: "+why)
+	}
+	if len(s.preferenceLevels(t)) != 0 {
+		refuse("placement preferences together with cluster volumes")
+		return
+	}
+	if len(ts) > 1 && !s.volumesStaticFor(t) {
+		refuse("the availability of the group's cluster volumes changes with every placement")
+		return
+	}
+	requeue := func(err error) {
+		log.G(ctx).WithError(err).Error("placement engine")
+		for _, x := range group {
+			s.enqueue(x)
+		}
+		s.gpu.nodeSetChanged()
+	}
+	f := &VolumesFilter{vs: s.volumes}
+	f.SetTask(t)
+	var allowed, excluded []string
+	for _, id := range s.gpu.order { // canonical order: ascending node ID
+		ni, err := s.nodeSet.nodeInfo(id)
+		if err != nil {
+			continue
+		}
+		if f.Check(&ni) {
+			allowed = append(allowed, id)
+		} else {
+			excluded = append(excluded, id)
+		}
+	}
+	s.gpu.markVolumeNodes(allowed)
+	var b tickBuf
+	if err := s.encodeGroup(ts, &b, now); err != nil {
+		refuse(err.Error())
+		return
+	}
+	g := &b.groups[len(b.groups)-1]
+	if g.con_cnt == 0 {
+		g.con_off = C.uint32_t(len(b.cons)) // the leaf term follows the group's constraints
+	}
+	b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(s.gpu.volCol), value: C.uint32_t(s.gpu.volGen)})
+	g.leaf_cnt = 1
+	if err := s.gpu.flushRows(&s.nodeSet); err != nil {
+		requeue(err)
+		return
+	}
+	outNode := make([]C.uint32_t, len(ts))
+	cnt := make([]C.uint32_t, C.PE_NUM_FILTERS)
+	tick := b.view()
+	if rc := C.pe_schedule(s.gpu.h, &tick, ptr(outNode), ptr(cnt)); rc != C.PE_OK {
+		requeue(s.gpu.err("pe_schedule"))
+		return
+	}
+	placed, firstPlaced := 0, ""
+	for i, x := range ts {
+		if idx := uint32(outNode[i]); idx != C.PE_NONE {
+			if placed == 0 {
+				firstPlaced = s.gpu.order[idx]
+			}
+			s.assign(x, s.gpu.order[idx], group, decisions) // chooses and reserves the attachments
+			placed++
+		}
+	}
+	if len(group) == 0 {
+		return
+	}
+	// Explain() reports what failed after the last node that PASSED (pipeline.go:55-68): every excluded node when nothing was
+	// placed; the excluded nodes after the one node that passed when exactly one task was; none when a re-check inside
+	// the fill loop passed (two or more placed).  DESIGN.md 4.7.
+	var counted []string
+	switch placed {
+	case 0:
+		counted = excluded
+	case 1:
+		for _, id := range excluded {
+			if id > firstPlaced {
+				counted = append(counted, id)
+			}
+		}
+	}
+	if len(counted) != 0 {
+		if err := s.countExcluded(t, counted, cnt, now); err != nil {
+			requeue(err)
+			return
+		}
+	}
+	s.noSuitableNodeWith(ctx, group, decisions, explainCounters(cnt))
 }
 
 // ---- placement preferences: nodeSet.tree's branches (nodeset.go:59-101) + scheduleNTasksOnSubtree (scheduler.go:772-825)
@@ -930,6 +1132,28 @@ func (s *Scheduler) taskFitNodeGPU(ctx context.Context, t *api.Task, nodeID stri
 		newT.Status.Err = explainCounters(outFail)
 		s.allTasks[t.ID] = &newT
 		return &newT
+	}
+	if hasClusterMounts(t) {
+		// VolumesFilter is the last filter of the pipeline: it names the error only when every device filter passed; the
+		// reservation pe_fit just made is taken back by uploading the row again from NodeInfo
+		ni, _ := s.nodeSet.nodeInfo(nodeID)
+		f := &VolumesFilter{vs: s.volumes}
+		f.SetTask(t)
+		verr := ""
+		if !f.Check(&ni) {
+			verr = f.Explain(1)
+		} else if attachments, err := s.volumes.chooseTaskVolumes(t, &ni); err != nil { // scheduler.go:664-675
+			verr = err.Error()
+		} else {
+			newT.Volumes = attachments
+		}
+		if verr != "" {
+			s.gpu.nodeChanged(nodeID)
+			newT.Status.Timestamp = ptypes.MustTimestampProto(time.Now())
+			newT.Status.Err = verr
+			s.allTasks[t.ID] = &newT
+			return &newT
+		}
 	}
 	newT.Status = api.TaskStatus{State: api.TaskStateAssigned, Timestamp: ptypes.MustTimestampProto(time.Now()),
 		Message: "scheduler confirmed task can run on preassigned node"}
