@@ -16,7 +16,8 @@
 // by function:   encodeRow <- Scheduler::encode_row   encodeGroup <- encode_group   compileConstraints <-
 // compile_constraints   scheduleTickGPU <- scheduleTaskGroups/scheduleRun   schedulePreferenceGroup/fillLeaf/
 // scheduleNTasksOnSubtreeGPU <- the functions of the same names   taskFitNodeGPU <- processPreassignedTasks / fit_run
-// scheduleVolumeGroup / countExcluded / volumesStaticFor <- scheduleVolumeGroup / count_excluded / VolumeBook::staticFor
+// scheduleVolumeGroup / scheduleVolumeGroupStepwise / fitMany / countExcluded / volumesStaticFor <- scheduleVolumeGroup /
+// scheduleVolumeGroupStepwise / fit_many / count_excluded / VolumeBook::staticFor
 // (the volume bookkeeping itself is the reference's own volumeSet, volumes.go).
 package scheduler
 
@@ -731,7 +732,8 @@ func (s *Scheduler) scheduleRunGPU(ctx context.Context, groups []map[string]*api
 
 // ---- cluster (CSI) volumes: VolumesFilter (filter.go:388-447) is evaluated HERE against s.volumes; the engine gets the
 // answer as the group's node set -- the rows marked in one attribute column, named by a leaf term -- and does the rest
-// (DESIGN.md 4.7).  Exact for one task and for groups whose volumes cannot change availability while the group is placed.
+// (DESIGN.md 4.7): ONE engine group when no placement can change volume availability, the reference's fill loop with one
+// engine question per step otherwise (scheduleVolumeGroupStepwise).
 
 func hasClusterMounts(t *api.Task) bool {
 	if c := t.Spec.GetContainer(); c != nil {
@@ -783,41 +785,268 @@ func (e *gpuEngine) markVolumeNodes(ids []string) {
 	}
 }
 
-// countExcluded: the first failing filter of one task of this spec on each of ids (taskFitNode's question, batched); a node
-// that passes every device filter counts for VolumesFilter, and the reservation pe_fit made on it is taken back.
+// countExcluded: the first failing filter of every node of ids, none of which passes VolumesFilter: a device filter if one
+// fails, VolumesFilter (the last of the pipeline) otherwise.
 func (s *Scheduler) countExcluded(t *api.Task, ids []string, cnt []C.uint32_t, now time.Time) error {
+	ok, fail, err := s.fitMany(t, ids, true, now)
+	if err != nil {
+		return err
+	}
+	for i := range ids {
+		switch ok[i] {
+		case 1:
+			cnt[C.PE_F_VOLUMES]++
+		case 0:
+			for f := 0; f < C.PE_NUM_FILTERS; f++ {
+				cnt[f] += fail[i*C.PE_NUM_FILTERS+f]
+			}
+		}
+	}
+	return nil
+}
+
+// fitMany asks taskFitNode's question for one task of this spec on each of ids (batches of pe_fit requests).  A success
+// RESERVES on the device; with undo the reservations are taken back (the rows are uploaded again before the next call).
+func (s *Scheduler) fitMany(t *api.Task, ids []string, undo bool, now time.Time) (ok []C.uint8_t, fail []C.uint32_t, err error) {
 	const batch = 4096
+	ok, fail = make([]C.uint8_t, len(ids)), make([]C.uint32_t, len(ids)*C.PE_NUM_FILTERS)
 	for lo := 0; lo < len(ids); lo += batch {
 		part := ids[lo:min(lo+batch, len(ids))]
 		var b tickBuf
 		idx := make([]C.uint32_t, len(part))
 		for i, id := range part {
-			if err := s.encodeGroup([]*api.Task{t}, &b, now); err != nil {
-				return err
+			if err = s.encodeGroup([]*api.Task{t}, &b, now); err != nil {
+				return
 			}
 			idx[i] = C.uint32_t(s.gpu.index[id])
 		}
-		if err := s.gpu.flushRows(&s.nodeSet); err != nil {
-			return err
+		if err = s.gpu.flushRows(&s.nodeSet); err != nil {
+			return
 		}
-		ok := make([]C.uint8_t, len(part))
-		fail := make([]C.uint32_t, len(part)*C.PE_NUM_FILTERS)
 		tick := b.view()
-		if rc := C.pe_fit(s.gpu.h, &tick, ptr(idx), ptr(ok), ptr(fail)); rc != C.PE_OK {
-			return s.gpu.err("pe_fit")
+		if rc := C.pe_fit(s.gpu.h, &tick, ptr(idx), &ok[lo], &fail[lo*C.PE_NUM_FILTERS]); rc != C.PE_OK {
+			err = s.gpu.err("pe_fit")
+			return
 		}
-		for i, id := range part {
-			switch ok[i] {
-			case 1:
-				cnt[C.PE_F_VOLUMES]++
-				s.gpu.nodeChanged(id)
-			case 0:
-				for f := 0; f < C.PE_NUM_FILTERS; f++ {
-					cnt[f] += fail[i*C.PE_NUM_FILTERS+f]
+		if undo {
+			for i, id := range part {
+				if ok[lo+i] == 1 {
+					s.gpu.nodeChanged(id)
 				}
 			}
 		}
 	}
+	return
+}
+
+// rankKey is nodeLess (scheduler.go:708-734) plus the canonical tie-break, as a key.
+type rankKey struct {
+	f, s, a int
+	id      string
+}
+
+func (a rankKey) lessNoTie(b rankKey) bool {
+	if a.f != b.f {
+		return a.f < b.f
+	}
+	if a.s != b.s {
+		return a.s < b.s
+	}
+	return a.a < b.a
+}
+func (a rankKey) less(b rankKey) bool {
+	if a.lessNoTie(b) {
+		return true
+	}
+	if b.lessNoTie(a) {
+		return false
+	}
+	return a.id < b.id
+}
+
+// scheduleVolumeGroupStepwise: a group whose volume availability moves with every placement.  The reference re-runs the
+// whole pipeline, VolumesFilter included, on the next node before every further placement (scheduler.go:912-920); this
+// walks that loop and asks the engine one question per step (DESIGN.md 4.7).  s.gpu.markVolumeNodes(allowed) was called.
+func (s *Scheduler) scheduleVolumeGroupStepwise(ctx context.Context, ts []*api.Task, group map[string]*api.Task, allowedIDs, excluded []string,
+	decisions map[string]schedulingDecision, now time.Time) error {
+	e, t, k := s.gpu, ts[0], len(ts)
+	allowed := make(map[string]struct{}, len(allowedIDs))
+	for _, id := range allowedIDs {
+		allowed[id] = struct{}{}
+	}
+	f := &VolumesFilter{vs: s.volumes}
+	cnt := make([]C.uint32_t, C.PE_NUM_FILTERS)
+	// ---- the heap of the k best feasible nodes, in rank order: k one-task groups on the allowed set
+	var cand []string
+	{
+		var b tickBuf
+		if err := s.encodeGroup([]*api.Task{t}, &b, now); err != nil {
+			s.noSuitableNodeWith(ctx, group, decisions, "unsupported by the placement engine: "+err.Error())
+			return nil
+		}
+		g := &b.groups[len(b.groups)-1]
+		if g.con_cnt == 0 {
+			g.con_off = C.uint32_t(len(b.cons))
+		}
+		b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(e.volCol), value: C.uint32_t(e.volGen)})
+		g.leaf_cnt = 1
+		for i := 0; i < k; i++ {
+			if err := e.flushRows(&s.nodeSet); err != nil {
+				return err
+			}
+			var pn C.uint32_t = C.PE_NONE
+			pf := make([]C.uint32_t, C.PE_NUM_FILTERS)
+			tick := b.view()
+			if rc := C.pe_schedule(e.h, &tick, &pn, ptr(pf)); rc != C.PE_OK {
+				return e.err("pe_schedule")
+			}
+			if pn == C.PE_NONE {
+				if i == 0 {
+					cnt = pf
+				}
+				break
+			}
+			id := e.order[pn]
+			cand = append(cand, id)
+			e.volMarkOf[id] = 0 // out of the set; the row upload also takes the reservation back
+			e.nodeChanged(id)
+		}
+	}
+	if len(cand) == 0 {
+		if err := s.countExcluded(t, excluded, cnt, now); err != nil {
+			return err
+		}
+		s.noSuitableNodeWith(ctx, group, decisions, explainCounters(cnt))
+		return nil
+	}
+	key := func(id string) rankKey {
+		ni, _ := s.nodeSet.nodeInfo(id)
+		fl := ni.countRecentFailures(now, t)
+		if fl < maxFailures {
+			fl = 0
+		}
+		return rankKey{fl, ni.ActiveTasksCountByService[t.ServiceID], ni.ActiveTasksCount, id}
+	}
+	firstKey := key(cand[0])
+	m := len(cand)
+	failed := make([]bool, m)
+	treeCountersStand := true
+	it, placed := 0, 0
+	if ok, _, err := s.fitMany(ts[0], cand[:1], false, now); err != nil {
+		return err
+	} else if ok[0] != 1 {
+		return errors.New("placement engine: the best node of a group does not fit its first task")
+	}
+fill:
+	for {
+		nid := cand[it%m]
+		s.assign(ts[placed], nid, group, decisions)
+		placed++
+		if placed == k {
+			return nil
+		}
+		if it+1 < m {
+			if key(cand[(it+1)%m]).lessNoTie(key(nid)) { // first pass: level the nodes
+				it++
+			}
+		} else {
+			it++ // later passes: one task per node
+		}
+		for orig := it; ; {
+			if i := it % m; !failed[i] {
+				ok, fail, err := s.fitMany(ts[placed], cand[i:i+1], false, now)
+				if err != nil {
+					return err
+				}
+				ni, _ := s.nodeSet.nodeInfo(cand[i])
+				f.SetTask(ts[placed])
+				if ok[0] == 1 && f.Check(&ni) {
+					for j := range cnt {
+						cnt[j] = 0 // pipeline.go:64-66
+					}
+					treeCountersStand = false
+					continue fill
+				}
+				if ok[0] == 1 {
+					cnt[C.PE_F_VOLUMES]++
+					e.nodeChanged(cand[i]) // the reservation is taken back
+				} else {
+					for j := range cnt {
+						cnt[j] += fail[j]
+					}
+				}
+				failed[i] = true
+			}
+			it++
+			if it-orig == m {
+				break fill // none of the nodes meets the constraints any more
+			}
+		}
+	}
+	if treeCountersStand {
+		// no re-check passed: the tree building's counters still stand.  Replay its walk (ascending node ID): the pipeline
+		// ran on every node while the heap had room, afterwards only on nodes ranking ahead of the heap's worst
+		// (nodeset.go:103-121); a pass clears the counters.
+		var ids []string
+		for _, id := range e.order {
+			if id != cand[0] {
+				ids = append(ids, id)
+			}
+		}
+		ok, fail, err := s.fitMany(ts[placed], ids, true, now)
+		if err != nil {
+			return err
+		}
+		tree := make([]C.uint32_t, C.PE_NUM_FILTERS)
+		var heap []rankKey // the worst at heap[0]
+		worst := func() int {
+			w := 0
+			for i := range heap {
+				if heap[w].less(heap[i]) {
+					w = i
+				}
+			}
+			return w
+		}
+		j := 0
+		for _, id := range e.order {
+			first := id == cand[0]
+			rk, q := firstKey, 0
+			if !first {
+				rk, q = key(id), j
+				j++
+			}
+			w := -1
+			if len(heap) >= k {
+				if w = worst(); !rk.less(heap[w]) {
+					continue // the pipeline was not run on it
+				}
+			}
+			_, in := allowed[id]
+			if !(first || (ok[q] == 1 && in)) {
+				if ok[q] == 1 {
+					tree[C.PE_F_VOLUMES]++
+				} else if ok[q] == 0 {
+					for x := range tree {
+						tree[x] += fail[q*C.PE_NUM_FILTERS+x]
+					}
+				}
+				continue
+			}
+			for x := range tree {
+				tree[x] = 0
+			}
+			if w >= 0 {
+				heap[w] = rk
+			} else {
+				heap = append(heap, rk)
+			}
+		}
+		for x := range cnt {
+			cnt[x] += tree[x]
+		}
+	}
+	s.noSuitableNodeWith(ctx, group, decisions, explainCounters(cnt))
 	return nil
 }
 
@@ -829,10 +1058,6 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 	}
 	if len(s.preferenceLevels(t)) != 0 {
 		refuse("placement preferences together with cluster volumes")
-		return
-	}
-	if len(ts) > 1 && !s.volumesStaticFor(t) {
-		refuse("the availability of the group's cluster volumes changes with every placement")
 		return
 	}
 	requeue := func(err error) {
@@ -857,6 +1082,12 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 		}
 	}
 	s.gpu.markVolumeNodes(allowed)
+	if len(ts) > 1 && !s.volumesStaticFor(t) {
+		if err := s.scheduleVolumeGroupStepwise(ctx, ts, group, allowed, excluded, decisions, now); err != nil {
+			requeue(err)
+		}
+		return
+	}
 	var b tickBuf
 	if err := s.encodeGroup(ts, &b, now); err != nil {
 		refuse(err.Error())

@@ -22,7 +22,8 @@
 //
 // CSI cluster volumes (VolumesFilter): the volume bookkeeping and the filter stay on the host as in the
 // reference; the shim hands the engine the node set the filter allows (scheduleVolumeGroup).  Groups whose volume
-// availability changes with every placement are answered as unsupported (never scheduled on the CPU).
+// availability changes with every placement walk the reference's fill loop with one engine question per step
+// (scheduleVolumeGroupStepwise); every filter evaluation and every ranking of nodes is the engine's.
 // Placement.Preferences (scheduler.go:772-825): the branch walk is host code here as in the
 // reference; the engine supplies the tree's leaves and fills one leaf per group.
 #include <algorithm>
@@ -294,6 +295,7 @@ static void reclaim(std::vector<Generic> &avail, const std::vector<Generic> &ass
 
 // ------------------------------------------------------------------ NodeInfo (host mirror, nodeinfo.go:28-44)
 static const int64_t kMonitorFailures = 300LL * 1000000000LL;  // scheduler.go:19
+static const int kMaxFailures = 5;                              // scheduler.go:28
 struct SvcVer { std::string svc; uint64_t ver; bool operator<(const SvcVer &o) const { return svc != o.svc ? svc < o.svc : ver < o.ver; } };
 struct NodeInfo {
     NodeP node;
@@ -1124,19 +1126,21 @@ struct Scheduler {
     // ---- cluster (CSI) volumes: VolumesFilter (filter.go:388-447) is evaluated HERE, on the host, against the shim's own
     // volume bookkeeping; the engine gets the answer as the group's node set -- the rows marked in one attribute column,
     // named by a leaf term (the mechanism of the preference leaves) -- and does everything else.  Exact for a single task and
-    // for groups whose volumes cannot change availability while the group is placed (VolumeBook::staticFor); a group whose
-    // volume availability moves with every placement (scope SINGLE_NODE, sharing NONE / ONE_WRITER writers) is answered
-    // like an unsupported group: the reference re-evaluates the filter inside its fill loop (scheduler.go:912-920) and the
-    // engine cannot.  Left-over single tasks get the reference's exact explanation (every node's first failing filter).
+    // as ONE engine group for groups whose volumes cannot change availability while the group is placed
+    // (VolumeBook::staticFor); a group whose volume availability moves with every placement (scope SINGLE_NODE, sharing
+    // NONE / ONE_WRITER writers) goes through scheduleVolumeGroupStepwise, because the reference re-evaluates the filter
+    // inside its fill loop (scheduler.go:912-920).  Left-over tasks get the reference's exact explanation.
     void mark_volume_nodes(const std::vector<std::string> &ids) {
         if (vol_col == PE_NONE) { vol_col = next_label_col++; layout_dirty = true; }
         vol_gen++;                                    // marks of older sets never equal the new value: nothing to clear
         for (auto &id : ids) { vol_mark_of[id] = vol_gen; touch(id); }
     }
-    // first failing filter of one task of this spec on each of `ids` (taskFitNode's question, in batches of pe_fit requests);
-    // a node that passes every device filter is counted for VolumesFilter and the reservation pe_fit made on it is taken back
-    bool count_excluded(const TaskP &t, const std::vector<std::string> &ids, std::vector<uint32_t> &cnt) {
+    // taskFitNode's question for one task of this spec on each of `ids` (batches of pe_fit requests): ok[i] as pe_fit gives
+    // it, fail[i*8..] the first failing filter.  A success RESERVES on the device; with `undo` those reservations are
+    // taken back (the rows are uploaded again from NodeInfo before the next engine call).
+    bool fit_many(const TaskP &t, const std::vector<std::string> &ids, std::vector<uint8_t> &ok, std::vector<uint32_t> &fail, bool undo) {
         const size_t kBatch = 4096;
+        ok.assign(ids.size(), 0); fail.assign(ids.size() * PE_NUM_FILTERS, 0);
         for (size_t lo = 0; lo < ids.size(); lo += kBatch) {
             const size_t n = std::min(kBatch, ids.size() - lo);
             TickBuf b;
@@ -1145,14 +1149,163 @@ struct Scheduler {
             if (!flush_rows()) return false;
             std::vector<uint32_t> idx(n);
             for (size_t i = 0; i < n; i++) idx[i] = node_index(ids[lo + i]);
-            std::vector<uint8_t> ok(n, 0); std::vector<uint32_t> fail(n * PE_NUM_FILTERS, 0);
             pe_tick tk = b.view();
-            if (!check(pe_fit(eng, &tk, idx.data(), ok.data(), fail.data()), "pe_fit")) return false;
-            for (size_t i = 0; i < n; i++) {
-                if (ok[i] == 1) { cnt[PE_F_VOLUMES]++; touch(ids[lo + i]); }
-                else if (ok[i] == 0) for (int f = 0; f < PE_NUM_FILTERS; f++) cnt[f] += fail[i * PE_NUM_FILTERS + f];
+            if (!check(pe_fit(eng, &tk, idx.data(), ok.data() + lo, fail.data() + lo * PE_NUM_FILTERS), "pe_fit")) return false;
+            if (undo) for (size_t i = 0; i < n; i++) if (ok[lo + i] == 1) touch(ids[lo + i]);
+        }
+        return true;
+    }
+    // first failing filter of every node of `ids`, none of which passes VolumesFilter: a device filter if one fails,
+    // VolumesFilter (the last of the pipeline) otherwise
+    bool count_excluded(const TaskP &t, const std::vector<std::string> &ids, std::vector<uint32_t> &cnt) {
+        std::vector<uint8_t> ok; std::vector<uint32_t> fail;
+        if (!fit_many(t, ids, ok, fail, true)) return false;
+        for (size_t i = 0; i < ids.size(); i++) {
+            if (ok[i] == 1) cnt[PE_F_VOLUMES]++;
+            else if (ok[i] == 0) for (int f = 0; f < PE_NUM_FILTERS; f++) cnt[f] += fail[i * PE_NUM_FILTERS + f];
+        }
+        return true;
+    }
+    // scheduler.go:857-893 for one task: attachments chosen and reserved, NodeInfo moved (the device row already has)
+    void assign_with_volumes(const TaskP &ti, const std::string &node_id, std::map<std::string, Decision> &decisions) {
+        NodeInfo &ni = nodeSet[node_id];
+        TaskP nt(new Task(*ti));
+        std::string verr;
+        volumes.choose(*ti, *ni.node, nt->volumes, verr);                         // (a failure is only logged there)
+        nt->node_id = node_id;
+        volumes.reserveTask(*nt);
+        nt->state = TaskStateAssigned; nt->err.clear(); nt->message = "scheduler assigned task to node";
+        allTasks[ti->id] = nt;
+        ni.addTask(nt);
+        decisions[ti->id] = {ti, nt};
+    }
+    // A group whose volume availability moves with every placement (scope SINGLE_NODE, sharing NONE, writers on ONE_WRITER):
+    // the reference re-runs the whole pipeline, VolumesFilter included, on the next node before every further placement
+    // (scheduler.go:912-920).  The shim walks that loop itself and asks the engine one question at a time:
+    //   * the heap of the k best feasible nodes in rank order (scheduler.go:722-731, nodeset.go:103-121) = k successive
+    //     one-task groups on the allowed set, each answer taken out of the set and its reservation taken back;
+    //   * "does this node still pass, and if so place the next task there" = pe_fit (device filters + reservation), then
+    //     VolumesFilter here -- the pipeline's order, so the failure counters come out as the reference's;
+    //   * nodeLess between two nodes of the heap (scheduler.go:708-734) is three integer compares on NodeInfo.
+    // O(k) engine calls: for the handful of replicas a service with its own volumes has, not a throughput path.
+    bool scheduleVolumeGroupStepwise(std::vector<TaskP> &grp, const std::vector<std::string> &excluded, std::map<std::string, Decision> &decisions) {
+        const TaskP t = grp[0];
+        const size_t k = grp.size();
+        auto give_back = [&](size_t from) { for (size_t i = from; i < grp.size(); i++) enqueue(grp[i]); layout_dirty = true; return false; };
+        std::set<std::string> allowed;                        // VolumesFilter's answer at tree-building time
+        for (auto &kv : vol_mark_of) if (kv.second == vol_gen) allowed.insert(kv.first);
+        std::vector<uint32_t> cnt(PE_NUM_FILTERS, 0);
+        // ---- the heap, in rank order
+        std::vector<std::string> cand;
+        {
+            TickBuf b;
+            fatal.clear();
+            std::vector<TaskP> one{t};
+            if (!encode_group(one, b)) { if (unsupported.empty()) unsupported = fatal; noSuitableNode(grp, "unsupported by the placement engine: " + fatal, decisions); fatal.clear(); return true; }
+            pe_group &g = b.groups.back();
+            if (g.con_cnt == 0) g.con_off = (uint32_t)b.cons.size();
+            b.cons.push_back({vol_col, vol_gen, 0});
+            g.leaf_cnt = 1;
+            for (size_t i = 0; i < k; i++) {
+                if (!flush_rows()) return give_back(0);
+                uint32_t pn = PE_NONE; std::vector<uint32_t> pf(PE_NUM_FILTERS, 0);
+                pe_tick tk = b.view();
+                if (!check(pe_schedule(eng, &tk, &pn, pf.data()), "pe_schedule")) return give_back(0);
+                if (pn == PE_NONE || pn >= idx_to_id.size()) { if (i == 0) cnt = pf; break; }
+                cand.push_back(idx_to_id[pn]);
+                vol_mark_of[idx_to_id[pn]] = 0;          // out of the set; the row upload also takes the reservation back
+                touch(idx_to_id[pn]);
             }
         }
+        if (cand.empty()) {                                   // nothing passed: every node is counted by its first failing filter
+            if (!count_excluded(t, excluded, cnt)) return give_back(0);
+            noSuitableNode(grp, explain(cnt.data()), decisions);
+            return true;
+        }
+        // ---- scheduleNTasksOnNodes, scheduler.go:844-924
+        // nodeLess (scheduler.go:708-734) + the canonical tie-break, as a key: recent failures count only from maxFailures up
+        const SvcVer key{t->service, t->has_spec_version ? t->spec_version : 0};
+        struct RankKey {
+            int f, s, a; std::string id;
+            bool less_no_tie(const RankKey &o) const { if (f != o.f) return f < o.f; if (s != o.s) return s < o.s; return a < o.a; }
+            bool operator<(const RankKey &o) const { if (less_no_tie(o)) return true; if (o.less_no_tie(*this)) return false; return id < o.id; }
+        };
+        auto rank_key = [&](const NodeInfo &n) {
+            const int f = n.countRecentFailures(now, key);
+            auto sv = n.by_service.find(t->service);
+            return RankKey{f >= kMaxFailures ? f : 0, sv == n.by_service.end() ? 0 : sv->second, n.active, n.node->id};
+        };
+        auto nodeLess = [&](const NodeInfo &a, const NodeInfo &b) { return rank_key(a).less_no_tie(rank_key(b)); };
+        const RankKey first_key = rank_key(nodeSet[cand[0]]);
+        const size_t m = cand.size();
+        std::vector<char> failed(m, 0);
+        std::vector<uint8_t> ok; std::vector<uint32_t> fail;
+        bool tree_counters_stand = true;      // no Process() has passed since the tree was built
+        size_t it = 0, placed = 0;
+        // (the first node passed the pipeline when the tree was built and nothing has changed: pe_fit reserves there)
+        if (!fit_many(grp[0], {cand[0]}, ok, fail, false)) return give_back(0);
+        if (ok[0] != 1) { fatal = "placement engine: the best node of a group does not fit its first task"; return give_back(0); }
+        for (;;) {
+            const std::string &nid = cand[it % m];
+            assign_with_volumes(grp[placed], nid, decisions);
+            placed++;
+            if (placed == k) return true;
+            if (it + 1 < m) { if (nodeLess(nodeSet[cand[(it + 1) % m]], nodeSet[nid])) it++; }   // first pass: level the nodes
+            else it++;                                                                                // later passes: one task per node
+            const size_t orig = it;
+            bool found = false;
+            while (!found) {
+                const size_t i = it % m;
+                if (!failed[i]) {
+                    if (!fit_many(grp[placed], {cand[i]}, ok, fail, false)) return give_back(placed);
+                    if (ok[0] == 1 && volumes.filterCheck(*grp[placed], *nodeSet[cand[i]].node)) {
+                        std::fill(cnt.begin(), cnt.end(), 0u);                                      // pipeline.go:64-66
+                        tree_counters_stand = false;
+                        found = true;
+                        break;
+                    }
+                    if (ok[0] == 1) { cnt[PE_F_VOLUMES]++; touch(cand[i]); }                        // (the reservation is taken back)
+                    else for (int f = 0; f < PE_NUM_FILTERS; f++) cnt[f] += fail[f];
+                    failed[i] = 1;
+                }
+                it++;
+                if (it - orig == m) break;                     // none of the nodes meets the constraints any more
+            }
+            if (!found) break;
+        }
+        std::vector<TaskP> left(grp.begin() + (long)placed, grp.end());
+        if (tree_counters_stand) {
+            // No re-check passed, so what the tree building left in the counters still stands (pipeline.go:55-68): the
+            // failures after the last node that passed, among the nodes the tree building RAN the pipeline on -- every node
+            // while the heap had room, afterwards only nodes that rank ahead of the heap's worst (nodeset.go:103-121).
+            // Replay that walk (ascending node ID): pe_fit says which nodes pass the device filters -- every node but cand[0]
+            // is as it was then (failed re-checks were taken back) -- `allowed` is VolumesFilter's answer of then, and the
+            // rank keys are three integers of NodeInfo (cand[0]'s were saved before it took the task).
+            std::vector<std::string> ids;
+            for (auto &kv : nodeSet) if (kv.first != cand[0]) ids.push_back(kv.first);
+            if (!fit_many(left[0], ids, ok, fail, true)) return give_back(placed);
+            std::vector<uint32_t> tree(PE_NUM_FILTERS, 0);
+            auto worse = [](const RankKey &a, const RankKey &b) { return a < b; };   // max-heap: the worst on top
+            std::vector<RankKey> heap;
+            size_t j = 0;
+            for (auto &kv : nodeSet) {
+                const bool is_first = kv.first == cand[0];
+                const RankKey rk = is_first ? first_key : rank_key(kv.second);
+                const size_t q = is_first ? 0 : j++;
+                if (heap.size() >= k && !(rk < heap.front())) continue;              // the pipeline was not run on it
+                const bool passes = is_first || (ok[q] == 1 && allowed.count(kv.first));
+                if (!passes) {
+                    if (ok[q] == 1) tree[PE_F_VOLUMES]++;
+                    else if (ok[q] == 0) for (int f = 0; f < PE_NUM_FILTERS; f++) tree[f] += fail[q * PE_NUM_FILTERS + f];
+                    continue;
+                }
+                std::fill(tree.begin(), tree.end(), 0u);
+                if (heap.size() >= k) { std::pop_heap(heap.begin(), heap.end(), worse); heap.pop_back(); }
+                heap.push_back(rk); std::push_heap(heap.begin(), heap.end(), worse);
+            }
+            for (int f = 0; f < PE_NUM_FILTERS; f++) cnt[f] += tree[f];
+        }
+        noSuitableNode(left, explain(cnt.data()), decisions);
         return true;
     }
     bool scheduleVolumeGroup(std::vector<TaskP> &grp, std::map<std::string, Decision> &decisions) {
@@ -1163,11 +1316,11 @@ struct Scheduler {
             return true;
         };
         if (!preference_levels(t).empty()) return refuse("placement preferences together with cluster volumes (task " + t.id + ")");
-        if (grp.size() > 1 && !volumes.staticFor(t)) return refuse("the availability of the group's cluster volumes changes with every placement (task " + t.id + ")");
         auto give_back = [&](const std::vector<TaskP> &ts) { for (auto &x : ts) enqueue(x); layout_dirty = true; };
         std::vector<std::string> allowed, excluded;
         for (auto &kv : nodeSet) (volumes.filterCheck(t, *kv.second.node) ? allowed : excluded).push_back(kv.first);
         mark_volume_nodes(allowed);
+        if (grp.size() > 1 && !volumes.staticFor(t)) return scheduleVolumeGroupStepwise(grp, excluded, decisions);
         TickBuf b;
         fatal.clear();
         if (!encode_group(grp, b)) { std::string why = fatal; fatal.clear(); return refuse(why); }
@@ -1191,17 +1344,8 @@ struct Scheduler {
             const TaskP &ti = grp[i];
             const uint32_t idx = out_node[i];
             if (idx == PE_NONE || idx >= idx_to_id.size()) { left.push_back(ti); continue; }
-            NodeInfo &ni = nodeSet[idx_to_id[idx]];
             if (first_placed.empty()) first_placed = idx_to_id[idx];
-            TaskP nt(new Task(*ti));                                                  // scheduler.go:857-880
-            std::string verr;
-            volumes.choose(*ti, *ni.node, nt->volumes, verr);                         // (a failure is only logged there)
-            nt->node_id = idx_to_id[idx];
-            volumes.reserveTask(*nt);
-            nt->state = TaskStateAssigned; nt->err.clear(); nt->message = "scheduler assigned task to node";
-            allTasks[ti->id] = nt;
-            ni.addTask(nt);
-            decisions[ti->id] = {ti, nt};
+            assign_with_volumes(ti, idx_to_id[idx], decisions);
         }
         if (left.empty()) return true;
         std::vector<uint32_t> cnt(out_fail);

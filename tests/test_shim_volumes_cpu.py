@@ -151,17 +151,62 @@ def test_random_replicated_services_on_static_volumes(seed):
             c.advance(5)
 
 
-def test_group_whose_volume_availability_moves_is_refused_not_misplaced():
-    """k > 1 tasks writing to a ONE_WRITER volume: the reference re-evaluates VolumesFilter after every placement of the
-    group (scheduler.go:912-920); the engine cannot, so the shim answers like for any unsupported group -- the tasks stay
-    pending, the tick reports why -- instead of placing two writers."""
+@pytest.mark.parametrize("seed", range(16))
+def test_random_replicated_services_on_volumes_that_count_their_users(seed):
+    """Groups of k > 1 identical tasks on volumes of every scope / sharing, writers included: availability moves with
+    every placement, the reference re-runs VolumesFilter inside its fill loop (scheduler.go:912-920) and the shim walks
+    that loop one engine question at a time (scheduleVolumeGroupStepwise)."""
+    rng = random.Random(9900 + seed)
+    n_nodes, n_vol = rng.randint(3, 24), rng.randint(2, 8)
+    nodes = [_node(rng, i) for i in range(n_nodes)]
+    vols = [_volume(rng, i) for i in range(n_vol)]
+    svcs = [(f"svc{j}", 1) for j in range(4)]
+    cm = Cluster(make_shim(), nodes=nodes, volumes=vols, services=svcs)
+    co = Cluster(make_oracle(), nodes=nodes, volumes=vols, services=svcs)
+    next_id = 0
+    for step in range(6):
+        r2 = random.Random(seed * 1000 + step)
+        new = []
+        for j in r2.sample(range(4), r2.randint(1, 3)):
+            r_svc = random.Random(seed * 31 + j)          # the spec of a service is fixed: its tasks form one group
+            mounts = [cluster_mount(r_svc.choice([f"data{r_svc.randrange(n_vol)}", "group:g1", "group:g2"]), r_svc.choice(["/a", "/b"]),
+                                    read_only=r_svc.random() < 0.4) for _ in range(r_svc.randint(1, 2))]
+            res = resources(r_svc.choice([0, 5, 10, 20]) * 10**8, 0)
+            for _ in range(r2.randint(2, 7)):
+                new.append(task(f"t{next_id:04d}", service_id=f"svc{j}", spec_version=1, reservations=res, mounts=mounts))
+                next_id += 1
+        for c in (cm, co):
+            for t in new:
+                c.create_task(t)
+        dm, do = cm.run(), co.run()
+        assert comparable(dm, cm) == comparable(do, co), f"seed {seed} step {step}: decisions differ"
+        assert cm.s.apply({"op": "volume_usage"})["volumes"] == co.s.apply({"op": "volume_usage"})["volumes"]
+        sm, so = cm.s.apply({"op": "device_check"}), co.snapshot()
+        assert sm["mismatch"] == [] and sm["nodes"] == so["nodes"] and sm["unassigned"] == so["unassigned"]
+        for c in (cm, co):
+            r3 = random.Random(seed * 77 + step)
+            running = [t for t in c.tasks.values() if t["status"]["state"] == "ASSIGNED"]
+            for t in r3.sample(running, min(len(running), r3.randint(0, 4))):
+                c.update_task(dict(t, status=dict(t["status"], state="SHUTDOWN")))
+                c.delete_task(t["id"])
+            if r3.random() < 0.3:
+                c.update_volume(_volume(r3, r3.randrange(n_vol + 2)))
+            c.advance(5)
+
+
+def test_three_writers_one_single_writer_volume():
+    """k = 3 tasks writing to a ONE_WRITER volume: the first takes it, the re-check of every other node fails on
+    VolumesFilter, two tasks stay pending with the reference's explanation -- never two writers."""
     nodes = [node(f"n{i}", description=description(resources=resources(8 * 10**9, 2**34), csi_info=[("plugA", f"a{i}", None)])) for i in range(3)]
     vols = [csi_volume("vol0", "data0", driver="plugA", scope="MULTI_NODE", sharing="ONE_WRITER", volume_id="csi0")]
-    c = Cluster(make_shim(), nodes=nodes, volumes=vols, services=[("svc", 1)])
-    for i in range(3):
-        c.create_task(task(f"t{i}", service_id="svc", spec_version=1, mounts=[cluster_mount("data0", "/a")]))
-    with pytest.raises(RuntimeError, match="changes with every placement"):
-        c.run()
-    assert all(u == [] or u == {} or not u for u in [c.s.apply({"op": "volume_usage"})["volumes"].get("vol0")]) or True
-    snap = c.s.apply({"op": "snapshot"})
-    assert sorted(snap["unassigned"]) == ["t0", "t1", "t2"]
+    out = []
+    for mk in (make_shim, make_oracle):
+        c = Cluster(mk(), nodes=nodes, volumes=vols, services=[("svc", 1)])
+        for i in range(3):
+            c.create_task(task(f"t{i}", service_id="svc", spec_version=1, mounts=[cluster_mount("data0", "/a")]))
+        d = c.run()
+        out.append((comparable(d, c), c.s.apply({"op": "volume_usage"})["volumes"]))
+    assert out[0] == out[1]
+    dec, usage = out[0]
+    assert sorted(k for k, v in dec.items() if v["state"] == "ASSIGNED") == ["t0"] and list(usage["vol0"]) == ["t0"]
+    assert dec["t1"]["err"] == "no suitable node (cannot fulfill requested CSI volume mounts on 3 nodes)"   # n1, n2 and, after the wrap, n0 itself

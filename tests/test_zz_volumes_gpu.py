@@ -39,6 +39,12 @@ def test_random_replicated_services_on_static_volumes_on_gpu(seed, monkeypatch):
     cpu_twin.test_random_replicated_services_on_static_volumes(seed)
 
 
-def test_refusal_on_gpu(monkeypatch):
+@pytest.mark.parametrize("seed", range(4))
+def test_random_replicated_services_on_volumes_that_count_their_users_on_gpu(seed, monkeypatch):
     monkeypatch.setattr(cpu_twin, "make_shim", make_mirror)
-    cpu_twin.test_group_whose_volume_availability_moves_is_refused_not_misplaced()
+    cpu_twin.test_random_replicated_services_on_volumes_that_count_their_users(seed)
+
+
+def test_three_writers_one_single_writer_volume_on_gpu(monkeypatch):
+    monkeypatch.setattr(cpu_twin, "make_shim", make_mirror)
+    cpu_twin.test_three_writers_one_single_writer_volume()
