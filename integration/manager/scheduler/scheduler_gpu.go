@@ -72,6 +72,7 @@ type gpuEngine struct {
 	volCol    uint32            // C.PE_NONE until the first group with cluster mounts
 	volGen    uint32            // the value that marks the current set (older marks never equal it: nothing to clear)
 	volMarkOf map[string]uint32 // node ID -> its mark
+	leafAlsoInVolumeSet bool   // a preference group with cluster mounts: every leaf visit carries the volume term too
 }
 
 func mustNewGPUEngine() *gpuEngine {
@@ -1056,8 +1057,9 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 	refuse := func(why string) {
 		s.noSuitableNodeWith(ctx, group, decisions, "unsupported by the placement engine: "+why)
 	}
-	if len(s.preferenceLevels(t)) != 0 {
-		refuse("placement preferences together with cluster volumes")
+	prefs := len(s.preferenceLevels(t)) != 0
+	if prefs && len(ts) > 1 && !s.volumesStaticFor(t) {
+		refuse("placement preferences on a group whose cluster volumes count their users")
 		return
 	}
 	requeue := func(err error) {
@@ -1082,6 +1084,14 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 		}
 	}
 	s.gpu.markVolumeNodes(allowed)
+	if prefs {
+		// the tree's branches and task sums do not depend on the pipeline (nodeset.go:59-101): the preference walk runs
+		// unchanged and every leaf visit carries the volume term next to the leaf's own terms (fillLeaf)
+		s.gpu.leafAlsoInVolumeSet = true
+		s.schedulePreferenceGroup(ctx, group, decisions, now)
+		s.gpu.leafAlsoInVolumeSet = false
+		return
+	}
 	if len(ts) > 1 && !s.volumesStaticFor(t) {
 		if err := s.scheduleVolumeGroupStepwise(ctx, ts, group, allowed, excluded, decisions, now); err != nil {
 			requeue(err)
@@ -1203,6 +1213,10 @@ func (s *Scheduler) fillLeaf(ctx context.Context, n int, leaf *prefTree, w *pref
 	}
 	b.cons = append(b.cons, leaf.leaf...)
 	g.leaf_cnt = C.uint32_t(len(leaf.leaf))
+	if s.gpu.leafAlsoInVolumeSet { // a preference group with cluster mounts (scheduleVolumeGroup)
+		b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(s.gpu.volCol), value: C.uint32_t(s.gpu.volGen)})
+		g.leaf_cnt++
+	}
 	if w.failed = s.gpu.flushRows(&s.nodeSet); w.failed != nil {
 		return 0
 	}

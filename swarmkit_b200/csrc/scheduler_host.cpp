@@ -550,6 +550,7 @@ struct Scheduler {
     uint32_t vol_gen = 0;                // value of that column for the set marked last
     std::vector<uint32_t> vol_marked;    // the rows that carry it
     std::map<std::string, uint32_t> vol_mark_of;   // node ID -> its current mark (0 = none), written into the row by encode_row
+    bool leaf_also_in_volume_set = false; // a preference group with cluster mounts: every leaf visit carries the volume term too
     int64_t now = 0;
 
     // ---- dictionaries (exact interning)
@@ -1048,10 +1049,12 @@ struct Scheduler {
 
     // what the engine decided for one encoded group: decisions, host mirror; tasks without a node come back in `left`
     void apply_group(const std::vector<TaskP> &grp, const uint32_t *out_node, std::vector<TaskP> &left, std::map<std::string, Decision> &decisions) {
+        const bool csi = !grp.empty() && has_cluster_mounts(*grp[0]);
         for (size_t i = 0; i < grp.size(); i++) {
             const TaskP &t = grp[i];
             uint32_t idx = out_node[i];
             if (idx == PE_NONE || idx >= idx_to_id.size()) { left.push_back(t); continue; }
+            if (csi) { assign_with_volumes(t, idx_to_id[idx], decisions); continue; }  // (attachments chosen and reserved)
             TaskP nt(new Task(*t));                                                   // scheduler.go:871-880
             nt->node_id = idx_to_id[idx];
             nt->state = TaskStateAssigned; nt->err.clear(); nt->message = "scheduler assigned task to node";
@@ -1315,11 +1318,22 @@ struct Scheduler {
             noSuitableNode(grp, "unsupported by the placement engine: " + why, decisions);
             return true;
         };
-        if (!preference_levels(t).empty()) return refuse("placement preferences together with cluster volumes (task " + t.id + ")");
+        const bool prefs = !preference_levels(t).empty();
+        if (prefs && grp.size() > 1 && !volumes.staticFor(t))
+            return refuse("placement preferences on a group whose cluster volumes count their users (task " + t.id + ")");
         auto give_back = [&](const std::vector<TaskP> &ts) { for (auto &x : ts) enqueue(x); layout_dirty = true; };
         std::vector<std::string> allowed, excluded;
         for (auto &kv : nodeSet) (volumes.filterCheck(t, *kv.second.node) ? allowed : excluded).push_back(kv.first);
         mark_volume_nodes(allowed);
+        if (prefs) {
+            // the tree's branches and task sums do not depend on the pipeline (nodeset.go:59-101 counts every node); each
+            // leaf visit is the leaf's engine group cut down to the volume set as well (same argument as for one group:
+            // the answer of VolumesFilter cannot move while this group is placed)
+            leaf_also_in_volume_set = true;
+            const bool ok = schedulePreferenceGroup(grp, decisions);
+            leaf_also_in_volume_set = false;
+            return ok;
+        }
         if (grp.size() > 1 && !volumes.staticFor(t)) return scheduleVolumeGroupStepwise(grp, excluded, decisions);
         TickBuf b;
         fatal.clear();
@@ -1401,6 +1415,7 @@ struct Scheduler {
         if (g.con_cnt == 0) g.con_off = (uint32_t)b.cons.size();       // the leaf terms follow the group's constraints
         b.cons.insert(b.cons.end(), leaf.leaf.begin(), leaf.leaf.end());
         g.leaf_cnt = (uint32_t)leaf.leaf.size();
+        if (leaf_also_in_volume_set) { b.cons.push_back({vol_col, vol_gen, 0}); g.leaf_cnt++; }   // (scheduleVolumeGroup)
         if (!flush_rows()) { w.engine_failed = true; return 0; }
         std::vector<uint32_t> out_node(m, PE_NONE), out_fail(PE_NUM_FILTERS, 0);
         pe_tick tk = b.view();

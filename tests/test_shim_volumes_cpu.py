@@ -8,7 +8,7 @@ import pytest
 
 import tests.test_oracle_volumes_scheduler as ref_scenarios
 from tests.oracle_lib import build_sched, build_shim_on_oracle
-from tests.sched_harness import Cluster, JsonScheduler, cluster_mount, comparable, csi_volume, description, node, resources, task
+from tests.sched_harness import Cluster, JsonScheduler, cluster_mount, comparable, csi_volume, description, node, placement, resources, task
 
 
 def make_shim():
@@ -37,7 +37,9 @@ def _node(rng, i):
         csi.append(("plugA", f"a{i}", {"zone": rng.choice(ZONES)} if rng.random() < 0.8 else None))
     if rng.random() < 0.4:
         csi.append(("plugB", f"b{i}", {"zone": rng.choice(ZONES), "rack": rng.choice(["r1", "r2"])}))
-    return node(f"n{i:03d}", state=rng.choice(["READY"] * 9 + ["DOWN"]), description=description(resources=resources(rng.randint(2, 8) * 10**9, 2**34), csi_info=csi))
+    lr = random.Random(i * 7919 + 13)
+    labels = {k: lr.choice(v) for k, v in (("az", ["a", "b", "c"]), ("rack", ["r1", "r2"])) if lr.random() < 0.85}
+    return node(f"n{i:03d}", state=rng.choice(["READY"] * 9 + ["DOWN"]), labels=labels, description=description(resources=resources(rng.randint(2, 8) * 10**9, 2**34), csi_info=csi))
 
 
 def _volume(rng, i):
@@ -73,8 +75,9 @@ def test_random_event_stream_with_volumes(seed):
         for _ in range(r2.randint(1, 8)):
             kind = r2.random()
             res = resources(r2.choice([0, 5, 10]) * 10**8, 0) if r2.random() < 0.5 else None
-            if kind < 0.65:      # one-off task with cluster mounts
-                new.append(task(f"t{next_id:04d}", service_id="svc", reservations=res, mounts=_mounts(r2, n_vol)))
+            if kind < 0.65:      # one-off task with cluster mounts (a third of them spread over a label as well)
+                pl = placement(preferences=["node.labels.az"]) if r2.random() < 0.33 else None
+                new.append(task(f"t{next_id:04d}", service_id="svc", reservations=res, mounts=_mounts(r2, n_vol), placement=pl))
             elif kind < 0.8:     # preassigned (global-mode) task with cluster mounts
                 new.append(task(f"t{next_id:04d}", service_id="svc", node_id=f"n{r2.randrange(n_nodes):03d}", reservations=res, mounts=_mounts(r2, n_vol)))
             else:                # plain task
@@ -112,7 +115,8 @@ def _static_volume(rng, i):
 @pytest.mark.parametrize("seed", range(16))
 def test_random_replicated_services_on_static_volumes(seed):
     """Groups of k > 1 identical tasks whose cluster mounts are read-only or on share-all volumes: one engine group on the
-    node set the host-side VolumesFilter allows."""
+    node set the host-side VolumesFilter allows; half the services also spread over node labels (every leaf visit of
+    their preference tree carries the volume term too)."""
     rng = random.Random(9500 + seed)
     n_nodes, n_vol = rng.randint(4, 30), rng.randint(2, 6)
     nodes = [_node(rng, i) for i in range(n_nodes)]
@@ -136,8 +140,9 @@ def test_random_replicated_services_on_static_volumes(seed):
                     src, vol_ro = (r_svc.choice(ok), False) if ok else ("group:g1", True)
                 mounts.append(cluster_mount(src, r_svc.choice(["/a", "/b"]), read_only=vol_ro))
             res = resources(r_svc.choice([0, 5, 10]) * 10**8, 0)
+            pl = placement(preferences=r_svc.choice([["node.labels.az"], ["node.labels.az", "node.labels.rack"]])) if r_svc.random() < 0.5 else None
             for _ in range(r2.randint(2, 9)):
-                new.append(task(f"t{next_id:04d}", service_id=f"svc{j}", spec_version=1, reservations=res, mounts=mounts))
+                new.append(task(f"t{next_id:04d}", service_id=f"svc{j}", spec_version=1, reservations=res, mounts=mounts, placement=pl))
                 next_id += 1
         for c in (cm, co):
             for t in new:
