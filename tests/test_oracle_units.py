@@ -293,3 +293,77 @@ def test_named_want_zero_claims_every_member(so):
     # selectNodeResources never hits its `len(nrs) == tr.Value` exit for Value 0 (resource_management.go:58-63)
     r = gen(so, "claim", nset("gpu", "a", "b", "c"), reservations=[discrete("gpu", 0)])
     assert r["ok"] and r["available"] == [] and len(r["assigned"]) == 3
+
+
+def test_has_resource_discrete(so):                                     # validate_test.go:10-29 (the three HasResource cases)
+    # The path asks the same question through HasEnough (validate.go:24-51, called by ResourceFilter.Check filter.go:96-103);
+    # for a discrete want on a discrete node resource the two functions agree: want <= available.
+    for want, expect in ((1, True), (5, True), (6, False)):
+        assert gen(so, "has_enough", [discrete("apple", 5)], reservations=[discrete("apple", want)])["enough"] is expect
+    # HasEnough's own branches: a kind the node does not have, and a named set counted by its members (:36-47)
+    assert gen(so, "has_enough", [discrete("apple", 5)], reservations=[discrete("pear", 1)])["enough"] is False
+    assert gen(so, "has_enough", nset("apple", "red", "orange", "blue"), reservations=[discrete("apple", 3)])["enough"] is True
+    assert gen(so, "has_enough", nset("apple", "red", "orange", "blue"), reservations=[discrete("apple", 4)])["enough"] is False
+
+
+def _kinds(a):
+    out = {}
+    for g in a:
+        out.setdefault(g["kind"], []).append(g)
+    return out
+
+
+def test_reclaim_resources_mixed(so):                                   # resource_management_test.go:187-230 TestReclaimResources
+    node_res = nset("orange", "green", "blue") + [discrete("apple", 3)] + nset("banana", "red", "orange", "green") + [discrete("cake", 2)]
+    assigned = nset("orange", "red", "orange") + nset("grape", "red", "orange") + [discrete("apple", 3), discrete("coffe", 2)]
+    a = gen(so, "reclaim_resources", node_res, assigned=assigned)["available"]
+    k = _kinds(a)
+    assert len(a) == 12 and {n: len(v) for n, v in k.items()} == {"apple": 1, "orange": 4, "banana": 3, "cake": 1, "grape": 2, "coffe": 1}
+    assert k["apple"][0]["value"] == 6 and k["cake"][0]["value"] == 2 and k["coffe"][0]["value"] == 2
+    assert sorted(g["named"] for g in k["orange"]) == ["blue", "green", "orange", "red"]
+    assert sorted(g["named"] for g in k["banana"]) == ["green", "orange", "red"]
+    assert sorted(g["named"] for g in k["grape"]) == ["orange", "red"]
+
+
+def _sanitize(so, node_res, available):
+    """sanitize(nodeRes, &available) (resource_management.go:135-205) as the path reaches it: Reclaim with nothing to give
+    back (NodeInfo.removeTask -> genericresource.Reclaim, nodeinfo.go:84-102, resource_management.go:74-91)."""
+    return so.apply({"op": "generic", "fn": "reclaim", "available": resources(0, 0, available), "assigned": resources(0, 0, []),
+                     "node": resources(0, 0, node_res)})["available"]
+
+
+def test_sanitize_discrete(so):                                         # :232-271 TestSanitizeDiscrete
+    assert _sanitize(so, [], [discrete("orange", 4)]) == []
+    assert _sanitize(so, [discrete("orange", 6)], [discrete("orange", 4)]) == [discrete("orange", 4)]
+    assert _sanitize(so, [discrete("orange", 4)], [discrete("orange", 4)]) == [discrete("orange", 4)]
+    assert _sanitize(so, [discrete("orange", 2)], [discrete("orange", 4)]) == [discrete("orange", 2)]
+    a = _sanitize(so, [discrete("orange", 2), discrete("banana", 6), discrete("cake", 6)],
+                  [discrete("orange", 2), discrete("cake", 2), discrete("apple", 4), discrete("banana", 8)])
+    assert [g["value"] for g in a] == [2, 2, 6] and [g["kind"] for g in a] == ["orange", "cake", "banana"]
+
+
+def test_sanitize_str(so):                                              # :273-291 TestSanitizeStr
+    avail = nset("apple", "red", "orange", "blue")
+    assert _sanitize(so, [], avail) == []
+    assert len(_sanitize(so, nset("apple", "red", "orange", "blue", "green"), avail)) == 3
+    assert len(_sanitize(so, nset("apple", "red", "orange", "blue"), avail)) == 3
+    assert len(_sanitize(so, nset("apple", "red", "orange"), avail)) == 2
+
+
+def test_sanitize_change_discrete_to_set(so):                           # :293-339 TestSanitizeChangeDiscreteToSet
+    assert _sanitize(so, nset("apple", "red"), [discrete("apple", 5)]) == nset("apple", "red")
+    a = _sanitize(so, nset("apple", "red", "orange", "green"), [discrete("apple", 5)])
+    assert sorted(g["named"] for g in a) == ["green", "orange", "red"]
+    node_res = nset("apple", "red", "orange", "green") + nset("orange", "red", "orange", "green") + nset("cake", "red", "orange", "green")
+    a = _sanitize(so, node_res, nset("apple", "green") + [discrete("cake", 3)] + nset("orange", "orange", "blue"))
+    k = _kinds(a)
+    assert len(a) == 5 and [g["named"] for g in k["apple"]] == ["green"] and [g["named"] for g in k["orange"]] == ["orange"]
+    assert sorted(g["named"] for g in k["cake"]) == ["green", "orange", "red"]
+
+
+def test_sanitize_change_set_to_discrete(so):                           # :341-373 TestSanitizeChangeSetToDiscrete
+    assert _sanitize(so, [discrete("apple", 5)], nset("apple", "red")) == [discrete("apple", 5)]
+    assert _sanitize(so, [discrete("apple", 5)], nset("apple", "red", "orange", "green")) == [discrete("apple", 5)]
+    a = _sanitize(so, [discrete("apple", 5), discrete("orange", 3), discrete("cake", 1)],
+                  [discrete("apple", 5), discrete("cake", 2)] + nset("orange", "orange", "blue"))
+    assert {g["kind"]: g["value"] for g in a} == {"apple": 5, "orange": 3, "cake": 1} and len(a) == 3
