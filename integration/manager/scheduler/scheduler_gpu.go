@@ -70,8 +70,7 @@ type gpuEngine struct {
 	layout    bool                // membership or a dictionary grew: every row is uploaded again
 	// CSI cluster volumes: the node set VolumesFilter allows for the group being scheduled, as one attribute column
 	volCol    uint32            // C.PE_NONE until the first group with cluster mounts
-	volGen    uint32            // the value that marks the current set (older marks never equal it: nothing to clear)
-	volMarkOf map[string]uint32 // node ID -> its mark
+	volIn     map[string]struct{} // the nodes that carry volMark in that column (every other row holds 0 = "")
 	leafAlsoInVolumeSet bool   // a preference group with cluster mounts: every leaf visit carries the volume term too
 }
 
@@ -86,7 +85,7 @@ func mustNewGPUEngine() *gpuEngine {
 		kinds: map[string]uint32{}, labelCols: map[string]uint32{}, prefCols: map[string]uint32{}, prefIDs: map[string]uint32{"": 0},
 		prefStr: []string{""}, ports: map[hostPortSpec]uint32{}, plugins: map[[2]string]uint32{}, nextCol: C.PE_ATTR_FIRST_LABEL,
 		index: map[string]uint32{}, dirty: map[string]struct{}{}, layout: true, recycleAt: 4096, volCol: C.PE_NONE,
-		volMarkOf: map[string]uint32{}}
+		volIn: map[string]struct{}{}}
 }
 
 // serviceID names the engine's per-service counter column.  The engine never frees a column, so the ids of services that
@@ -203,6 +202,8 @@ func normArch(a string) string { // filter.go:291-306
 
 // ---- node rows: the device mirror of NodeInfo (nodeinfo.go:28-44) --------------------------------------------------
 
+const volMark = 1 // the value of gpuEngine.volCol on the rows of the current volume node set
+
 type rowBatch struct {
 	rows  []C.pe_node_row
 	attrs []C.pe_kv32
@@ -280,8 +281,8 @@ func (e *gpuEngine) encodeRow(idx uint32, ni *NodeInfo, b *rowBatch) {
 			attr(col, e.prefID(v))
 		}
 	}
-	if m := e.volMarkOf[n.ID]; e.volCol != C.PE_NONE && m != 0 {
-		attr(e.volCol, m)
+	if _, in := e.volIn[n.ID]; e.volCol != C.PE_NONE && in {
+		attr(e.volCol, volMark)
 	}
 	r.attr_cnt = C.uint32_t(len(b.attrs)) - r.attr_off
 	r.gen_off = C.uint32_t(len(b.gens))
@@ -779,10 +780,23 @@ func (e *gpuEngine) markVolumeNodes(ids []string) {
 		e.nextCol++
 		e.nodeSetChanged()
 	}
-	e.volGen++
+	// only the rows whose membership changes are uploaded: consecutive groups with the same mounts mostly ask for the
+	// set that is already marked
+	next := make(map[string]struct{}, len(ids))
 	for _, id := range ids {
-		e.volMarkOf[id] = e.volGen
-		e.nodeChanged(id)
+		next[id] = struct{}{}
+	}
+	for id := range e.volIn {
+		if _, ok := next[id]; !ok {
+			delete(e.volIn, id)
+			e.nodeChanged(id)
+		}
+	}
+	for _, id := range ids {
+		if _, ok := e.volIn[id]; !ok {
+			e.volIn[id] = struct{}{}
+			e.nodeChanged(id)
+		}
 	}
 }
 
@@ -889,7 +903,7 @@ func (s *Scheduler) scheduleVolumeGroupStepwise(ctx context.Context, ts []*api.T
 		if g.con_cnt == 0 {
 			g.con_off = C.uint32_t(len(b.cons))
 		}
-		b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(e.volCol), value: C.uint32_t(e.volGen)})
+		b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(e.volCol), value: C.uint32_t(volMark)})
 		g.leaf_cnt = 1
 		for i := 0; i < k; i++ {
 			if err := e.flushRows(&s.nodeSet); err != nil {
@@ -909,7 +923,7 @@ func (s *Scheduler) scheduleVolumeGroupStepwise(ctx context.Context, ts []*api.T
 			}
 			id := e.order[pn]
 			cand = append(cand, id)
-			e.volMarkOf[id] = 0 // out of the set; the row upload also takes the reservation back
+			delete(e.volIn, id) // out of the set; the row upload also takes the reservation back
 			e.nodeChanged(id)
 		}
 	}
@@ -1107,7 +1121,7 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 	if g.con_cnt == 0 {
 		g.con_off = C.uint32_t(len(b.cons)) // the leaf term follows the group's constraints
 	}
-	b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(s.gpu.volCol), value: C.uint32_t(s.gpu.volGen)})
+	b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(s.gpu.volCol), value: C.uint32_t(volMark)})
 	g.leaf_cnt = 1
 	if err := s.gpu.flushRows(&s.nodeSet); err != nil {
 		requeue(err)
@@ -1214,7 +1228,7 @@ func (s *Scheduler) fillLeaf(ctx context.Context, n int, leaf *prefTree, w *pref
 	b.cons = append(b.cons, leaf.leaf...)
 	g.leaf_cnt = C.uint32_t(len(leaf.leaf))
 	if s.gpu.leafAlsoInVolumeSet { // a preference group with cluster mounts (scheduleVolumeGroup)
-		b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(s.gpu.volCol), value: C.uint32_t(s.gpu.volGen)})
+		b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(s.gpu.volCol), value: C.uint32_t(volMark)})
 		g.leaf_cnt++
 	}
 	if w.failed = s.gpu.flushRows(&s.nodeSet); w.failed != nil {

@@ -547,9 +547,8 @@ struct Scheduler {
     std::map<std::string, std::pair<bool, uint64_t>> services;
     VolumeBook volumes;                  // CSI cluster volumes: host-side bookkeeping (volumes.go)
     uint32_t vol_col = PE_NONE;          // attribute column that names the node set of a group with cluster mounts
-    uint32_t vol_gen = 0;                // value of that column for the set marked last
-    std::vector<uint32_t> vol_marked;    // the rows that carry it
-    std::map<std::string, uint32_t> vol_mark_of;   // node ID -> its current mark (0 = none), written into the row by encode_row
+    static const uint32_t vol_gen = 1;   // the column's value on the rows of the set (0 = "" on every other row)
+    std::set<std::string> vol_in;        // the nodes that carry it, written into the row by encode_row
     bool leaf_also_in_volume_set = false; // a preference group with cluster mounts: every leaf visit carries the volume term too
     int64_t now = 0;
 
@@ -688,7 +687,7 @@ struct Scheduler {
             auto f = m->find(key);
             if (f != m->end()) attr(lc.second, f->second);
         }
-        if (vol_col != PE_NONE) { auto vm = vol_mark_of.find(n.id); if (vm != vol_mark_of.end() && vm->second) b.attrs.push_back({vol_col, vm->second}); }
+        if (vol_col != PE_NONE && vol_in.count(n.id)) b.attrs.push_back({vol_col, vol_gen});
         for (auto &pc : pref_cols) {                                                               // nodeset.go:69-82
             const std::string key = pc.first.substr(2);
             const std::map<std::string, std::string> *m = nullptr;
@@ -829,7 +828,7 @@ struct Scheduler {
         if (it == nodeSet.end()) { NodeInfo ni; ni.node = n; ni.avail = res; ni.last_cleanup = now; nodeSet[n->id] = ni; layout_dirty = true; }
         else { it->second.node = n; it->second.avail = res; touch(n->id); }
     }
-    void removeNode(const std::string &id) { if (nodeSet.erase(id)) layout_dirty = true; }   // nodeset.go:46-48
+    void removeNode(const std::string &id) { if (nodeSet.erase(id)) layout_dirty = true; vol_in.erase(id); }   // nodeset.go:46-48
 
     // ---- group descriptors <- the filters' SetTask (filter.go) --------------------
     struct TickBuf {
@@ -1133,10 +1132,13 @@ struct Scheduler {
     // (VolumeBook::staticFor); a group whose volume availability moves with every placement (scope SINGLE_NODE, sharing
     // NONE / ONE_WRITER writers) goes through scheduleVolumeGroupStepwise, because the reference re-evaluates the filter
     // inside its fill loop (scheduler.go:912-920).  Left-over tasks get the reference's exact explanation.
-    void mark_volume_nodes(const std::vector<std::string> &ids) {
+    void mark_volume_nodes(const std::vector<std::string> &ids) {       // ids ascending (built in nodeSet order)
         if (vol_col == PE_NONE) { vol_col = next_label_col++; layout_dirty = true; }
-        vol_gen++;                                    // marks of older sets never equal the new value: nothing to clear
-        for (auto &id : ids) { vol_mark_of[id] = vol_gen; touch(id); }
+        // only the rows whose membership changes are uploaded: consecutive groups with the same mounts (the tasks of one
+        // service, a tick's one-off tasks of one spec) mostly ask for the set that is already marked
+        std::set<std::string> next(ids.begin(), ids.end());
+        for (auto it = vol_in.begin(); it != vol_in.end();) { if (!next.count(*it)) { touch(*it); it = vol_in.erase(it); } else ++it; }
+        for (auto &id : ids) if (vol_in.insert(id).second) touch(id);
     }
     // taskFitNode's question for one task of this spec on each of `ids` (batches of pe_fit requests): ok[i] as pe_fit gives
     // it, fail[i*8..] the first failing filter.  A success RESERVES on the device; with `undo` those reservations are
@@ -1196,7 +1198,7 @@ struct Scheduler {
         const size_t k = grp.size();
         auto give_back = [&](size_t from) { for (size_t i = from; i < grp.size(); i++) enqueue(grp[i]); layout_dirty = true; return false; };
         std::set<std::string> allowed;                        // VolumesFilter's answer at tree-building time
-        for (auto &kv : vol_mark_of) if (kv.second == vol_gen) allowed.insert(kv.first);
+        allowed = vol_in;
         std::vector<uint32_t> cnt(PE_NUM_FILTERS, 0);
         // ---- the heap, in rank order
         std::vector<std::string> cand;
@@ -1216,7 +1218,7 @@ struct Scheduler {
                 if (!check(pe_schedule(eng, &tk, &pn, pf.data()), "pe_schedule")) return give_back(0);
                 if (pn == PE_NONE || pn >= idx_to_id.size()) { if (i == 0) cnt = pf; break; }
                 cand.push_back(idx_to_id[pn]);
-                vol_mark_of[idx_to_id[pn]] = 0;          // out of the set; the row upload also takes the reservation back
+                vol_in.erase(idx_to_id[pn]);             // out of the set; the row upload also takes the reservation back
                 touch(idx_to_id[pn]);
             }
         }

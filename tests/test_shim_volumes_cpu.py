@@ -215,3 +215,27 @@ def test_three_writers_one_single_writer_volume():
     dec, usage = out[0]
     assert sorted(k for k, v in dec.items() if v["state"] == "ASSIGNED") == ["t0"] and list(usage["vol0"]) == ["t0"]
     assert dec["t1"]["err"] == "no suitable node (cannot fulfill requested CSI volume mounts on 3 nodes)"   # n1, n2 and, after the wrap, n0 itself
+
+
+def test_volume_node_set_is_marked_incrementally():
+    """Fifty one-off tasks with the same read-only mount on 200 nodes: the node set VolumesFilter allows is written into
+    the node table once (its 100 rows); every later task finds it marked and only the rows the tick itself changed move."""
+    nodes = [node(f"n{i:03d}", description=description(resources=resources(8 * 10**9, 2**34),
+                                                        csi_info=[("plugA", f"a{i}", {"zone": "z1" if i % 2 else "z2"})])) for i in range(200)]
+    vols = [csi_volume("vol0", "data0", driver="plugA", scope="MULTI_NODE", sharing="ALL", volume_id="csi0", accessible_topology=[{"zone": "z1"}])]
+    c = Cluster(make_shim(), nodes=nodes, volumes=vols, services=["svc"])
+    c.run()
+    s0 = c.s.apply({"op": "device_check"})
+    for i in range(50):
+        c.create_task(task(f"t{i:02d}", service_id="svc", mounts=[cluster_mount("data0", "/a", read_only=True)]))
+    d = c.run()
+    assert all(v["state"] == "ASSIGNED" and int(v["node_id"][1:]) % 2 == 1 for v in d.values())
+    s1 = c.s.apply({"op": "device_check"})
+    assert s1["mismatch"] == []
+    # one full upload when the mark column is allocated (200 rows) and nothing else: placements move the device rows themselves
+    assert s1["full_uploads"] - s0["full_uploads"] == 1 and s1["rows_uploaded"] - s0["rows_uploaded"] == 200, (s0, s1)
+    for i in range(50, 100):
+        c.create_task(task(f"t{i:02d}", service_id="svc", mounts=[cluster_mount("data0", "/a", read_only=True)]))
+    c.run()
+    s2 = c.s.apply({"op": "device_check"})
+    assert s2["mismatch"] == [] and s2["full_uploads"] == s1["full_uploads"] and s2["rows_uploaded"] == s1["rows_uploaded"], (s1, s2)
