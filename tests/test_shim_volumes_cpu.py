@@ -8,7 +8,8 @@ import pytest
 
 import tests.test_oracle_volumes_scheduler as ref_scenarios
 from tests.oracle_lib import build_sched, build_shim_on_oracle
-from tests.sched_harness import Cluster, JsonScheduler, cluster_mount, comparable, csi_volume, description, node, placement, resources, task
+from tests.sched_harness import (Cluster, JsonScheduler, cluster_mount, comparable, csi_volume, description, discrete, host_port, named, node, placement,
+                                 resources, task)
 
 
 def make_shim():
@@ -39,7 +40,9 @@ def _node(rng, i):
         csi.append(("plugB", f"b{i}", {"zone": rng.choice(ZONES), "rack": rng.choice(["r1", "r2"])}))
     lr = random.Random(i * 7919 + 13)
     labels = {k: lr.choice(v) for k, v in (("az", ["a", "b", "c"]), ("rack", ["r1", "r2"])) if lr.random() < 0.85}
-    return node(f"n{i:03d}", state=rng.choice(["READY"] * 9 + ["DOWN"]), labels=labels, description=description(resources=resources(rng.randint(2, 8) * 10**9, 2**34), csi_info=csi))
+    gen = ([discrete("apple", lr.randint(1, 4))] if lr.random() < 0.6 else []) + ([named("gpu", f"g{j}") for j in range(lr.randint(1, 3))] if lr.random() < 0.4 else [])
+    return node(f"n{i:03d}", state=rng.choice(["READY"] * 9 + ["DOWN"]), labels=labels,
+                description=description(resources=resources(rng.randint(2, 8) * 10**9, 2**34, gen), csi_info=csi))
 
 
 def _volume(rng, i):
@@ -176,9 +179,11 @@ def test_random_replicated_services_on_volumes_that_count_their_users(seed):
             r_svc = random.Random(seed * 31 + j)          # the spec of a service is fixed: its tasks form one group
             mounts = [cluster_mount(r_svc.choice([f"data{r_svc.randrange(n_vol)}", "group:g1", "group:g2"]), r_svc.choice(["/a", "/b"]),
                                     read_only=r_svc.random() < 0.4) for _ in range(r_svc.randint(1, 2))]
-            res = resources(r_svc.choice([0, 5, 10, 20]) * 10**8, 0)
+            res = resources(r_svc.choice([0, 5, 10, 20]) * 10**8, 0, [discrete(r_svc.choice(["apple", "gpu"]), 1)] if r_svc.random() < 0.4 else [])
+            pl = placement(constraints=r_svc.choice([[], [], ["node.labels.az != c"], ["node.labels.rack == r1"]]), max_replicas=r_svc.choice([0, 0, 1, 2]))
+            ports = [host_port(r_svc.choice([80, 443]))] if r_svc.random() < 0.3 else None
             for _ in range(r2.randint(2, 7)):
-                new.append(task(f"t{next_id:04d}", service_id=f"svc{j}", spec_version=1, reservations=res, mounts=mounts))
+                new.append(task(f"t{next_id:04d}", service_id=f"svc{j}", spec_version=1, reservations=res, mounts=mounts, placement=pl, ports=ports))
                 next_id += 1
         for c in (cm, co):
             for t in new:

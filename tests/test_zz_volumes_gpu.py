@@ -48,3 +48,8 @@ def test_random_replicated_services_on_volumes_that_count_their_users_on_gpu(see
 def test_three_writers_one_single_writer_volume_on_gpu(monkeypatch):
     monkeypatch.setattr(cpu_twin, "make_shim", make_mirror)
     cpu_twin.test_three_writers_one_single_writer_volume()
+
+
+def test_volume_node_set_is_marked_incrementally_on_gpu(monkeypatch):
+    monkeypatch.setattr(cpu_twin, "make_shim", make_mirror)
+    cpu_twin.test_volume_node_set_is_marked_incrementally()
