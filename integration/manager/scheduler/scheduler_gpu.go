@@ -72,6 +72,7 @@ type gpuEngine struct {
 	volCol    uint32            // C.PE_NONE until the first group with cluster mounts
 	volIn     map[string]struct{} // the nodes that carry volMark in that column (every other row holds 0 = "")
 	leafAlsoInVolumeSet bool   // a preference group with cluster mounts: every leaf visit carries the volume term too
+	leafStepwise        bool   // ... and, when its volumes count their users, walks the fill loop itself
 }
 
 func mustNewGPUEngine() *gpuEngine {
@@ -879,6 +880,124 @@ func (a rankKey) less(b rankKey) bool {
 	return a.id < b.id
 }
 
+// rankOf is the rank key of a node for tasks of t's spec.
+func (s *Scheduler) rankOf(id string, t *api.Task, now time.Time) rankKey {
+	ni, _ := s.nodeSet.nodeInfo(id)
+	fl := ni.countRecentFailures(now, t)
+	if fl < maxFailures {
+		fl = 0
+	}
+	return rankKey{fl, ni.ActiveTasksCountByService[t.ServiceID], ni.ActiveTasksCount, id}
+}
+
+// probeBest: the `want` best feasible nodes of (leaf terms AND the volume set), in rank order: successive one-task groups,
+// each answer taken out of the volume set and its reservation taken back (the row goes up again before the next call).
+// firstFail: the counters of the first question when it found no node.  errUnsupported wraps an encoder refusal.
+func (s *Scheduler) probeBest(t *api.Task, leafTerms []C.pe_constraint, want int, now time.Time) (cand []string, firstFail []C.uint32_t, err error) {
+	e := s.gpu
+	var b tickBuf
+	if err = s.encodeGroup([]*api.Task{t}, &b, now); err != nil {
+		return nil, nil, fmt.Errorf("%w: %v", errUnsupported, err)
+	}
+	g := &b.groups[len(b.groups)-1]
+	if g.con_cnt == 0 {
+		g.con_off = C.uint32_t(len(b.cons))
+	}
+	b.cons = append(b.cons, leafTerms...)
+	b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(e.volCol), value: C.uint32_t(volMark)})
+	g.leaf_cnt = C.uint32_t(len(leafTerms) + 1)
+	for i := 0; i < want; i++ {
+		if err = e.flushRows(&s.nodeSet); err != nil {
+			return
+		}
+		var pn C.uint32_t = C.PE_NONE
+		pf := make([]C.uint32_t, C.PE_NUM_FILTERS)
+		tick := b.view()
+		if rc := C.pe_schedule(e.h, &tick, &pn, ptr(pf)); rc != C.PE_OK {
+			return nil, nil, e.err("pe_schedule")
+		}
+		if pn == C.PE_NONE {
+			if i == 0 {
+				firstFail = pf
+			}
+			break
+		}
+		id := e.order[pn]
+		cand = append(cand, id)
+		delete(e.volIn, id)
+		e.nodeChanged(id)
+	}
+	return
+}
+
+var errUnsupported = errors.New("unsupported by the placement engine")
+
+// fillStepwise is scheduleNTasksOnNodes (scheduler.go:844-924) over an ordered node list with one engine question per step:
+// "does this node still pass, and if so the next task goes there" = pe_fit (device filters + reservation), then
+// VolumesFilter here -- the pipeline's order, so cnt moves as the reference's failure counters do (cleared by every pass).
+// Returns the tasks placed (a prefix of ts) and whether a re-check passed.
+func (s *Scheduler) fillStepwise(ts []*api.Task, cand []string, cnt []C.uint32_t, group map[string]*api.Task,
+	decisions map[string]schedulingDecision, now time.Time) (placed int, passed bool, err error) {
+	k, m := len(ts), len(cand)
+	if k == 0 || m == 0 {
+		return
+	}
+	f := &VolumesFilter{vs: s.volumes}
+	failed := make([]bool, m)
+	it := 0
+	if ok, _, ferr := s.fitMany(ts[0], cand[:1], false, now); ferr != nil {
+		return 0, false, ferr
+	} else if ok[0] != 1 {
+		return 0, false, errors.New("placement engine: the best node of a group does not fit its first task")
+	}
+fill:
+	for {
+		nid := cand[it%m]
+		s.assign(ts[placed], nid, group, decisions)
+		placed++
+		if placed == k {
+			return
+		}
+		if it+1 < m {
+			if s.rankOf(cand[(it+1)%m], ts[0], now).lessNoTie(s.rankOf(nid, ts[0], now)) { // first pass: level the nodes
+				it++
+			}
+		} else {
+			it++ // later passes: one task per node
+		}
+		for orig := it; ; {
+			if i := it % m; !failed[i] {
+				ok, fail, ferr := s.fitMany(ts[placed], cand[i:i+1], false, now)
+				if ferr != nil {
+					return placed, passed, ferr
+				}
+				ni, _ := s.nodeSet.nodeInfo(cand[i])
+				f.SetTask(ts[placed])
+				if ok[0] == 1 && f.Check(&ni) {
+					for j := range cnt {
+						cnt[j] = 0 // pipeline.go:64-66
+					}
+					passed = true
+					continue fill
+				}
+				if ok[0] == 1 {
+					cnt[C.PE_F_VOLUMES]++
+					s.gpu.nodeChanged(cand[i]) // the reservation is taken back
+				} else {
+					for j := range cnt {
+						cnt[j] += fail[j]
+					}
+				}
+				failed[i] = true
+			}
+			it++
+			if it-orig == m {
+				return // none of the nodes meets the constraints any more
+			}
+		}
+	}
+}
+
 // scheduleVolumeGroupStepwise: a group whose volume availability moves with every placement.  The reference re-runs the
 // whole pipeline, VolumesFilter included, on the next node before every further placement (scheduler.go:912-920); this
 // walks that loop and asks the engine one question per step (DESIGN.md 4.7).  s.gpu.markVolumeNodes(allowed) was called.
@@ -889,116 +1008,33 @@ func (s *Scheduler) scheduleVolumeGroupStepwise(ctx context.Context, ts []*api.T
 	for _, id := range allowedIDs {
 		allowed[id] = struct{}{}
 	}
-	f := &VolumesFilter{vs: s.volumes}
 	cnt := make([]C.uint32_t, C.PE_NUM_FILTERS)
-	// ---- the heap of the k best feasible nodes, in rank order: k one-task groups on the allowed set
-	var cand []string
-	{
-		var b tickBuf
-		if err := s.encodeGroup([]*api.Task{t}, &b, now); err != nil {
-			s.noSuitableNodeWith(ctx, group, decisions, "unsupported by the placement engine: "+err.Error())
-			return nil
-		}
-		g := &b.groups[len(b.groups)-1]
-		if g.con_cnt == 0 {
-			g.con_off = C.uint32_t(len(b.cons))
-		}
-		b.cons = append(b.cons, C.pe_constraint{col: C.uint32_t(e.volCol), value: C.uint32_t(volMark)})
-		g.leaf_cnt = 1
-		for i := 0; i < k; i++ {
-			if err := e.flushRows(&s.nodeSet); err != nil {
-				return err
-			}
-			var pn C.uint32_t = C.PE_NONE
-			pf := make([]C.uint32_t, C.PE_NUM_FILTERS)
-			tick := b.view()
-			if rc := C.pe_schedule(e.h, &tick, &pn, ptr(pf)); rc != C.PE_OK {
-				return e.err("pe_schedule")
-			}
-			if pn == C.PE_NONE {
-				if i == 0 {
-					cnt = pf
-				}
-				break
-			}
-			id := e.order[pn]
-			cand = append(cand, id)
-			delete(e.volIn, id) // out of the set; the row upload also takes the reservation back
-			e.nodeChanged(id)
-		}
+	cand, firstFail, err := s.probeBest(t, nil, k, now)
+	if errors.Is(err, errUnsupported) {
+		s.noSuitableNodeWith(ctx, group, decisions, err.Error())
+		return nil
+	} else if err != nil {
+		return err
 	}
-	if len(cand) == 0 {
+	if len(cand) == 0 { // nothing passed: every node is counted by its first failing filter
+		if firstFail != nil {
+			cnt = firstFail
+		}
 		if err := s.countExcluded(t, excluded, cnt, now); err != nil {
 			return err
 		}
 		s.noSuitableNodeWith(ctx, group, decisions, explainCounters(cnt))
 		return nil
 	}
-	key := func(id string) rankKey {
-		ni, _ := s.nodeSet.nodeInfo(id)
-		fl := ni.countRecentFailures(now, t)
-		if fl < maxFailures {
-			fl = 0
-		}
-		return rankKey{fl, ni.ActiveTasksCountByService[t.ServiceID], ni.ActiveTasksCount, id}
-	}
-	firstKey := key(cand[0])
-	m := len(cand)
-	failed := make([]bool, m)
-	treeCountersStand := true
-	it, placed := 0, 0
-	if ok, _, err := s.fitMany(ts[0], cand[:1], false, now); err != nil {
+	firstKey := s.rankOf(cand[0], t, now)
+	placed, passed, err := s.fillStepwise(ts, cand, cnt, group, decisions, now)
+	if err != nil {
 		return err
-	} else if ok[0] != 1 {
-		return errors.New("placement engine: the best node of a group does not fit its first task")
 	}
-fill:
-	for {
-		nid := cand[it%m]
-		s.assign(ts[placed], nid, group, decisions)
-		placed++
-		if placed == k {
-			return nil
-		}
-		if it+1 < m {
-			if key(cand[(it+1)%m]).lessNoTie(key(nid)) { // first pass: level the nodes
-				it++
-			}
-		} else {
-			it++ // later passes: one task per node
-		}
-		for orig := it; ; {
-			if i := it % m; !failed[i] {
-				ok, fail, err := s.fitMany(ts[placed], cand[i:i+1], false, now)
-				if err != nil {
-					return err
-				}
-				ni, _ := s.nodeSet.nodeInfo(cand[i])
-				f.SetTask(ts[placed])
-				if ok[0] == 1 && f.Check(&ni) {
-					for j := range cnt {
-						cnt[j] = 0 // pipeline.go:64-66
-					}
-					treeCountersStand = false
-					continue fill
-				}
-				if ok[0] == 1 {
-					cnt[C.PE_F_VOLUMES]++
-					e.nodeChanged(cand[i]) // the reservation is taken back
-				} else {
-					for j := range cnt {
-						cnt[j] += fail[j]
-					}
-				}
-				failed[i] = true
-			}
-			it++
-			if it-orig == m {
-				break fill // none of the nodes meets the constraints any more
-			}
-		}
+	if placed == k {
+		return nil
 	}
-	if treeCountersStand {
+	if !passed {
 		// no re-check passed: the tree building's counters still stand.  Replay its walk (ascending node ID): the pipeline
 		// ran on every node while the heap had room, afterwards only on nodes ranking ahead of the heap's worst
 		// (nodeset.go:103-121); a pass clears the counters.
@@ -1013,7 +1049,7 @@ fill:
 			return err
 		}
 		tree := make([]C.uint32_t, C.PE_NUM_FILTERS)
-		var heap []rankKey // the worst at heap[0]
+		var heap []rankKey
 		worst := func() int {
 			w := 0
 			for i := range heap {
@@ -1028,7 +1064,7 @@ fill:
 			first := id == cand[0]
 			rk, q := firstKey, 0
 			if !first {
-				rk, q = key(id), j
+				rk, q = s.rankOf(id, t, now), j
 				j++
 			}
 			w := -1
@@ -1072,10 +1108,6 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 		s.noSuitableNodeWith(ctx, group, decisions, "unsupported by the placement engine: "+why)
 	}
 	prefs := len(s.preferenceLevels(t)) != 0
-	if prefs && len(ts) > 1 && !s.volumesStaticFor(t) {
-		refuse("placement preferences on a group whose cluster volumes count their users")
-		return
-	}
 	requeue := func(err error) {
 		log.G(ctx).WithError(err).Error("placement engine")
 		for _, x := range group {
@@ -1102,8 +1134,9 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 		// the tree's branches and task sums do not depend on the pipeline (nodeset.go:59-101): the preference walk runs
 		// unchanged and every leaf visit carries the volume term next to the leaf's own terms (fillLeaf)
 		s.gpu.leafAlsoInVolumeSet = true
+		s.gpu.leafStepwise = len(ts) > 1 && !s.volumesStaticFor(t) // the walk of the leaf's heap, step by step (fillLeafStepwise)
 		s.schedulePreferenceGroup(ctx, group, decisions, now)
-		s.gpu.leafAlsoInVolumeSet = false
+		s.gpu.leafAlsoInVolumeSet, s.gpu.leafStepwise = false, false
 		return
 	}
 	if len(ts) > 1 && !s.volumesStaticFor(t) {
@@ -1197,6 +1230,8 @@ type prefTree struct {
 	tasks int
 	next  map[string]*prefTree
 	leaf  []C.pe_constraint // the (column == value) path that names a leaf
+	cand  []string          // fillLeafStepwise: the leaf's heap (decision_tree.go), best first
+	built bool
 }
 
 type prefWalk struct {
@@ -1204,11 +1239,67 @@ type prefWalk struct {
 	group    map[string]*api.Task
 	lastFail []C.uint32_t
 	failed   error
+	size     int // maxAssignments of the tree building: the size of every leaf's heap
+}
+
+// fillLeafStepwise: a leaf visit of a group whose cluster volumes count their users.  The leaf's heap is made once -- the k
+// best nodes of (leaf AND volume set) as the tree building saw them: nothing has touched this leaf's nodes since, other
+// leaves hold other nodes -- and every visit walks scheduleNTasksOnNodes over it with one engine question per step.  A
+// visit after the first finds the heap collapsed (decision_tree.go:30-45): every node is put to the pipeline again, the
+// ones that fail leave the heap for good, the rest are ordered by their rank of now.
+func (s *Scheduler) fillLeafStepwise(ctx context.Context, n int, leaf *prefTree, w *prefWalk, decisions map[string]schedulingDecision, now time.Time) int {
+	m := min(n, len(w.pending))
+	if m <= 0 || w.failed != nil {
+		return 0
+	}
+	sub, t := w.pending[:m], w.pending[0]
+	if !leaf.built {
+		cand, _, err := s.probeBest(t, leaf.leaf, w.size, now)
+		if errors.Is(err, errUnsupported) {
+			return 0
+		} else if err != nil {
+			w.failed = err
+			return 0
+		}
+		leaf.cand, leaf.built = cand, true
+	} else {
+		ok, _, err := s.fitMany(t, leaf.cand, true, now)
+		if err != nil {
+			w.failed = err
+			return 0
+		}
+		f := &VolumesFilter{vs: s.volumes}
+		f.SetTask(t)
+		var kept []rankKey
+		for i, id := range leaf.cand {
+			if ni, _ := s.nodeSet.nodeInfo(id); ok[i] == 1 && f.Check(&ni) {
+				kept = append(kept, s.rankOf(id, t, now))
+			}
+		}
+		sort.Slice(kept, func(i, j int) bool { return kept[i].less(kept[j]) })
+		leaf.cand = leaf.cand[:0]
+		for _, rk := range kept {
+			leaf.cand = append(leaf.cand, rk.id)
+		}
+	}
+	cnt := make([]C.uint32_t, C.PE_NUM_FILTERS)
+	placed, _, err := s.fillStepwise(sub, leaf.cand, cnt, w.group, decisions, now)
+	if err != nil {
+		w.failed = err
+	}
+	w.pending = w.pending[placed:]
+	if placed < m {
+		w.lastFail = cnt
+	}
+	return placed
 }
 
 // fillLeaf: n tasks on one leaf = one engine group with leaf_cnt > 0 (the leaf's k best feasible nodes and
 // scheduleNTasksOnNodes over them, on the device).  Why this is exact: DESIGN.md, "Placement preferences".
 func (s *Scheduler) fillLeaf(ctx context.Context, n int, leaf *prefTree, w *prefWalk, decisions map[string]schedulingDecision, now time.Time) int {
+	if s.gpu.leafStepwise {
+		return s.fillLeafStepwise(ctx, n, leaf, w, decisions, now)
+	}
 	m := n
 	if m > len(w.pending) {
 		m = len(w.pending)
@@ -1347,7 +1438,7 @@ func (s *Scheduler) schedulePreferenceGroup(ctx context.Context, group map[strin
 		tr.tasks += int(tasks[i])
 		tr.leaf = path
 	}
-	w := &prefWalk{pending: ts, group: group}
+	w := &prefWalk{pending: ts, group: group, size: len(ts)}
 	s.scheduleNTasksOnSubtreeGPU(ctx, len(ts), root, w, decisions, now)
 	if w.failed != nil {
 		requeue(w.failed)

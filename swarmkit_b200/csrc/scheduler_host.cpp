@@ -550,6 +550,7 @@ struct Scheduler {
     static const uint32_t vol_gen = 1;   // the column's value on the rows of the set (0 = "" on every other row)
     std::set<std::string> vol_in;        // the nodes that carry it, written into the row by encode_row
     bool leaf_also_in_volume_set = false; // a preference group with cluster mounts: every leaf visit carries the volume term too
+    bool leaf_stepwise = false;           // ... and, when its volumes count their users, walks the fill loop itself (fillLeafStepwise)
     int64_t now = 0;
 
     // ---- dictionaries (exact interning)
@@ -1193,79 +1194,75 @@ struct Scheduler {
     //     VolumesFilter here -- the pipeline's order, so the failure counters come out as the reference's;
     //   * nodeLess between two nodes of the heap (scheduler.go:708-734) is three integer compares on NodeInfo.
     // O(k) engine calls: for the handful of replicas a service with its own volumes has, not a throughput path.
-    bool scheduleVolumeGroupStepwise(std::vector<TaskP> &grp, const std::vector<std::string> &excluded, std::map<std::string, Decision> &decisions) {
-        const TaskP t = grp[0];
-        const size_t k = grp.size();
-        auto give_back = [&](size_t from) { for (size_t i = from; i < grp.size(); i++) enqueue(grp[i]); layout_dirty = true; return false; };
-        std::set<std::string> allowed;                        // VolumesFilter's answer at tree-building time
-        allowed = vol_in;
-        std::vector<uint32_t> cnt(PE_NUM_FILTERS, 0);
-        // ---- the heap, in rank order
-        std::vector<std::string> cand;
-        {
-            TickBuf b;
-            fatal.clear();
-            std::vector<TaskP> one{t};
-            if (!encode_group(one, b)) { if (unsupported.empty()) unsupported = fatal; noSuitableNode(grp, "unsupported by the placement engine: " + fatal, decisions); fatal.clear(); return true; }
-            pe_group &g = b.groups.back();
-            if (g.con_cnt == 0) g.con_off = (uint32_t)b.cons.size();
-            b.cons.push_back({vol_col, vol_gen, 0});
-            g.leaf_cnt = 1;
-            for (size_t i = 0; i < k; i++) {
-                if (!flush_rows()) return give_back(0);
-                uint32_t pn = PE_NONE; std::vector<uint32_t> pf(PE_NUM_FILTERS, 0);
-                pe_tick tk = b.view();
-                if (!check(pe_schedule(eng, &tk, &pn, pf.data()), "pe_schedule")) return give_back(0);
-                if (pn == PE_NONE || pn >= idx_to_id.size()) { if (i == 0) cnt = pf; break; }
-                cand.push_back(idx_to_id[pn]);
-                vol_in.erase(idx_to_id[pn]);             // out of the set; the row upload also takes the reservation back
-                touch(idx_to_id[pn]);
-            }
+    // nodeLess (scheduler.go:708-734) + the canonical tie-break, as a key: recent failures count only from maxFailures up
+    struct RankKey {
+        int f, s, a; std::string id;
+        bool less_no_tie(const RankKey &o) const { if (f != o.f) return f < o.f; if (s != o.s) return s < o.s; return a < o.a; }
+        bool operator<(const RankKey &o) const { if (less_no_tie(o)) return true; if (o.less_no_tie(*this)) return false; return id < o.id; }
+    };
+    RankKey rank_key(const NodeInfo &n, const Task &t) const {
+        const int f = n.countRecentFailures(now, SvcVer{t.service, t.has_spec_version ? t.spec_version : 0});
+        auto sv = n.by_service.find(t.service);
+        return RankKey{f >= kMaxFailures ? f : 0, sv == n.by_service.end() ? 0 : sv->second, n.active, n.node->id};
+    }
+    // The `want` best feasible nodes of (leaf terms AND the volume set), in rank order: successive one-task groups, each
+    // answer taken out of the volume set and its reservation taken back (the row goes up again before the next call).
+    // 0 = engine failure, 1 = ok, 2 = the group cannot be encoded (reason in `fatal`).  first_fail: the counters of the
+    // first question when it found no node.
+    int probe_best(const TaskP &t, const std::vector<pe_constraint> &leaf_terms, size_t want, std::vector<std::string> &cand, std::vector<uint32_t> *first_fail) {
+        TickBuf b;
+        fatal.clear();
+        std::vector<TaskP> one{t};
+        if (!encode_group(one, b)) return 2;
+        pe_group &g = b.groups.back();
+        if (g.con_cnt == 0) g.con_off = (uint32_t)b.cons.size();
+        b.cons.insert(b.cons.end(), leaf_terms.begin(), leaf_terms.end());
+        b.cons.push_back({vol_col, vol_gen, 0});
+        g.leaf_cnt = (uint32_t)leaf_terms.size() + 1;
+        for (size_t i = 0; i < want; i++) {
+            if (!flush_rows()) return 0;
+            uint32_t pn = PE_NONE; std::vector<uint32_t> pf(PE_NUM_FILTERS, 0);
+            pe_tick tk = b.view();
+            if (!check(pe_schedule(eng, &tk, &pn, pf.data()), "pe_schedule")) return 0;
+            if (pn == PE_NONE || pn >= idx_to_id.size()) { if (i == 0 && first_fail) *first_fail = pf; break; }
+            cand.push_back(idx_to_id[pn]);
+            vol_in.erase(idx_to_id[pn]);
+            touch(idx_to_id[pn]);
         }
-        if (cand.empty()) {                                   // nothing passed: every node is counted by its first failing filter
-            if (!count_excluded(t, excluded, cnt)) return give_back(0);
-            noSuitableNode(grp, explain(cnt.data()), decisions);
-            return true;
-        }
-        // ---- scheduleNTasksOnNodes, scheduler.go:844-924
-        // nodeLess (scheduler.go:708-734) + the canonical tie-break, as a key: recent failures count only from maxFailures up
-        const SvcVer key{t->service, t->has_spec_version ? t->spec_version : 0};
-        struct RankKey {
-            int f, s, a; std::string id;
-            bool less_no_tie(const RankKey &o) const { if (f != o.f) return f < o.f; if (s != o.s) return s < o.s; return a < o.a; }
-            bool operator<(const RankKey &o) const { if (less_no_tie(o)) return true; if (o.less_no_tie(*this)) return false; return id < o.id; }
-        };
-        auto rank_key = [&](const NodeInfo &n) {
-            const int f = n.countRecentFailures(now, key);
-            auto sv = n.by_service.find(t->service);
-            return RankKey{f >= kMaxFailures ? f : 0, sv == n.by_service.end() ? 0 : sv->second, n.active, n.node->id};
-        };
-        auto nodeLess = [&](const NodeInfo &a, const NodeInfo &b) { return rank_key(a).less_no_tie(rank_key(b)); };
-        const RankKey first_key = rank_key(nodeSet[cand[0]]);
-        const size_t m = cand.size();
+        return 1;
+    }
+    // scheduleNTasksOnNodes (scheduler.go:844-924) over an ordered node list with one engine question per step: "does this
+    // node still pass, and if so the next task goes there" = pe_fit (device filters + reservation), then VolumesFilter
+    // here -- the pipeline's order, so `cnt` moves as the reference's failure counters do (cleared by every pass,
+    // pipeline.go:64-66; `passed` says whether one happened).  Returns the tasks placed (a prefix of `tasks`), -1 on an
+    // engine failure.
+    int fill_stepwise(const std::vector<TaskP> &tasks, const std::vector<std::string> &cand, std::vector<uint32_t> &cnt, bool &passed,
+                      std::map<std::string, Decision> &decisions) {
+        const size_t k = tasks.size(), m = cand.size();
+        if (!k || !m) return 0;
         std::vector<char> failed(m, 0);
         std::vector<uint8_t> ok; std::vector<uint32_t> fail;
-        bool tree_counters_stand = true;      // no Process() has passed since the tree was built
         size_t it = 0, placed = 0;
-        // (the first node passed the pipeline when the tree was built and nothing has changed: pe_fit reserves there)
-        if (!fit_many(grp[0], {cand[0]}, ok, fail, false)) return give_back(0);
-        if (ok[0] != 1) { fatal = "placement engine: the best node of a group does not fit its first task"; return give_back(0); }
+        // (the first node is taken without a question: it passed when the list was made; pe_fit reserves there)
+        if (!fit_many(tasks[0], {cand[0]}, ok, fail, false)) return -1;
+        if (ok[0] != 1) { fatal = "placement engine: the best node of a group does not fit its first task"; return -1; }
         for (;;) {
             const std::string &nid = cand[it % m];
-            assign_with_volumes(grp[placed], nid, decisions);
+            assign_with_volumes(tasks[placed], nid, decisions);
             placed++;
-            if (placed == k) return true;
-            if (it + 1 < m) { if (nodeLess(nodeSet[cand[(it + 1) % m]], nodeSet[nid])) it++; }   // first pass: level the nodes
-            else it++;                                                                                // later passes: one task per node
+            if (placed == k) return (int)placed;
+            if (it + 1 < m) {                                                                         // first pass: level the nodes
+                if (rank_key(nodeSet[cand[(it + 1) % m]], *tasks[0]).less_no_tie(rank_key(nodeSet[nid], *tasks[0]))) it++;
+            } else it++;                                                                              // later passes: one task per node
             const size_t orig = it;
             bool found = false;
             while (!found) {
                 const size_t i = it % m;
                 if (!failed[i]) {
-                    if (!fit_many(grp[placed], {cand[i]}, ok, fail, false)) return give_back(placed);
-                    if (ok[0] == 1 && volumes.filterCheck(*grp[placed], *nodeSet[cand[i]].node)) {
-                        std::fill(cnt.begin(), cnt.end(), 0u);                                      // pipeline.go:64-66
-                        tree_counters_stand = false;
+                    if (!fit_many(tasks[placed], {cand[i]}, ok, fail, false)) return -1;
+                    if (ok[0] == 1 && volumes.filterCheck(*tasks[placed], *nodeSet[cand[i]].node)) {
+                        std::fill(cnt.begin(), cnt.end(), 0u);
+                        passed = true;
                         found = true;
                         break;
                     }
@@ -1276,10 +1273,33 @@ struct Scheduler {
                 it++;
                 if (it - orig == m) break;                     // none of the nodes meets the constraints any more
             }
-            if (!found) break;
+            if (!found) return (int)placed;
         }
+    }
+    bool scheduleVolumeGroupStepwise(std::vector<TaskP> &grp, const std::vector<std::string> &excluded, std::map<std::string, Decision> &decisions) {
+        const TaskP t = grp[0];
+        const size_t k = grp.size();
+        auto give_back = [&](size_t from) { for (size_t i = from; i < grp.size(); i++) enqueue(grp[i]); layout_dirty = true; return false; };
+        const std::set<std::string> allowed = vol_in;         // VolumesFilter's answer at tree-building time
+        std::vector<uint32_t> cnt(PE_NUM_FILTERS, 0);
+        // ---- the heap, in rank order
+        std::vector<std::string> cand;
+        const int pr = probe_best(t, {}, k, cand, &cnt);
+        if (pr == 0) return give_back(0);
+        if (pr == 2) { if (unsupported.empty()) unsupported = fatal; noSuitableNode(grp, "unsupported by the placement engine: " + fatal, decisions); fatal.clear(); return true; }
+        if (cand.empty()) {                                   // nothing passed: every node is counted by its first failing filter
+            if (!count_excluded(t, excluded, cnt)) return give_back(0);
+            noSuitableNode(grp, explain(cnt.data()), decisions);
+            return true;
+        }
+        const RankKey first_key = rank_key(nodeSet[cand[0]], *t);
+        bool passed = false;                                  // has a Process() passed since the tree was built?
+        const int res = fill_stepwise(grp, cand, cnt, passed, decisions);
+        if (res < 0) { size_t done = 0; for (auto &x : grp) if (decisions.count(x->id)) done++; return give_back(done); }
+        const size_t placed = (size_t)res;
+        if (placed == k) return true;
         std::vector<TaskP> left(grp.begin() + (long)placed, grp.end());
-        if (tree_counters_stand) {
+        if (!passed) {
             // No re-check passed, so what the tree building left in the counters still stands (pipeline.go:55-68): the
             // failures after the last node that passed, among the nodes the tree building RAN the pipeline on -- every node
             // while the heap had room, afterwards only nodes that rank ahead of the heap's worst (nodeset.go:103-121).
@@ -1288,6 +1308,7 @@ struct Scheduler {
             // rank keys are three integers of NodeInfo (cand[0]'s were saved before it took the task).
             std::vector<std::string> ids;
             for (auto &kv : nodeSet) if (kv.first != cand[0]) ids.push_back(kv.first);
+            std::vector<uint8_t> ok; std::vector<uint32_t> fail;
             if (!fit_many(left[0], ids, ok, fail, true)) return give_back(placed);
             std::vector<uint32_t> tree(PE_NUM_FILTERS, 0);
             auto worse = [](const RankKey &a, const RankKey &b) { return a < b; };   // max-heap: the worst on top
@@ -1295,7 +1316,7 @@ struct Scheduler {
             size_t j = 0;
             for (auto &kv : nodeSet) {
                 const bool is_first = kv.first == cand[0];
-                const RankKey rk = is_first ? first_key : rank_key(kv.second);
+                const RankKey rk = is_first ? first_key : rank_key(kv.second, *t);
                 const size_t q = is_first ? 0 : j++;
                 if (heap.size() >= k && !(rk < heap.front())) continue;              // the pipeline was not run on it
                 const bool passes = is_first || (ok[q] == 1 && allowed.count(kv.first));
@@ -1321,19 +1342,18 @@ struct Scheduler {
             return true;
         };
         const bool prefs = !preference_levels(t).empty();
-        if (prefs && grp.size() > 1 && !volumes.staticFor(t))
-            return refuse("placement preferences on a group whose cluster volumes count their users (task " + t.id + ")");
         auto give_back = [&](const std::vector<TaskP> &ts) { for (auto &x : ts) enqueue(x); layout_dirty = true; };
         std::vector<std::string> allowed, excluded;
         for (auto &kv : nodeSet) (volumes.filterCheck(t, *kv.second.node) ? allowed : excluded).push_back(kv.first);
         mark_volume_nodes(allowed);
         if (prefs) {
             // the tree's branches and task sums do not depend on the pipeline (nodeset.go:59-101 counts every node); each
-            // leaf visit is the leaf's engine group cut down to the volume set as well (same argument as for one group:
-            // the answer of VolumesFilter cannot move while this group is placed)
+            // leaf visit is the leaf's engine group cut down to the volume set as well when the answer of VolumesFilter
+            // cannot move while this group is placed, and a walk of the leaf's heap step by step when it can
             leaf_also_in_volume_set = true;
+            leaf_stepwise = grp.size() > 1 && !volumes.staticFor(t);
             const bool ok = schedulePreferenceGroup(grp, decisions);
-            leaf_also_in_volume_set = false;
+            leaf_also_in_volume_set = leaf_stepwise = false;
             return ok;
         }
         if (grp.size() > 1 && !volumes.staticFor(t)) return scheduleVolumeGroupStepwise(grp, excluded, decisions);
@@ -1396,13 +1416,53 @@ struct Scheduler {
         int tasks = 0;
         std::map<std::string, std::unique_ptr<PrefTree>> next;   // canonical branch order: ascending label value, "" first
         std::vector<pe_constraint> leaf;                          // the (column == value) path that names a leaf
+        std::vector<std::string> cand;                            // fillLeafStepwise: the leaf's heap (decision_tree.go), best first
+        bool cand_built = false;
     };
     struct PrefWalk {
         std::vector<TaskP> pending;            // ascending task ID
         std::vector<uint32_t> last_fail;       // failure counters of the last visit that came back short
         bool have_fail = false, engine_failed = false;
+        size_t group_size = 0;                 // maxAssignments of the tree building: the size of every leaf's heap
     };
+    // A leaf visit of a group whose cluster volumes count their users: the leaf's heap is made once -- the k best nodes of
+    // (leaf AND volume set) as the tree building saw them: nothing has touched this leaf's nodes since, other leaves hold
+    // other nodes -- and every visit walks scheduleNTasksOnNodes over it with one engine question per step.  A visit after
+    // the first finds the heap collapsed (decision_tree.go:30-45): every node is put to the pipeline again, the ones that
+    // fail leave the heap for good, the rest are ordered by their rank of now.
+    int fillLeafStepwise(int n, PrefTree &leaf, PrefWalk &w, std::map<std::string, Decision> &decisions) {
+        const size_t m = std::min<size_t>((size_t)std::max(n, 0), w.pending.size());
+        if (m == 0 || w.engine_failed) return 0;
+        std::vector<TaskP> sub(w.pending.begin(), w.pending.begin() + (long)m);
+        const TaskP t = sub[0];
+        if (!leaf.cand_built) {
+            const int pr = probe_best(t, leaf.leaf, w.group_size, leaf.cand, nullptr);
+            if (pr == 0) { w.engine_failed = true; return 0; }
+            if (pr == 2) { if (unsupported.empty()) unsupported = fatal; fatal.clear(); return 0; }
+            leaf.cand_built = true;
+        } else {
+            std::vector<uint8_t> ok; std::vector<uint32_t> fail;
+            if (!fit_many(t, leaf.cand, ok, fail, true)) { w.engine_failed = true; return 0; }
+            std::vector<RankKey> kept;
+            for (size_t i = 0; i < leaf.cand.size(); i++)
+                if (ok[i] == 1 && volumes.filterCheck(*t, *nodeSet[leaf.cand[i]].node)) kept.push_back(rank_key(nodeSet[leaf.cand[i]], *t));
+            std::sort(kept.begin(), kept.end());
+            leaf.cand.clear();
+            for (auto &rk : kept) leaf.cand.push_back(rk.id);
+        }
+        if (leaf.cand.empty()) return 0;
+        std::vector<uint32_t> cnt(PE_NUM_FILTERS, 0);
+        bool passed = false;
+        const int res = fill_stepwise(sub, leaf.cand, cnt, passed, decisions);
+        size_t placed = 0;
+        if (res < 0) { w.engine_failed = true; for (auto &x : sub) if (decisions.count(x->id)) placed++; }
+        else placed = (size_t)res;
+        w.pending.erase(w.pending.begin(), w.pending.begin() + (long)placed);
+        if (placed < m) { w.last_fail = cnt; w.have_fail = true; }
+        return (int)placed;
+    }
     int fillLeaf(int n, PrefTree &leaf, PrefWalk &w, std::map<std::string, Decision> &decisions) {
+        if (leaf_stepwise) return fillLeafStepwise(n, leaf, w, decisions);
         const size_t m = std::min<size_t>((size_t)std::max(n, 0), w.pending.size());
         if (m == 0 || w.engine_failed) return 0;
         std::vector<TaskP> sub(w.pending.begin(), w.pending.begin() + (long)m);
@@ -1486,6 +1546,7 @@ struct Scheduler {
         }
         PrefWalk w;
         w.pending = grp;
+        w.group_size = grp.size();
         scheduleNTasksOnSubtree((int)grp.size(), root, w, decisions);
         if (w.engine_failed) { give_back(w.pending); return false; }
         if (!w.pending.empty()) noSuitableNode(w.pending, w.have_fail ? explain(w.last_fail.data()) : std::string(), decisions);

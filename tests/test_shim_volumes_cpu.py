@@ -163,7 +163,8 @@ def test_random_replicated_services_on_static_volumes(seed):
 def test_random_replicated_services_on_volumes_that_count_their_users(seed):
     """Groups of k > 1 identical tasks on volumes of every scope / sharing, writers included: availability moves with
     every placement, the reference re-runs VolumesFilter inside its fill loop (scheduler.go:912-920) and the shim walks
-    that loop one engine question at a time (scheduleVolumeGroupStepwise)."""
+    that loop one engine question at a time (scheduleVolumeGroupStepwise); half the services spread over node labels as
+    well, so the walk happens inside the leaves of their preference tree (fillLeafStepwise)."""
     rng = random.Random(9900 + seed)
     n_nodes, n_vol = rng.randint(3, 24), rng.randint(2, 8)
     nodes = [_node(rng, i) for i in range(n_nodes)]
@@ -180,7 +181,8 @@ def test_random_replicated_services_on_volumes_that_count_their_users(seed):
             mounts = [cluster_mount(r_svc.choice([f"data{r_svc.randrange(n_vol)}", "group:g1", "group:g2"]), r_svc.choice(["/a", "/b"]),
                                     read_only=r_svc.random() < 0.4) for _ in range(r_svc.randint(1, 2))]
             res = resources(r_svc.choice([0, 5, 10, 20]) * 10**8, 0, [discrete(r_svc.choice(["apple", "gpu"]), 1)] if r_svc.random() < 0.4 else [])
-            pl = placement(constraints=r_svc.choice([[], [], ["node.labels.az != c"], ["node.labels.rack == r1"]]), max_replicas=r_svc.choice([0, 0, 1, 2]))
+            pl = placement(constraints=r_svc.choice([[], [], ["node.labels.az != c"], ["node.labels.rack == r1"]]), max_replicas=r_svc.choice([0, 0, 1, 2]),
+                           preferences=r_svc.choice([[], [], ["node.labels.az"], ["node.labels.az", "node.labels.rack"]]))
             ports = [host_port(r_svc.choice([80, 443]))] if r_svc.random() < 0.3 else None
             for _ in range(r2.randint(2, 7)):
                 new.append(task(f"t{next_id:04d}", service_id=f"svc{j}", spec_version=1, reservations=res, mounts=mounts, placement=pl, ports=ports))
