@@ -103,3 +103,26 @@ def test_service_ids_are_recycled_under_churn():
                 c.update_task(dict(t, status=dict(t["status"], state="SHUTDOWN")))
                 c.delete_task(t["id"])
     assert high <= 16, high          # 120 services came and went; at most a handful of ids were ever alive together
+
+
+@pytest.mark.parametrize("network_constraints", [False, True])
+def test_reference_benchmark_shape(network_constraints):
+    """benchScheduler's store contents (scheduler_test.go:3378-3468) at 300 nodes x 600 tasks: nodes with an engine but no
+    resource description, every third one with a `network` Network plugin; one-off tasks without a service, with a network
+    attachment on that driver in the *Constraints* variants.  Shim and object oracle agree; every task is assigned; the
+    spread is level over the eligible nodes."""
+    from collections import Counter
+    from tests.sched_harness import description, engine, node, task
+    nodes = [node(f"n{i:04d}", description=description(engine=engine(plugins=[("Network", "network")] if i % 3 == 0 else []))) for i in range(300)]
+    tasks = [task(f"task{i:04d}", networks=["network"] if network_constraints else ()) for i in range(600)]
+    out = []
+    for mk in (make_shim, make_oracle):
+        c = Cluster(mk(), nodes=nodes)
+        for t in tasks:
+            c.create_task(t)
+        out.append(c.run())
+    assert out[0] == out[1]
+    per_node = Counter(d["node_id"] for d in out[0].values())
+    assert all(d["state"] == "ASSIGNED" for d in out[0].values())
+    eligible = [n["id"] for i, n in enumerate(nodes) if i % 3 == 0] if network_constraints else [n["id"] for n in nodes]
+    assert set(per_node) <= set(eligible) and len(per_node) == len(eligible) and max(per_node.values()) - min(per_node.values()) <= 1
