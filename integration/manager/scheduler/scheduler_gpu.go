@@ -1115,6 +1115,9 @@ func (s *Scheduler) scheduleVolumeGroup(ctx context.Context, group map[string]*a
 		}
 		s.gpu.nodeSetChanged()
 	}
+	// (the C++ shim also keeps this answer between groups that ask the same question -- same mounts, no volume, counted use
+	// or node changed since: VolumeBook::epoch / node_epoch in scheduler_host.cpp; here that needs a change counter in
+	// volumeSet.reserveVolume / releaseVolume / addOrUpdateVolume, three one-line additions to volumes.go)
 	f := &VolumesFilter{vs: s.volumes}
 	f.SetTask(t)
 	var allowed, excluded []string

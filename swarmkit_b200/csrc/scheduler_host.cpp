@@ -432,8 +432,12 @@ struct VolumeBook {
     std::map<std::string, Entry> vols;
     std::map<std::string, std::set<std::string>> by_group;     // a group's volumes in ascending ID (canonical order)
     std::map<std::string, std::string> by_name;
+    uint64_t epoch = 0;      // moves whenever an answer of check() may have: the shim keeps VolumesFilter's last node set by it
 
+    // does a use of this volume (by a reader / a writer) change what check() says about it for anyone else?
+    static bool counts_users(const Volume &v, bool ro) { return v.scope == VolScopeSingle || v.sharing == VolShareNone || (v.sharing == VolShareOneWriter && !ro); }
     void addOrUpdate(const Volume &v) {                         // volumes.go:61-81 (an update keeps the stored spec: :69-70)
+        epoch++;
         if (!vols.count(v.id)) { Entry e; e.v = v; vols[v.id] = e; }
         by_group[v.group].insert(v.id);
         by_name[v.name] = v.id;
@@ -441,6 +445,7 @@ struct VolumeBook {
     void remove(const std::string &id) {                        // :83-96
         auto it = vols.find(id);
         if (it == vols.end()) return;
+        epoch++;
         by_group[it->second.v.group].erase(id);
         by_name.erase(it->second.v.name);
         vols.erase(it);
@@ -448,6 +453,7 @@ struct VolumeBook {
     void reserve(const std::string &vid, const std::string &task, const std::string &node, bool ro) {   // :150-160
         auto it = vols.find(vid);
         if (it == vols.end()) return;
+        if (counts_users(it->second.v, ro)) epoch++;
         it->second.tasks[task] = Use{node, ro};
         it->second.nodes[node]++;
     }
@@ -456,6 +462,7 @@ struct VolumeBook {
         if (it == vols.end()) return;
         auto u = it->second.tasks.find(task);
         if (u == it->second.tasks.end()) return;
+        if (counts_users(it->second.v, u->second.read_only)) epoch++;
         int &c = it->second.nodes[u->second.node];
         if (c > 0) c--;
         it->second.tasks.erase(u);
@@ -549,6 +556,11 @@ struct Scheduler {
     uint32_t vol_col = PE_NONE;          // attribute column that names the node set of a group with cluster mounts
     static const uint32_t vol_gen = 1;   // the column's value on the rows of the set (0 = "" on every other row)
     std::set<std::string> vol_in;        // the nodes that carry it, written into the row by encode_row
+    // VolumesFilter's answer for the mounts asked about last: the tasks of one service, or a tick's one-off tasks of one
+    // spec, ask the same question again and again; it stands until a volume, a counted use or a node changes
+    struct VolAnswer { bool valid = false; std::string mounts; uint64_t vol_epoch = 0, node_epoch = 0, id = 0; std::vector<std::string> allowed, excluded; } vol_answer;
+    uint64_t node_epoch = 0;             // moves with every node event
+    uint64_t vol_in_answer = 0;          // the answer vol_in holds in full (0 = none: a stepwise walk took nodes out)
     bool leaf_also_in_volume_set = false; // a preference group with cluster mounts: every leaf visit carries the volume term too
     bool leaf_stepwise = false;           // ... and, when its volumes count their users, walks the fill loop itself (fillLeafStepwise)
     int64_t now = 0;
@@ -826,10 +838,11 @@ struct Scheduler {
                     gr::consume(res.generic, kv.second->assigned);
                 }
         }
+        node_epoch++;
         if (it == nodeSet.end()) { NodeInfo ni; ni.node = n; ni.avail = res; ni.last_cleanup = now; nodeSet[n->id] = ni; layout_dirty = true; }
         else { it->second.node = n; it->second.avail = res; touch(n->id); }
     }
-    void removeNode(const std::string &id) { if (nodeSet.erase(id)) layout_dirty = true; vol_in.erase(id); }   // nodeset.go:46-48
+    void removeNode(const std::string &id) { node_epoch++; if (nodeSet.erase(id)) layout_dirty = true; vol_in.erase(id); }   // nodeset.go:46-48
 
     // ---- group descriptors <- the filters' SetTask (filter.go) --------------------
     struct TickBuf {
@@ -1227,6 +1240,7 @@ struct Scheduler {
             if (pn == PE_NONE || pn >= idx_to_id.size()) { if (i == 0 && first_fail) *first_fail = pf; break; }
             cand.push_back(idx_to_id[pn]);
             vol_in.erase(idx_to_id[pn]);
+            vol_in_answer = 0;
             touch(idx_to_id[pn]);
         }
         return 1;
@@ -1343,9 +1357,16 @@ struct Scheduler {
         };
         const bool prefs = !preference_levels(t).empty();
         auto give_back = [&](const std::vector<TaskP> &ts) { for (auto &x : ts) enqueue(x); layout_dirty = true; };
-        std::vector<std::string> allowed, excluded;
-        for (auto &kv : nodeSet) (volumes.filterCheck(t, *kv.second.node) ? allowed : excluded).push_back(kv.first);
-        mark_volume_nodes(allowed);
+        std::string mounts;
+        for (auto &m : t.mounts) if (m.type == MountCluster) { mounts += m.source; mounts += m.read_only ? "\x01" : "\x02"; }
+        if (!(vol_answer.valid && vol_answer.mounts == mounts && vol_answer.vol_epoch == volumes.epoch && vol_answer.node_epoch == node_epoch)) {
+            vol_answer.allowed.clear(); vol_answer.excluded.clear();
+            for (auto &kv : nodeSet) (volumes.filterCheck(t, *kv.second.node) ? vol_answer.allowed : vol_answer.excluded).push_back(kv.first);
+            vol_answer.valid = true; vol_answer.mounts = mounts; vol_answer.vol_epoch = volumes.epoch; vol_answer.node_epoch = node_epoch;
+            vol_answer.id++;
+        }
+        const std::vector<std::string> &allowed = vol_answer.allowed, &excluded = vol_answer.excluded;   // (stand until the next question)
+        if (vol_in_answer != vol_answer.id || vol_col == PE_NONE) { mark_volume_nodes(allowed); vol_in_answer = vol_answer.id; }
         if (prefs) {
             // the tree's branches and task sums do not depend on the pipeline (nodeset.go:59-101 counts every node); each
             // leaf visit is the leaf's engine group cut down to the volume set as well when the answer of VolumesFilter
